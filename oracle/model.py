@@ -438,6 +438,7 @@ def ocean_step(oc, g, p, dt, u_atm, v_atm, Q_net=None, ice_mask=None):
         Ts_adv = ops.advect_semilag(oc.Ts, oc.uo, oc.vo, sub, a, dlat, dlon, cosr)
         oc.Ts = (1.0 - p.oc_adv_alpha) * oc.Ts + p.oc_adv_alpha * Ts_adv
         if p.oc_K_h > 0.0:
+            oc.Ts = ops.nan_to_num(oc.Ts)       # ocean.py:112 cleans the caller's array (copy=False)
             oc.Ts = oc.Ts + sub * p.oc_K_h * ops.laplacian(oc.Ts, dlat, dlon, cosr, a)
         if p.oc_use_qnet and (Q_net is not None):
             tend = Q_net / (p.oc_rho_w * p.oc_cp_w * p.oc_H)

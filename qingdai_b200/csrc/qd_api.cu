@@ -1,0 +1,783 @@
+// qd_api.cu -- context, C ABI and step orchestration of libqd_b200 (see include/qd_b200.h).
+//
+// The step is a fixed sequence of phase kernels on one CUDA stream; everything data dependent
+// (medians, renormalisation sums, the weak-humidity fallback, the ocean's CFL sub-step count)
+// stays on the device in the per-member scalar table and is consumed by later kernels.
+#include "qd_loop.cuh"
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include <algorithm>
+
+#ifdef QD_HOST_EMU
+thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+void qd_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+  gridDim = grid; blockDim = block;
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      blockIdx = dim3(bx, by, 0);
+      for (unsigned ty = 0; ty < block.y; ++ty)
+        for (unsigned tx = 0; tx < block.x; ++tx) { threadIdx = dim3(tx, ty, 0); body(); }
+    }
+}
+#endif
+
+#define QD_NUSER_ROWS 4
+#define QD_NPART 4
+
+struct qd_route {
+  int ready = 0, n_levels = 0, n_lakes = 0;
+  long long n_order = 0;
+  std::vector<int> level_off;                       // host: [n_levels+1]
+  int *d_level_cells = nullptr;                     // cells sorted by level
+  int *d_don_off = nullptr, *d_don = nullptr;       // early donors CSR per cell (sorted by order position)
+  int *d_late_off = nullptr, *d_late = nullptr;     // late donors CSR
+  int *d_ocean_list = nullptr; long long n_ocean = 0;     // ocean-draining cells in flow_order order
+  int *d_lake_list = nullptr, *d_lake_of = nullptr; long long n_lake_store = 0;
+  unsigned char* d_in_order = nullptr;
+  double *d_buffer = nullptr, *d_mass = nullptr, *d_after = nullptr, *d_out = nullptr;
+};
+
+struct qd_ctx {
+  int nlat, nlon, ncell, batch, device, nblk;
+  cudaStream_t stream;
+  QdGeo geo;
+  double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
+  double* fields; uint8_t* masks;
+  double* d_part[QD_NPART]; unsigned* d_ticket;
+  unsigned* d_hist; QdSelState* d_sel;
+  qd_forcing_t* d_forcing; int forcing_cap; int* d_step_idx; double* d_hcos;
+  double *d_twid, *d_spec_coef, *d_spec_out;
+  double* d_stage[5];
+  long long launches;
+  int atm_counter, oc_counter, has_cloud_eff;
+  int last_nsub_max;
+  QdGaussW w_sigma1, w_cloud; int w_set;
+  char err[512];
+  qd_route route;
+  void* prof;
+};
+
+#ifndef QD_HOST_EMU
+#include <map>
+#include <string>
+struct qd_prof_rec { const char* name; cudaEvent_t a, b; };
+struct qd_prof {
+  int on = 0;
+  std::vector<qd_prof_rec> pending;
+  std::map<std::string, std::pair<long long, double>> acc;   // name -> (count, ms)
+};
+static qd_prof* qd_prof_of(qd_ctx* c);
+static int qd_prof_begin(qd_ctx* c, const char* name) {
+  qd_prof* p = qd_prof_of(c);
+  if (!p || !p->on) return -1;
+  qd_prof_rec r; r.name = name;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, c->stream);
+  p->pending.push_back(r);
+  return (int)p->pending.size() - 1;
+}
+static void qd_prof_end(qd_ctx* c, int idx) {
+  if (idx < 0) return;
+  qd_prof* p = qd_prof_of(c);
+  cudaEventRecord(p->pending[idx].b, c->stream);
+}
+static void qd_prof_harvest(qd_ctx* c) {
+  qd_prof* p = qd_prof_of(c);
+  if (!p) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& r : p->pending) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto& e = p->acc[r.name];
+    e.first += 1; e.second += ms;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  p->pending.clear();
+}
+#else
+static inline int qd_prof_begin(qd_ctx*, const char*) { return -1; }
+static inline void qd_prof_end(qd_ctx*, int) {}
+#endif
+
+static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
+  if (c) snprintf(c->err, sizeof(c->err), "%s: %s", what, e != cudaSuccess ? cudaGetErrorString(e) : "invalid argument");
+  return code;
+}
+#define QD_CUDA(c, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return qd_fail((c), QD_E_CUDA, #call, e_); } while (0)
+#define QD_CHECK_LAUNCH(c) do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return qd_fail((c), QD_E_CUDA, "kernel launch", e_); } while (0)
+#define QD_REQUIRE(c, cond) do { if (!(cond)) return qd_fail((c), QD_E_INVALID, #cond, cudaSuccess); } while (0)
+#define QD_BOUND(c) do { if (!(c)->fields || !(c)->masks) return qd_fail((c), QD_E_UNBOUND, "qd_bind was not called", cudaSuccess); } while (0)
+
+// Every launch goes through QD_KG so that launches are counted and, in profiling mode, bracketed by
+// CUDA events on the launching stream (per-kernel device time for bench.py's roofline object).
+#define QD_KG(c, kern, grid, block, ...) do { \
+    const int pi_ = qd_prof_begin((c), #kern); \
+    QD_LAUNCH(kern, (grid), (block), (c)->stream, __VA_ARGS__); \
+    qd_prof_end((c), pi_); (c)->launches++; } while (0)
+#define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+
+#ifndef QD_HOST_EMU
+static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
+#endif
+extern "C" int qd_profile(qd_ctx* c, int enable) {
+  if (!c) return QD_E_INVALID;
+#ifndef QD_HOST_EMU
+  if (!c->prof) c->prof = new qd_prof();
+  qd_prof* p = qd_prof_of(c);
+  qd_prof_harvest(c);
+  if (enable && !p->on) p->acc.clear();
+  p->on = enable ? 1 : 0;
+#else
+  (void)enable;
+#endif
+  return QD_OK;
+}
+// "name count total_ms\n" per kernel, largest total first; returns the number of bytes written
+extern "C" int qd_profile_report(qd_ctx* c, char* buf, int buflen) {
+  if (!c || !buf || buflen < 1) return QD_E_INVALID;
+  buf[0] = 0;
+#ifndef QD_HOST_EMU
+  qd_prof* p = qd_prof_of(c);
+  if (!p) return 0;
+  qd_prof_harvest(c);
+  std::vector<std::pair<double, std::string>> order;
+  for (auto& kv : p->acc) order.push_back({-kv.second.second, kv.first});
+  std::sort(order.begin(), order.end());
+  int n = 0;
+  for (auto& o : order) {
+    auto& e = p->acc[o.second];
+    int w = snprintf(buf + n, buflen - n, "%s %lld %.6f\n", o.second.c_str(), e.first, e.second);
+    if (w < 0 || w >= buflen - n) break;
+    n += w;
+  }
+  return n;
+#else
+  return 0;
+#endif
+}
+
+static inline double* F(qd_ctx* c, int id) { return c->fields + (size_t)id * c->batch * c->ncell; }
+static inline uint8_t* M(qd_ctx* c, int id) { return c->masks + (size_t)id * c->batch * c->ncell; }
+static inline const double* ROW(qd_ctx* c, int id) { return c->d_rows + (size_t)id * c->nlat; }
+
+// ------------------------------------------------------------------------------ lifecycle
+extern "C" int qd_version(void) { return 100; }
+extern "C" const char* qd_last_error(const qd_ctx* c) { return c ? c->err : "null context"; }
+
+extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, double dlat, double dlon,
+                         double a_sq, double dlon_sq, const double* rows_host, const double* cols_host,
+                         const double* params_host, qd_ctx** out) {
+  if (!out || nlat < 3 || nlon < 3 || batch < 1 || !rows_host || !cols_host || !params_host) return QD_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return QD_E_NODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return QD_E_NODEVICE;
+  qd_ctx* c = new qd_ctx();
+  memset(c->err, 0, sizeof(c->err));
+  c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
+  c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
+  c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
+  c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
+  c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr;
+  const size_t nrows = (size_t)(QD_R_COUNT + QD_NUSER_ROWS) * nlat;
+#define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
+  QD_ALLOC(c->d_rows, nrows * 8);
+  QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
+  QD_ALLOC(c->d_prm, (size_t)batch * QD_P_COUNT * 8);
+  QD_ALLOC(c->d_scal, (size_t)batch * QD_S_COUNT * 8);
+  for (int k = 0; k < QD_NPART; ++k) QD_ALLOC(c->d_part[k], (size_t)batch * c->nblk * 8);
+  QD_ALLOC(c->d_ticket, (size_t)batch * 8 * sizeof(unsigned));
+  QD_ALLOC(c->d_hist, (size_t)batch * QD_SEL_BINS * sizeof(unsigned));
+  QD_ALLOC(c->d_sel, (size_t)batch * sizeof(QdSelState));
+  QD_ALLOC(c->d_step_idx, sizeof(int));
+  QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
+  QD_ALLOC(c->d_twid, (size_t)2 * nlon * 8);
+  QD_ALLOC(c->d_spec_coef, (size_t)batch * nlat * 2 * (nlon / 2 + 1) * 8);
+  QD_ALLOC(c->d_spec_out, (size_t)batch * c->ncell * 8);
+  for (int k = 0; k < 5; ++k) QD_ALLOC(c->d_stage[k], (size_t)c->ncell * 8);
+#undef QD_ALLOC
+  c->h_prm = (double*)malloc((size_t)batch * QD_P_COUNT * 8);
+  memcpy(c->h_prm, params_host, (size_t)batch * QD_P_COUNT * 8);
+  cudaMemcpy(c->d_rows, rows_host, (size_t)QD_R_COUNT * nlat * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_cols, cols_host, (size_t)QD_C_COUNT * nlon * 8, cudaMemcpyHostToDevice);
+  cudaMemcpy(c->d_prm, params_host, (size_t)batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice);
+  {
+    std::vector<double> tw(2 * (size_t)nlon);
+    for (int m = 0; m < nlon; ++m) {
+      const double ang = 2.0 * 3.14159265358979323846 * (double)m / (double)nlon;
+      tw[m] = cos(ang); tw[nlon + m] = sin(ang);
+    }
+    cudaMemcpy(c->d_twid, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice);
+  }
+  QdGeo& g = c->geo;
+  g.nlat = nlat; g.nlon = nlon; g.ncell = c->ncell; g.batch = batch;
+  g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
+  g.rows = c->d_rows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
+  if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
+  *out = c;
+  return QD_OK;
+}
+
+static void qd_route_free(qd_route& r) {
+  cudaFree(r.d_level_cells); cudaFree(r.d_don_off); cudaFree(r.d_don); cudaFree(r.d_late_off); cudaFree(r.d_late);
+  cudaFree(r.d_ocean_list); cudaFree(r.d_lake_list); cudaFree(r.d_lake_of); cudaFree(r.d_in_order);
+  cudaFree(r.d_buffer); cudaFree(r.d_mass); cudaFree(r.d_after); cudaFree(r.d_out);
+  r = qd_route();
+}
+
+extern "C" int qd_destroy(qd_ctx* c) {
+  if (!c) return QD_E_INVALID;
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal);
+  for (int k = 0; k < QD_NPART; ++k) cudaFree(c->d_part[k]);
+  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_sel); cudaFree(c->d_step_idx); cudaFree(c->d_hcos);
+  cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
+  for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
+  qd_route_free(c->route);
+  free(c->h_prm);
+#ifndef QD_HOST_EMU
+  if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
+#endif
+  delete c;
+  return QD_OK;
+}
+
+extern "C" int qd_set_stream(qd_ctx* c, void* s) { if (!c) return QD_E_INVALID; c->stream = (cudaStream_t)s; return QD_OK; }
+extern "C" int qd_synchronize(qd_ctx* c) { if (!c) return QD_E_INVALID; QD_CUDA(c, cudaStreamSynchronize(c->stream)); return QD_OK; }
+extern "C" int qd_bind(qd_ctx* c, double* fields, uint8_t* masks) {
+  if (!c || !fields || !masks) return QD_E_INVALID;
+  c->fields = fields; c->masks = masks;
+  return QD_OK;
+}
+extern "C" int qd_set_params(qd_ctx* c, const double* p) {
+  if (!c || !p) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(c->h_prm, p, (size_t)c->batch * QD_P_COUNT * 8);
+  QD_CUDA(c, cudaMemcpy(c->d_prm, p, (size_t)c->batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice));
+  return QD_OK;
+}
+extern "C" int qd_set_rows(qd_ctx* c, const double* rows) {
+  if (!c || !rows) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QD_CUDA(c, cudaMemcpy(c->d_rows, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
+  return QD_OK;
+}
+extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
+  if (!c || !out) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QD_CUDA(c, cudaMemcpy(out, c->d_scal, (size_t)c->batch * QD_S_COUNT * 8, cudaMemcpyDeviceToHost));
+  return QD_OK;
+}
+extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
+extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_host) {
+  if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host) return nullptr;
+  cudaStreamSynchronize(c->stream);
+  double* dst = c->d_rows + (size_t)(QD_R_COUNT + slot) * c->nlat;
+  if (cudaMemcpy(dst, rows_host, (size_t)c->nlat * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return dst;
+}
+extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
+extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
+extern "C" int qd_get_counters(qd_ctx* c, int* a, int* o, int* ce) {
+  if (!c) return QD_E_INVALID;
+  if (a) *a = c->atm_counter; if (o) *o = c->oc_counter; if (ce) *ce = c->has_cloud_eff;
+  return QD_OK;
+}
+
+static int qd_xfer(qd_ctx* c, void* dev_base, size_t elem, int member, void* host, bool up) {
+  QD_BOUND(c);
+  QD_REQUIRE(c, member >= -1 && member < c->batch && host);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t one = (size_t)c->ncell * elem;
+  char* d = (char*)dev_base + (member < 0 ? 0 : (size_t)member * one);
+  const size_t n = member < 0 ? one * c->batch : one;
+  if (up) QD_CUDA(c, cudaMemcpy(d, host, n, cudaMemcpyHostToDevice));
+  else QD_CUDA(c, cudaMemcpy(host, d, n, cudaMemcpyDeviceToHost));
+  return QD_OK;
+}
+extern "C" int qd_upload_field(qd_ctx* c, int f, int m, const double* h) { if (!c || f < 0 || f >= QD_F_COUNT) return QD_E_INVALID; return qd_xfer(c, F(c, f), 8, m, (void*)h, true); }
+extern "C" int qd_download_field(qd_ctx* c, int f, int m, double* h) { if (!c || f < 0 || f >= QD_F_COUNT) return QD_E_INVALID; return qd_xfer(c, F(c, f), 8, m, h, false); }
+extern "C" int qd_upload_mask(qd_ctx* c, int f, int m, const uint8_t* h) { if (!c || f < 0 || f >= QD_M_COUNT) return QD_E_INVALID; return qd_xfer(c, M(c, f), 1, m, (void*)h, true); }
+extern "C" int qd_download_mask(qd_ctx* c, int f, int m, uint8_t* h) { if (!c || f < 0 || f >= QD_M_COUNT) return QD_E_INVALID; return qd_xfer(c, M(c, f), 1, m, h, false); }
+
+// ------------------------------------------------------------------------------ operator building blocks
+static QdFields mk_fields(int n) { QdFields f; memset(&f, 0, sizeof(f)); f.n = n; for (int k = 0; k < QD_MAX_FIELDS; ++k) f.scale[k] = 1.0; return f; }
+
+static int op_laplacian(qd_ctx* c, int n, const double* const* src, double* const* dst, const double* cosr) {
+  QdFields f = mk_fields(n);
+  for (int k = 0; k < n; ++k) { f.src[k] = src[k]; f.dst[k] = dst[k]; }
+  QD_K(c, k_laplacian, c->geo, f, cosr);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+// n fields in place: F <- F - k4*lap(lap F)*sub, repeated nsub times (dynamics.py:205-212)
+static int op_hyper(qd_ctx* c, int n, double* const* fld, double* const* scratch, const double* const* k4rows,
+                    const double* scale, double dt, int nsub, const double* cosr) {
+  if (dt <= 0.0 || n <= 0) return QD_OK;
+  const int ns = nsub > 1 ? nsub : 1;
+  const double sub = dt / ns;
+  for (int s = 0; s < ns; ++s) {
+    QdFields f = mk_fields(n);
+    for (int k = 0; k < n; ++k) { f.src[k] = fld[k]; f.dst[k] = scratch[k]; }
+    QD_K(c, k_laplacian, c->geo, f, cosr);
+    QdFields u = mk_fields(n);
+    for (int k = 0; k < n; ++k) { u.src[k] = scratch[k]; u.dst[k] = fld[k]; u.aux[k] = k4rows[k]; u.scale[k] = scale ? scale[k] : 1.0; }
+    QD_K(c, k_hyper_update, c->geo, u, cosr, sub, 0.0);
+  }
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+static int op_shapiro(qd_ctx* c, int n, double* const* fld, double* const* scratch, int passes) {
+  const int np = passes > 1 ? passes : 1;
+  for (int p = 0; p < np; ++p) {
+    QdFields a = mk_fields(n), b2 = mk_fields(n);
+    for (int k = 0; k < n; ++k) { a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k]; }
+    QD_K(c, k_shapiro_lon, c->geo, a, p == 0 ? 1 : 0);
+    QD_K(c, k_shapiro_lat, c->geo, b2);
+  }
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+// Gaussian weight tables supplied by the host (NumPy-evaluated, bit-identical to scipy's).
+static QdGaussW mk_gauss_w(int radius, int wrap, const double* weights) {
+  QdGaussW w; memset(&w, 0, sizeof(w));
+  w.r = radius; w.wrap = wrap;
+  for (int k = 0; k <= 2 * radius; ++k) w.w[k] = weights[k];
+  return w;
+}
+extern "C" int qd_set_gauss(qd_ctx* c, int which, int radius, int wrap, const double* weights) {
+  if (!c || radius < 0 || radius > QD_GAUSS_MAXR || !weights) return QD_E_INVALID;
+  if (which == 0) c->w_sigma1 = mk_gauss_w(radius, wrap, weights); else c->w_cloud = mk_gauss_w(radius, wrap, weights);
+  c->w_set |= (1 << (which ? 1 : 0));
+  return QD_OK;
+}
+static int op_gauss(qd_ctx* c, int n, double* const* fld, double* const* scratch, const QdGaussW& w) {
+  if (w.r == 0) return QD_OK;
+  QdFields a = mk_fields(n), b2 = mk_fields(n);
+  for (int k = 0; k < n; ++k) { a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k]; }
+  QD_K(c, k_gauss_lat, c->geo, a, w);
+  QD_K(c, k_gauss_lon, c->geo, b2, w);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
+  if (damp <= 0.0 || cutoff <= 0.0) return QD_OK;      // reference only cleans NaNs here; fields are finite
+  const int bins = c->nlon / 2 + 1;
+  if (bins <= 1) return QD_OK;
+  const int kN = bins - 1;
+  int kcut = (int)(cutoff * kN);
+  kcut = std::max(1, std::min(kN, kcut));
+  const double fac = std::max(0.0, 1.0 - std::min(1.0, damp));
+  QD_KG(c, k_zonal_bandstop, dim3(c->nlat, c->batch), dim3(QD_THREADS), c->geo, fld, c->d_twid, kcut, 1.0 - fac,
+        c->d_spec_coef, c->d_spec_out);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+// exact median of positives of x -> dst[b*stride] (and count -> cnt[b*stride])
+static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst, double* cnt, int stride) {
+  for (int pass = 0; pass < 4; ++pass) QD_K(c, k_select_hist, c->geo, x, pass, c->d_hist, c->d_sel, c->d_ticket + 0 * c->batch);
+  QD_K(c, k_select_close, c->geo, x, c->d_sel, c->d_ticket + 1 * c->batch, empty_value, dst, cnt, stride);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
+// ------------------------------------------------------------------------------ operator C ABI
+extern "C" int qd_laplacian(qd_ctx* c, const double* in, double* out, const double* cosr) {
+  if (!c || !in || !out || !cosr) return QD_E_INVALID;
+  const double* s[1] = {in}; double* d[1] = {out};
+  return op_laplacian(c, 1, s, d, cosr);
+}
+extern "C" int qd_hyperdiffuse(qd_ctx* c, double* f, double* scratch, const double* k4rows, double k4_scale, double dt, int nsub, const double* cosr) {
+  if (!c || !f || !scratch || !k4rows || !cosr) return QD_E_INVALID;
+  double* fl[1] = {f}; double* sc[1] = {scratch}; const double* kr[1] = {k4rows}; double s[1] = {k4_scale};
+  return op_hyper(c, 1, fl, sc, kr, s, dt, nsub, cosr);
+}
+extern "C" int qd_advect(qd_ctx* c, const double* in, const double* u, const double* v, double* out, double dt, const double* cosr) {
+  if (!c || !in || !u || !v || !out || !cosr) return QD_E_INVALID;
+  QdFields f = mk_fields(1); f.src[0] = in; f.dst[0] = out;
+  QD_K(c, k_advect, c->geo, f, u, v, dt, cosr);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+extern "C" int qd_shapiro(qd_ctx* c, double* f, double* scratch, int n) {
+  if (!c || !f || !scratch) return QD_E_INVALID;
+  double* fl[1] = {f}; double* sc[1] = {scratch};
+  return op_shapiro(c, 1, fl, sc, n);
+}
+extern "C" int qd_gaussian(qd_ctx* c, double* f, double* scratch, int radius, int wrap, const double* weights) {
+  if (!c || !f || !scratch || !weights || radius < 0 || radius > QD_GAUSS_MAXR) return QD_E_INVALID;
+  const QdGaussW w = mk_gauss_w(radius, wrap, weights);
+  double* fl[1] = {f}; double* sc[1] = {scratch};
+  return op_gauss(c, 1, fl, sc, w);
+}
+extern "C" int qd_zonal_bandstop(qd_ctx* c, double* f, double cutoff, double damp) {
+  if (!c || !f) return QD_E_INVALID;
+  return op_bandstop(c, f, cutoff, damp);
+}
+extern "C" int qd_divergence(qd_ctx* c, const double* u, const double* v, double* out) {
+  if (!c || !u || !v || !out) return QD_E_INVALID;
+  QD_K(c, k_divvort, c->geo, u, v, out, 0);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+extern "C" int qd_vorticity(qd_ctx* c, const double* u, const double* v, double* out) {
+  if (!c || !u || !v || !out) return QD_E_INVALID;
+  QD_K(c, k_divvort, c->geo, u, v, out, 1);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+extern "C" int qd_median_pos(qd_ctx* c, const double* in, double empty_value, double* out_host) {
+  if (!c || !in || !out_host) return QD_E_INVALID;
+  int rc = op_median(c, in, empty_value, c->d_scal + QD_S_TMP0, c->d_scal + QD_S_TMP1, QD_S_COUNT);
+  if (rc) return rc;
+  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+  rc = qd_get_scalars(c, s.data());
+  if (rc) return rc;
+  for (int b = 0; b < c->batch; ++b) out_host[b] = s[(size_t)b * QD_S_COUNT + QD_S_TMP0];
+  return QD_OK;
+}
+extern "C" int qd_wsum(qd_ctx* c, const double* in, double* out_host) {
+  if (!c || !in || !out_host) return QD_E_INVALID;
+  QD_K(c, k_wsum, c->geo, in, ROW(c, QD_R_W), c->d_part[0], c->d_ticket + 2 * c->batch, c->d_scal + QD_S_TMP2, QD_S_COUNT);
+  QD_CHECK_LAUNCH(c);
+  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+  int rc = qd_get_scalars(c, s.data());
+  if (rc) return rc;
+  for (int b = 0; b < c->batch; ++b) out_host[b] = s[(size_t)b * QD_S_COUNT + QD_S_TMP2];
+  return QD_OK;
+}
+extern "C" int qd_minmax(qd_ctx* c, const double* in, double* out_host) {
+  if (!c || !in || !out_host) return QD_E_INVALID;
+  // diagnostics only (every ~100-200 steps in the reference): staged through the host
+  std::vector<double> h((size_t)c->ncell);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < c->batch; ++b) {
+    QD_CUDA(c, cudaMemcpy(h.data(), in + (size_t)b * c->ncell, (size_t)c->ncell * 8, cudaMemcpyDeviceToHost));
+    double lo = h[0], hi = h[0];
+    for (int k = 1; k < c->ncell; ++k) { if (h[k] < lo) lo = h[k]; if (h[k] > hi) hi = h[k]; }
+    out_host[2 * b] = lo; out_host[2 * b + 1] = hi;
+  }
+  return QD_OK;
+}
+
+// host-buffer forms of the jax_compat seam (single member, staged through private device buffers)
+static int stage_up(qd_ctx* c, int k, const double* h) { QD_CUDA(c, cudaMemcpyAsync(c->d_stage[k], h, (size_t)c->ncell * 8, cudaMemcpyHostToDevice, c->stream)); return QD_OK; }
+static int stage_down(qd_ctx* c, int k, double* h) {
+  QD_CUDA(c, cudaMemcpyAsync(h, c->d_stage[k], (size_t)c->ncell * 8, cudaMemcpyDeviceToHost, c->stream));
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  return QD_OK;
+}
+struct BatchOne { qd_ctx* c; int saved; BatchOne(qd_ctx* c_) : c(c_), saved(c_->batch) { c->batch = 1; c->geo.batch = 1; } ~BatchOne() { c->batch = saved; c->geo.batch = saved; } };
+
+extern "C" int qd_laplacian_host(qd_ctx* c, const double* in, double* out, const double* cos_rows) {
+  if (!c || !in || !out || !cos_rows) return QD_E_INVALID;
+  const double* cr = qd_user_row(c, 0, cos_rows);
+  if (!cr) return qd_fail(c, QD_E_CUDA, "qd_user_row", cudaSuccess);
+  BatchOne one(c);
+  int rc = stage_up(c, 0, in); if (rc) return rc;
+  rc = qd_laplacian(c, c->d_stage[0], c->d_stage[1], cr); if (rc) return rc;
+  return stage_down(c, 1, out);
+}
+extern "C" int qd_hyperdiffuse_host(qd_ctx* c, const double* in, double* out, const double* k4_map, double k4_scalar,
+                                    double dt, int nsub, const double* cos_rows) {
+  if (!c || !in || !out || !cos_rows) return QD_E_INVALID;
+  // k4 maps in the reference are functions of latitude only (dynamics.py:557-563, ocean.py:343-347):
+  // the first column is the row table.  A scalar k4 becomes a constant row.
+  std::vector<double> k4r((size_t)c->nlat);
+  bool allneg = true;
+  for (int j = 0; j < c->nlat; ++j) {
+    double v = k4_map ? k4_map[(size_t)j * c->nlon] : k4_scalar;
+    if (v != v) v = 0.0;
+    k4r[j] = v;
+    if (k4_map) { for (int i = 0; i < c->nlon; ++i) if (k4_map[(size_t)j * c->nlon + i] != v) return qd_fail(c, QD_E_INVALID, "k4 map must be constant along longitude", cudaSuccess); }
+    if (v > 0.0) allneg = false;
+  }
+  if (dt <= 0.0 || allneg) { if (out != in) memcpy(out, in, (size_t)c->ncell * 8); return QD_OK; }   // early-outs dynamics.py:190-204
+  const double* cr = qd_user_row(c, 0, cos_rows);
+  const double* kr = qd_user_row(c, 1, k4r.data());
+  if (!cr || !kr) return qd_fail(c, QD_E_CUDA, "qd_user_row", cudaSuccess);
+  BatchOne one(c);
+  int rc = stage_up(c, 0, in); if (rc) return rc;
+  rc = qd_hyperdiffuse(c, c->d_stage[0], c->d_stage[1], kr, 1.0, dt, nsub, cr); if (rc) return rc;
+  return stage_down(c, 0, out);
+}
+extern "C" int qd_advect_host(qd_ctx* c, const double* in, const double* u, const double* v, double* out, double dt, const double* cos_rows) {
+  if (!c || !in || !u || !v || !out || !cos_rows) return QD_E_INVALID;
+  const double* cr = qd_user_row(c, 0, cos_rows);
+  if (!cr) return qd_fail(c, QD_E_CUDA, "qd_user_row", cudaSuccess);
+  BatchOne one(c);
+  int rc = stage_up(c, 0, in); if (rc) return rc;
+  rc = stage_up(c, 1, u); if (rc) return rc;
+  rc = stage_up(c, 2, v); if (rc) return rc;
+  rc = qd_advect(c, c->d_stage[0], c->d_stage[1], c->d_stage[2], c->d_stage[3], dt, cr); if (rc) return rc;
+  return stage_down(c, 3, out);
+}
+
+// ------------------------------------------------------------------------------ atmosphere step
+static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
+  const double dt = cfg->dt;
+  const int has_alb = mode_loop ? cfg->loop_with_albedo : cfg->has_albedo;
+  QdColArgs A; memset(&A, 0, sizeof(A));
+  A.u = F(c, QD_F_U); A.v = F(c, QD_F_V); A.h = F(c, QD_F_H); A.ts = F(c, QD_F_TS); A.q = F(c, QD_F_Q);
+  A.cloud = F(c, QD_F_CLOUD); A.hice = F(c, QD_F_HICE); A.wland = F(c, QD_F_WLAND); A.ssnow = F(c, QD_F_SSNOW);
+  A.eday = F(c, QD_F_EDAY);
+  A.ts_pre = F(c, QD_F_X2); A.q_pre = F(c, QD_F_X3);
+  A.isr = F(c, QD_F_ISR); A.isr_a = F(c, QD_F_ISR_A); A.isr_b = F(c, QD_F_ISR_B); A.olr = F(c, QD_F_OLR);
+  A.eflux = F(c, QD_F_EFLUX); A.pcond = F(c, QD_F_PCOND); A.lh = F(c, QD_F_LH); A.lhrel = F(c, QD_F_LHREL);
+  A.albedo = F(c, QD_F_ALBEDO); A.teq = F(c, QD_F_TEQ); A.csnow = F(c, QD_F_CSNOW); A.rland = F(c, QD_F_RLAND);
+  A.alpha_eco = F(c, QD_F_ALPHA_ECO);
+  A.precip = F(c, QD_F_PRECIP); A.cloud_eff = F(c, QD_F_CLOUD_EFF); A.base_albedo = F(c, QD_F_BASE_ALBEDO);
+  A.elevation = F(c, QD_F_ELEVATION); A.fcanopy = F(c, QD_F_FCANOPY); A.hcos = c->d_hcos;
+  A.land = M(c, QD_M_LAND); A.glacier = M(c, QD_M_GLACIER);
+  A.forcing = c->d_forcing; A.step_idx = c->d_step_idx;
+  A.dt = dt; A.mode_loop = mode_loop; A.has_albedo = has_alb; A.has_cloud_eff = c->has_cloud_eff;
+  A.with_hydrology = cfg->with_hydrology; A.with_eco = cfg->with_eco; A.store_isr_ab = cfg->store_isr_ab;
+  QD_K(c, k_column, c->geo, A);
+
+  if (has_alb) {
+    bool need_median = false;
+    for (int b = 0; b < c->batch; ++b) {
+      const double* P = c->h_prm + (size_t)b * QD_P_COUNT;
+      if (P[QD_P_CLOUD_COUPLE] != 0.0 && P[QD_P_PCOND_REF] != P[QD_P_PCOND_REF]) need_median = true;
+    }
+    if (need_median) { int rc = op_median(c, F(c, QD_F_PCOND), 1e-6, c->d_scal + QD_S_PREF_ATM, c->d_scal + QD_S_CNT_PCOND, QD_S_COUNT); if (rc) return rc; }
+    QdEnergyArgs E; memset(&E, 0, sizeof(E));
+    E.h = F(c, QD_F_H); E.hice = F(c, QD_F_HICE); E.ts_pre = F(c, QD_F_X2); E.olr = F(c, QD_F_OLR); E.cloud_eff = F(c, QD_F_CLOUD_EFF);
+    E.ts = F(c, QD_F_TS); E.q_pre = F(c, QD_F_X3); E.cloud = F(c, QD_F_CLOUD); E.pcond = F(c, QD_F_PCOND); E.isr = F(c, QD_F_ISR);
+    E.albedo = F(c, QD_F_ALBEDO); E.teq = F(c, QD_F_TEQ); E.u = F(c, QD_F_U); E.v = F(c, QD_F_V); E.lh = F(c, QD_F_LH); E.lhrel = F(c, QD_F_LHREL);
+    E.cs_map = F(c, QD_F_CS_MAP); E.land = M(c, QD_M_LAND); E.dt = dt;
+    QD_K(c, k_energy, c->geo, E);
+    c->has_cloud_eff = 1;
+  }
+  c->atm_counter += 1;                       // dynamics.py:451, before the cadence tests
+  const int sc = c->atm_counter;
+
+  QdAdvMomArgs AM; memset(&AM, 0, sizeof(AM));
+  AM.ts_pre = F(c, QD_F_X2); AM.q_pre = F(c, QD_F_X3); AM.h = F(c, QD_F_H); AM.friction = F(c, QD_F_FRICTION);
+  AM.ts = F(c, QD_F_TS); AM.q = F(c, QD_F_Q); AM.u = F(c, QD_F_U); AM.v = F(c, QD_F_V); AM.dt = dt;
+  QD_K(c, k_advect_momentum, c->geo, AM);
+
+  const double* cos_lap = ROW(c, QD_R_COS_LAP_ATM);
+  if (cfg->diff_enable && (sc % std::max(1, cfg->diff_every) == 0)) {
+    double* uvh[3] = {F(c, QD_F_U), F(c, QD_F_V), F(c, QD_F_H)};
+    double* sx[5] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6), F(c, QD_F_X7), F(c, QD_F_X8)};
+    const double* kr[5] = {ROW(c, QD_R_K4_U), ROW(c, QD_R_K4_V), ROW(c, QD_R_K4_H), ROW(c, QD_R_K4_Q), ROW(c, QD_R_K4_C)};
+    if (cfg->k4_nsub <= 1) {
+      double* fl[5] = {uvh[0], uvh[1], uvh[2], nullptr, nullptr};
+      const double* kk[5] = {kr[0], kr[1], kr[2], nullptr, nullptr};
+      int n = 3;
+      if (cfg->apply_q) { fl[n] = F(c, QD_F_Q); kk[n] = kr[3]; ++n; }
+      if (cfg->apply_cloud) { fl[n] = F(c, QD_F_CLOUD); kk[n] = kr[4]; ++n; }
+      int rc = op_hyper(c, n, fl, sx, kk, nullptr, dt, 1, cos_lap); if (rc) return rc;
+    } else {
+      int rc = op_hyper(c, 3, uvh, sx, kr, nullptr, dt, cfg->k4_nsub, cos_lap); if (rc) return rc;
+      double* fl[2]; const double* kk[2]; int n = 0;
+      if (cfg->apply_q) { fl[n] = F(c, QD_F_Q); kk[n] = kr[3]; ++n; }
+      if (cfg->apply_cloud) { fl[n] = F(c, QD_F_CLOUD); kk[n] = kr[4]; ++n; }
+      if (n) { rc = op_hyper(c, n, fl, sx, kk, nullptr, dt, 1, cos_lap); if (rc) return rc; }
+    }
+  }
+  if (cfg->shapiro_every > 0 && (sc % cfg->shapiro_every == 0)) {
+    double* fl[3] = {F(c, QD_F_U), F(c, QD_F_V), F(c, QD_F_H)};
+    double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    int rc = op_shapiro(c, 3, fl, sx, cfg->shapiro_n); if (rc) return rc;
+    double* f2[2]; int n = 0;
+    if (cfg->shapiro_q) f2[n++] = F(c, QD_F_Q);
+    if (cfg->shapiro_cloud) f2[n++] = F(c, QD_F_CLOUD);
+    if (n) { rc = op_shapiro(c, n, f2, sx, std::max(1, cfg->shapiro_n - 1)); if (rc) return rc; }
+  }
+  if (cfg->spec_every > 0 && (sc % cfg->spec_every == 0)) {
+    int rc;
+    if ((rc = op_bandstop(c, F(c, QD_F_U), cfg->spec_cutoff, cfg->spec_damp))) return rc;
+    if ((rc = op_bandstop(c, F(c, QD_F_V), cfg->spec_cutoff, cfg->spec_damp))) return rc;
+    if ((rc = op_bandstop(c, F(c, QD_F_H), cfg->spec_cutoff, cfg->spec_damp))) return rc;
+  }
+  // cloud tail: advect with the NEW winds, then dissipation / damping / hygiene (+ Q_net in loop mode)
+  {
+    QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X4);
+    QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_ATM));
+    QdTailArgs T; memset(&T, 0, sizeof(T));
+    T.u = F(c, QD_F_U); T.v = F(c, QD_F_V); T.h = F(c, QD_F_H); T.ts = F(c, QD_F_TS); T.q = F(c, QD_F_Q); T.cloud = F(c, QD_F_CLOUD);
+    T.cloud_adv = F(c, QD_F_X4); T.hice = F(c, QD_F_HICE); T.isr = F(c, QD_F_ISR); T.albedo = F(c, QD_F_ALBEDO);
+    T.cloud_eff = F(c, QD_F_CLOUD_EFF); T.lh = F(c, QD_F_LH); T.uo = F(c, QD_F_UO); T.vo = F(c, QD_F_VO);
+    T.qnet = F(c, QD_F_QNET); T.ice = M(c, QD_M_ICE); T.land = M(c, QD_M_LAND);
+    T.part_max_u = c->d_part[0]; T.part_max_va = c->d_part[1]; T.ticket = c->d_ticket + 3 * c->batch;
+    T.dt = dt; T.with_qnet = (mode_loop && cfg->with_ocean) ? 1 : 0; T.has_cloud_eff = c->has_cloud_eff; T.with_max = 0;
+    QD_K(c, k_tail, c->geo, T);
+  }
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
+extern "C" int qd_atmos_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
+  if (!c || !cfg) return QD_E_INVALID;
+  QD_BOUND(c);
+  return atmos_core(c, cfg, 0);
+}
+
+// ------------------------------------------------------------------------------ ocean step
+static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
+  const double dt = cfg->dt;
+  c->oc_counter += 1;                        // ocean.py:281
+  QdOcPrepArgs P0; memset(&P0, 0, sizeof(P0));
+  P0.u = F(c, QD_F_U); P0.v = F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
+  P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
+  P0.ticket = c->d_ticket + 4 * c->batch;
+  QD_K(c, k_ocean_prep, c->geo, P0);
+  QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt);
+  QD_CHECK_LAUNCH(c);
+  // data-dependent sub-step count: one small read-back per step
+  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+  int rc = qd_get_scalars(c, s.data()); if (rc) return rc;
+  int nmax = 1;
+  for (int b = 0; b < c->batch; ++b) nmax = std::max(nmax, (int)s[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
+  c->last_nsub_max = nmax;
+  const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
+  const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
+  const double* P = c->h_prm;   // overrides are taken from member 0 (ensemble members share the switches)
+  const int ovu = P[QD_P_OC_K4_U] == P[QD_P_OC_K4_U], ovv = P[QD_P_OC_K4_V] == P[QD_P_OC_K4_V], ove = P[QD_P_OC_K4_ETA] == P[QD_P_OC_K4_ETA];
+  for (int sub = 0; sub < nmax; ++sub) {
+    QdSubCtl sc{sub, 1};
+    QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
+    Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
+    Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
+    QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+    if (do_hyper) {
+      const int ns = std::max(1, cfg->oc_k4_nsub);
+      for (int q = 0; q < ns; ++q) {
+        QdFields f = mk_fields(3);
+        f.src[0] = F(c, QD_F_X2); f.src[1] = F(c, QD_F_X3); f.src[2] = F(c, QD_F_ETA);
+        f.dst[0] = F(c, QD_F_X4); f.dst[1] = F(c, QD_F_X5); f.dst[2] = F(c, QD_F_X6);
+        QD_K(c, k_ocean_lap, c->geo, f, sc);
+        QdFields u = mk_fields(3);
+        u.src[0] = F(c, QD_F_X4); u.src[1] = F(c, QD_F_X5); u.src[2] = F(c, QD_F_X6);
+        u.dst[0] = F(c, QD_F_X2); u.dst[1] = F(c, QD_F_X3); u.dst[2] = F(c, QD_F_ETA);
+        // rows: sigma4*dx^4 (divided by sub_dt on device) or user rows 2/3 holding constant overrides
+        u.aux[0] = ovu ? ROW(c, QD_R_COUNT + 2) : ROW(c, QD_R_OC_S4DX4);
+        u.aux[1] = ovv ? ROW(c, QD_R_COUNT + 2) : ROW(c, QD_R_OC_S4DX4);
+        u.aux[2] = ove ? ROW(c, QD_R_COUNT + 3) : ROW(c, QD_R_OC_S4DX4);
+        u.scale[2] = 0.5;
+        QD_K(c, k_ocean_hyper, c->geo, u, sc, ns, ovu, ovv, ove);
+      }
+    }
+    if (do_shap) {
+      // members that are done must not be filtered again: only valid when every member shares n_sub
+      double* fl[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
+      double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+      rc = op_shapiro(c, 3, fl, sx, cfg->oc_shapiro_n); if (rc) return rc;
+    }
+    QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
+    Co.ub = F(c, QD_F_X2); Co.vb = F(c, QD_F_X3); Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
+    Co.ticket = c->d_ticket + 5 * c->batch;
+    QD_K(c, k_ocean_continuity, c->geo, Co, sc);
+    QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
+    Sa.sst = F(c, QD_F_SST); Sa.ub = F(c, QD_F_X2); Sa.vb = F(c, QD_F_X3); Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
+    QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
+    QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
+    Sb.tb = F(c, QD_F_X7); Sb.ub = F(c, QD_F_X2); Sb.vb = F(c, QD_F_X3); Sb.qnet = F(c, QD_F_QNET);
+    Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
+    Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
+    Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
+    QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
+  }
+  QdOcPolarArgs Po; memset(&Po, 0, sizeof(Po));
+  Po.sst = F(c, QD_F_SST); Po.uo = F(c, QD_F_UO); Po.vo = F(c, QD_F_VO); Po.ts_atm = F(c, QD_F_TS);
+  Po.land = M(c, QD_M_LAND); Po.ice = M(c, QD_M_ICE); Po.has_ice = cfg->oc_has_ice; Po.inject = inject;
+  QD_KG(c, k_ocean_polar, dim3(2, c->batch), dim3(QD_THREADS), c->geo, Po);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
+extern "C" int qd_ocean_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
+  if (!c || !cfg) return QD_E_INVALID;
+  QD_BOUND(c);
+  return ocean_core(c, cfg, 0);
+}
+extern "C" int qd_last_nsub(qd_ctx* c, int* out) {
+  if (!c || !out) return QD_E_INVALID;
+  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+  int rc = qd_get_scalars(c, s.data()); if (rc) return rc;
+  for (int b = 0; b < c->batch; ++b) out[b] = (int)s[(size_t)b * QD_S_COUNT + QD_S_NSUB];
+  return QD_OK;
+}
+
+// ------------------------------------------------------------------------------ script loop step
+static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
+  const double dt = cfg->dt;
+  const double* P = c->h_prm;
+  const bool orog = P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0;
+  if ((c->w_set & 3) != 3) return qd_fail(c, QD_E_STATE, "qd_set_gauss(0|1) must be called before qd_loop_step", cudaSuccess);
+  const QdGaussW w1 = c->w_sigma1;
+  int rc;
+  QD_KG(c, k_forcing_cols, dim3((c->nlon + 127) / 128), dim3(128), c->geo, c->d_forcing, c->d_step_idx, c->d_hcos);
+  // precipitation (physics.py:253-354)
+  QdPrecipAArgs Pa; memset(&Pa, 0, sizeof(Pa));
+  Pa.u = F(c, QD_F_U); Pa.v = F(c, QD_F_V); Pa.pcond = F(c, QD_F_PCOND); Pa.nx = F(c, QD_F_OROG_NX); Pa.ny = F(c, QD_F_OROG_NY);
+  Pa.pos = F(c, QD_F_X0); Pa.orog_raw = F(c, QD_F_X1); Pa.part = c->d_part[0]; Pa.ticket = c->d_ticket + 6 * c->batch;
+  QD_K(c, k_precip_a, c->geo, Pa);
+  if (orog) { double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X2)}; if ((rc = op_gauss(c, 1, fl, sx, w1))) return rc; }
+  if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT))) return rc;
+  QdPrecipBArgs Pb; memset(&Pb, 0, sizeof(Pb));
+  Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = F(c, QD_F_X1); Pb.praw = F(c, QD_F_X2);
+  Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
+  QD_K(c, k_precip_b, c->geo, Pb);
+  QdPrecipCArgs Pc; Pc.praw = F(c, QD_F_X2); Pc.pos = F(c, QD_F_X0); Pc.g0 = F(c, QD_F_X3); Pc.g1 = F(c, QD_F_X4);
+  QD_K(c, k_precip_c, c->geo, Pc, w1);
+  QdPrecipDArgs Pd; Pd.g0 = F(c, QD_F_X3); Pd.g1 = F(c, QD_F_X4); Pd.precip = F(c, QD_F_PRECIP);
+  QD_K(c, k_precip_d, c->geo, Pd, w1);
+  // clouds (run_simulation.py:1866-1934)
+  if ((rc = op_median(c, F(c, QD_F_PRECIP), 1e-6, c->d_scal + QD_S_PREF, c->d_scal + QD_S_CNT_PRECIP, QD_S_COUNT))) return rc;
+  QdCloudAArgs Ca; Ca.precip = F(c, QD_F_PRECIP); Ca.ts = F(c, QD_F_TS); Ca.u = F(c, QD_F_U); Ca.v = F(c, QD_F_V);
+  Ca.craw = F(c, QD_F_X0); Ca.sraw = F(c, QD_F_X1);
+  QD_K(c, k_cloud_a, c->geo, Ca);
+  {
+    QdFields f = mk_fields(2); f.src[0] = F(c, QD_F_X0); f.src[1] = F(c, QD_F_X1); f.dst[0] = F(c, QD_F_X2); f.dst[1] = F(c, QD_F_X3);
+    QD_K(c, k_gauss_lat, c->geo, f, w1);
+  }
+  QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt;
+  QD_K(c, k_cloud_b, c->geo, Cb, w1);
+  if (P[QD_P_CLOUD_ADVECT] != 0.0) {
+    QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X0);
+    QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_HALF));
+    const double sig = P[QD_P_CLOUD_SMOOTH_SIGMA];
+    QdGaussW wc = c->w_cloud;
+    if (!(sig > 0.0)) wc.r = 0;
+    const double* src = F(c, QD_F_X0);
+    if (wc.r > 0) {
+      QdFields g1 = mk_fields(1); g1.src[0] = F(c, QD_F_X0); g1.dst[0] = F(c, QD_F_X1);
+      QD_K(c, k_gauss_lat, c->geo, g1, wc);
+      src = F(c, QD_F_X1);
+    }
+    QdCloudCArgs Cc; Cc.g0 = src; Cc.cloud = F(c, QD_F_CLOUD);
+    QD_K(c, k_cloud_c, c->geo, Cc, wc);
+  }
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
+extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps) {
+  if (!c || !cfg || !forcing || nsteps < 1) return QD_E_INVALID;
+  QD_BOUND(c);
+  if (nsteps > c->forcing_cap) {
+    QD_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_forcing);
+    c->forcing_cap = std::max(nsteps, 64);
+    QD_CUDA(c, cudaMalloc((void**)&c->d_forcing, (size_t)c->forcing_cap * sizeof(qd_forcing_t)));
+  }
+  QD_CUDA(c, cudaMemcpyAsync(c->d_forcing, forcing, (size_t)nsteps * sizeof(qd_forcing_t), cudaMemcpyHostToDevice, c->stream));
+  QD_CUDA(c, cudaMemsetAsync(c->d_step_idx, 0, sizeof(int), c->stream));
+  for (int s = 0; s < nsteps; ++s) {
+    int rc;
+    if ((rc = loop_physics(c, cfg))) return rc;
+    if ((rc = atmos_core(c, cfg, 1))) return rc;
+    if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
+    if (cfg->with_routing && c->route.ready) {
+      QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), M(c, QD_M_LAND), c->route.d_buffer, cfg->dt);
+    }
+    QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
+  }
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
+#include "qd_route.cuh"

@@ -1,0 +1,310 @@
+// qd_ocean.cuh -- WindDrivenSlabOcean.step (pygcm/ocean.py:265-533) as phase kernels.
+//
+// Slots: the persistent state lives in (UO, VO, SST) = "A"; each CFL sub-step writes momentum to
+// "B" scratch (UB, VB), runs del^4 in place on B, and the closing kernel of the sub-step reads B
+// with neighbours (mean4 outlier fix) and writes A again -- the loop closes for any sub-step
+// count without pointer swaps.  The sub-step count is data dependent (ocean.py:293-303): it is
+// computed on the device per ensemble member and every sub-step kernel exits early for members
+// that are already done.
+#pragma once
+#include "qd_phys.cuh"
+
+struct QdSubCtl { int sub; int active; };    // active=0: not an ocean sub-step kernel (no early exit)
+
+QD_HD bool qd_sub_done(const QdGeo& g, int b, const QdSubCtl& sc) {
+  return sc.active && (sc.sub >= (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
+}
+
+// Wind stress (ocean.py:285-290) + the two maxima behind n_sub (ocean.py:298-299).
+struct QdOcPrepArgs {
+  const double *u, *v, *uo, *vo;
+  double *taux, *tauy, *part_u, *part_va;
+  unsigned* ticket;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs A) {
+  QD_CELL_PROLOGUE(g)
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  double mu = 0.0, mva = 0.0;
+  if (active) {
+    const size_t c = off + idx;
+    const double uo = A.uo[c], vo = A.vo[c];
+    const double ur = A.u[c] - uo, vr = A.v[c] - vo;
+    const double Va = sqrt(ur * ur + vr * vr);
+    const double Ve = qd_min(Va, P[QD_P_OC_VCAP]);
+    A.taux[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * ur);
+    A.tauy[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * vr);
+    mu = sqrt(uo * uo + vo * vo);
+    mva = Va;
+  }
+  double t;
+  double* pu = A.part_u + (size_t)b * gridDim.x;
+  double* pv = A.part_va + (size_t)b * gridDim.x;
+  if (qd_block_max<0>(mu, &t)) pu[blockIdx.x] = t;
+  if (qd_block_max<1>(mva, &t)) pv[blockIdx.x] = t;
+  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
+    double m1 = 0.0, m2 = 0.0;
+    const bool o1 = qd_final_max<2>(pu, gridDim.x, &m1);
+    const bool o2 = qd_final_max<3>(pv, gridDim.x, &m2);
+    // the owner thread of both reductions is the same thread (thread 0 / the serial host thread)
+    if (o1 && o2) {
+      double* S = g.scal + (size_t)b * QD_S_COUNT;
+      S[QD_S_MAX_UOCEAN] = m1;
+      S[QD_S_MAX_VA] = m2;
+    }
+  }
+}
+
+// n_sub = clip(ceil(max(c, uadv) * (dt / max(1e-12, dx_min)) / max(1e-3, cfl)), 1, 500)  (ocean.py:297-303)
+__global__ void k_ocean_nsub(QdGeo g, double dt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= g.batch) return;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  double* S = g.scal + (size_t)b * QD_S_COUNT;
+  const double c = sqrt(P[QD_P_OC_G] * P[QD_P_OC_H]);
+  const double uadv = fmax(S[QD_S_MAX_UOCEAN], S[QD_S_MAX_VA]);
+  const double target = fmax(1e-3, P[QD_P_OC_CFL]);
+  double n = ceil(fmax(c, uadv) * (dt / fmax(1e-12, P[QD_P_OC_DX_MIN])) / target);
+  if (!(n >= 1.0)) n = 1.0;
+  if (n > 500.0) n = 500.0;
+  S[QD_S_NSUB] = n;
+  S[QD_S_SUB_DT] = dt / n;
+}
+
+// Momentum + land zeroing + polar sponge (ocean.py:306-336): A -> B.
+struct QdOcMomArgs {
+  const double *eta, *uo, *vo, *taux, *tauy;
+  double *ub, *vb;
+  const uint8_t* land;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_momentum(QdGeo g, QdOcMomArgs A, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  if (!active || qd_sub_done(g, b, sc)) return;
+  const size_t c = off + idx;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
+  const int nlon = g.nlon, nlat = g.nlat;
+  const double* eta = A.eta + off;
+  const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+  const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;     // np.roll wraps pole to pole
+  const double de_dl = (eta[(size_t)j * nlon + ip] - eta[(size_t)j * nlon + im]) / (2.0 * g.dlon);
+  const double de_dp = (eta[(size_t)jp * nlon + i] - eta[(size_t)jm * nlon + i]) / (2.0 * g.dlat);
+  const double gx = de_dl / (g.a * qd_row(g, QD_R_COS_ADV_HALF)[j]);
+  const double gy = de_dp / g.a;
+  const double f = qd_row(g, QD_R_FCOR)[j];
+  double uo = A.uo[c], vo = A.vo[c];
+  const double rH = P[QD_P_OC_RHO_W] * P[QD_P_OC_H];
+  const double du = (f * vo - P[QD_P_OC_G] * gx + A.taux[c] / rH - P[QD_P_OC_R_BOT] * uo);
+  const double dv = (-f * uo - P[QD_P_OC_G] * gy + A.tauy[c] / rH - P[QD_P_OC_R_BOT] * vo);
+  uo = uo + sub_dt * du;
+  vo = vo + sub_dt * dv;
+  if (A.land[c] == 1) { uo = 0.0; vo = 0.0; }
+  const double rex = qd_row(g, QD_R_OC_SPONGE)[j];
+  uo = uo - sub_dt * rex * uo;
+  vo = vo - sub_dt * rex * vo;
+  A.ub[c] = uo;
+  A.vb[c] = vo;
+}
+
+// del^4 on (UB, VB, ETA) with k4 = sigma4*dx^4/max(1e-12, sub_dt) (ocean.py:341-356): two passes.
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_lap(QdGeo g, QdFields f, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  if (!active || qd_sub_done(g, b, sc)) return;
+  const double* cosr = qd_row(g, QD_R_COS_ADV_HALF);
+  for (int k = 0; k < f.n; ++k) {
+    QdCleanLoad F{f.src[k] + off, g.nlon};
+    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+  }
+}
+// aux[k] = row table (sigma4*dx^4, or a constant row for QD_OCEAN_K4_* overrides with over[k]=1)
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_hyper(QdGeo g, QdFields f, QdSubCtl sc, int k4_nsub, int over0, int over1, int over2) {
+  QD_CELL_PROLOGUE(g)
+  if (!active || qd_sub_done(g, b, sc)) return;
+  const double* cosr = qd_row(g, QD_R_COS_ADV_HALF);
+  const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
+  const double inner = sub_dt / (double)(k4_nsub > 1 ? k4_nsub : 1);
+  const int over[3] = {over0, over1, over2};
+  for (int k = 0; k < f.n; ++k) {
+    QdCleanLoad L{f.src[k] + off, g.nlon};
+    const double L2 = qd_lap_cell(L, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    double k4 = f.aux[k][j];
+    if (!over[k]) { k4 = k4 / fmax(1e-12, sub_dt); k4 = f.scale[k] * k4; }
+    const double cur = qd_nan_to_num(f.dst[k][off + idx]);
+    f.dst[k][off + idx] = qd_nan_to_num(cur - k4 * L2 * inner);
+  }
+}
+
+// Continuity (ocean.py:364-367) + the area-weighted ocean sum of eta for the mean removal (:369-375).
+struct QdOcContArgs {
+  const double *ub, *vb;
+  double *eta, *part;
+  const uint8_t* land;
+  unsigned* ticket;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcContArgs A, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  const bool done = qd_sub_done(g, b, sc);
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  double contrib = 0.0;
+  if (active && !done) {
+    const size_t c = off + idx;
+    const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
+    const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);
+    double e = A.eta[c] + (-sub_dt * P[QD_P_OC_H] * div);
+    const bool land = A.land[c] == 1;
+    if (land) e = 0.0;
+    A.eta[c] = e;
+    contrib = e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
+  }
+  double t;
+  double* part = A.part + (size_t)b * gridDim.x;
+  if (qd_block_sum<0>(contrib, &t)) part[blockIdx.x] = t;
+  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
+    if (qd_final_sum<1>(part, gridDim.x, &t)) { if (!done) g.scal[(size_t)b * QD_S_COUNT + QD_S_ETA_NUM] = t; }
+  }
+}
+
+// eta mean removal + hygiene (ocean.py:375,436-443) and SST semi-Lagrangian blend (ocean.py:380-382): A -> TB.
+struct QdOcSstAArgs {
+  const double *sst, *ub, *vb;
+  double *eta, *tb;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_advect(QdGeo g, QdOcSstAArgs A, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  if (!active || qd_sub_done(g, b, sc)) return;
+  const size_t c = off + idx;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double* S = g.scal + (size_t)b * QD_S_COUNT;
+  const double sub_dt = S[QD_S_SUB_DT];
+  double e = A.eta[c];
+  if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - S[QD_S_ETA_NUM] / (P[QD_P_OC_WSUM_OCEAN] + 1e-15);
+  A.eta[c] = qd_clip(qd_nan_to_num(e), -P[QD_P_OC_ETA_CAP], P[QD_P_OC_ETA_CAP]);
+  double y, x;
+  qd_departure(A.ub[c], A.vb[c], sub_dt, g.a, qd_row(g, QD_R_COS_ADV_HALF)[j], g.dlat, g.dlon, j, i, &y, &x);
+  const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
+  const double al = P[QD_P_OC_ADV_ALPHA];
+  A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
+}
+
+// SST diffusion + Q_net heating (ocean.py:384-406), outlier handling of currents (ocean.py:408-434): B -> A.
+// On the member's last sub-step the non-polar rows also get the final Ts clip (ocean.py:531-533) and,
+// in loop mode, the SST injection into the atmosphere's T_s (run_simulation.py:2252-2253); the two
+// polar rows are finished by k_ocean_polar.
+struct QdOcSstBArgs {
+  const double *tb, *ub, *vb, *qnet;
+  double *sst, *uo, *vo, *ts_atm;
+  const uint8_t *land, *ice;
+  int has_q, has_ice, inject;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  if (!active || qd_sub_done(g, b, sc)) return;
+  const size_t c = off + idx;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double* S = g.scal + (size_t)b * QD_S_COUNT;
+  const double sub_dt = S[QD_S_SUB_DT];
+  const int nlon = g.nlon, nlat = g.nlat;
+  double T = A.tb[c];
+  if (P[QD_P_OC_K_H] > 0.0) {
+    QdCleanLoad F{A.tb + off, nlon};
+    const double lap = qd_lap_cell(F, j, i, nlat, nlon, g.dlat, g.dlon_sq, g.a_sq, qd_row(g, QD_R_COS_ADV_HALF));
+    T = qd_nan_to_num(T) + sub_dt * P[QD_P_OC_K_H] * lap;
+  }
+  const bool ocean = A.land[c] != 1;
+  const bool ice = A.has_ice ? (A.ice[c] != 0) : false;
+  if (P[QD_P_OC_USE_QNET] != 0.0 && A.has_q) {
+    const double tend = A.qnet[c] / (P[QD_P_OC_RHO_W] * P[QD_P_OC_CP_W] * P[QD_P_OC_H]);
+    if (ocean && !ice) T = T + sub_dt * tend;
+    else if (ocean && ice && A.has_ice && P[QD_P_OC_ICE_QFAC] > 0.0) T = T + sub_dt * P[QD_P_OC_ICE_QFAC] * tend;
+  }
+  T = qd_nan_to_num(T);
+  // currents
+  const double* ub = A.ub + off;
+  const double* vb = A.vb + off;
+  double uo = qd_nan_to_num(ub[idx]), vo = qd_nan_to_num(vb[idx]);
+  const double cap = P[QD_P_OC_MAX_U];
+  const double speed = sqrt(uo * uo + vo * vo);
+  if (P[QD_P_OC_MEAN4] != 0.0) {
+    if (speed > cap) {
+      const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+      const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;
+      const size_t n_ = (size_t)jp * nlon + i, s_ = (size_t)jm * nlon + i, e_ = (size_t)j * nlon + ip, w_ = (size_t)j * nlon + im;
+      uo = 0.25 * (qd_nan_to_num(ub[n_]) + qd_nan_to_num(ub[s_]) + qd_nan_to_num(ub[e_]) + qd_nan_to_num(ub[w_]));
+      vo = 0.25 * (qd_nan_to_num(vb[n_]) + qd_nan_to_num(vb[s_]) + qd_nan_to_num(vb[e_]) + qd_nan_to_num(vb[w_]));
+    }
+    const double sp2 = sqrt(uo * uo + vo * vo);
+    const double sc2 = (sp2 > cap) ? cap / (sp2 + 1e-12) : 1.0;
+    uo = uo * sc2;
+    vo = vo * sc2;
+  } else {
+    const double sc1 = (speed > cap) ? cap / (speed + 1e-12) : 1.0;
+    uo = uo * sc1;
+    vo = vo * sc1;
+  }
+  A.uo[c] = uo;
+  A.vo[c] = vo;
+  const bool last = sc.active ? (sc.sub == (int)S[QD_S_NSUB] - 1) : true;
+  if (last && j > 0 && j < nlat - 1) {
+    T = qd_clip(T, P[QD_P_OC_TS_MIN], P[QD_P_OC_TS_MAX]);
+    if (A.inject && ocean && !ice) A.ts_atm[c] = T;
+  }
+  A.sst[c] = T;
+}
+
+// Polar rows: ring means (ocean.py:197-262), final clip, SST injection.  grid = (2 poles, B).
+template <int SLOT, class Fn>
+QD_D double qd_block_sum_n(int n, Fn fn) {
+  __shared__ double res;
+#if QD_EMU
+  if (threadIdx.x == 0) { double s = 0.0; for (int k = 0; k < n; ++k) s += fn(k); res = s; }
+  return res;
+#else
+  double s = 0.0;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) s += fn(k);
+  double tot;
+  if (qd_block_sum<SLOT>(s, &tot)) res = tot;
+  __syncthreads();
+  return res;
+#endif
+}
+struct QdOcPolarArgs {
+  double *sst, *uo, *vo, *ts_atm;
+  const uint8_t *land, *ice;
+  int has_ice, inject;
+};
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarArgs A) {
+  const int b = blockIdx.y, north = blockIdx.x;
+  const int j = north ? g.nlat - 1 : 0, n = g.nlon;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const size_t base = (size_t)b * g.ncell + (size_t)j * n;
+  double* T = A.sst + base;
+  double* U = A.uo + base;
+  double* V = A.vo + base;
+  const uint8_t* land = A.land + base;
+  const double* sl = g.cols + (size_t)QD_C_SIN_LON * n;
+  const double* cl = g.cols + (size_t)QD_C_COS_LON * n;
+  const double sgn = north ? -1.0 : 1.0;
+  if (P[QD_P_OC_POLAR_FIX] != 0.0) {
+    const double cnt = qd_block_sum_n<0>(n, [&](int k) { return land[k] != 1 ? 1.0 : 0.0; });
+    if (cnt > 0.0) {
+      const double st = qd_block_sum_n<1>(n, [&](int k) { return land[k] != 1 ? T[k] : 0.0; });
+      const double sx = qd_block_sum_n<2>(n, [&](int k) { return land[k] != 1 ? (-sl[k] * U[k] + sgn * cl[k] * V[k]) : 0.0; });
+      const double sy = qd_block_sum_n<3>(n, [&](int k) { return land[k] != 1 ? (cl[k] * U[k] + sgn * sl[k] * V[k]) : 0.0; });
+      const double mt = st / cnt, mx = sx / cnt, my = sy / cnt;
+      __syncthreads();
+      QD_BLOCK_FIRST_FOR(k, n) {
+        if (land[k] != 1) {
+          T[k] = mt;
+          U[k] = -sl[k] * mx + cl[k] * my;
+          V[k] = sgn * cl[k] * mx + sgn * sl[k] * my;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  QD_BLOCK_FIRST_FOR(k, n) {
+    const double t = qd_clip(T[k], P[QD_P_OC_TS_MIN], P[QD_P_OC_TS_MAX]);
+    T[k] = t;
+    const bool ice = A.has_ice ? (A.ice[base + k] != 0) : false;
+    if (A.inject && land[k] != 1 && !ice) A.ts_atm[base + k] = t;
+  }
+}

@@ -1,0 +1,403 @@
+// qd_ops.cuh -- numeric operators of the Qingdai step as sm_100a kernels.
+//
+// Layout: every field is float64 [B][nlat][nlon]; a thread owns one cell, threads run along
+// longitude (linear cell index) so that every warp touches consecutive addresses whatever
+// n_lon is; blockIdx.y is the ensemble member.  These kernels are HBM/L2-bandwidth work:
+// no tensor cores, no reshaping into GEMMs.  Operand order follows the reference's NumPy
+// expressions exactly (compile with -fmad=false) so fields agree to the last few ulp.
+#pragma once
+#include "qd_rt.h"
+#include "../../include/qd_b200.h"
+
+#define QD_THREADS 256
+#define QD_MAX_FIELDS 6
+#define QD_GAUSS_MAXR 8
+#define QD_SIGMA_SB 5.670374e-8   /* constants.py:10 */
+
+struct QdGeo {
+  int nlat, nlon, ncell, batch;
+  double a, dlat, dlon, a_sq, dlon_sq;
+  const double* rows;    // [QD_R_COUNT + 4 user][nlat]
+  const double* cols;    // [QD_C_COUNT][nlon]
+  const double* prm;     // [B][QD_P_COUNT]
+  double* scal;          // [B][QD_S_COUNT]
+};
+
+struct QdFields {          // up to QD_MAX_FIELDS field pointers passed by value
+  int n;
+  const double* src[QD_MAX_FIELDS];
+  double* dst[QD_MAX_FIELDS];
+  const double* aux[QD_MAX_FIELDS];   // per-field row table (k4 rows) or second input
+  double scale[QD_MAX_FIELDS];
+};
+
+struct QdGaussW { int r; int wrap; double w[2 * QD_GAUSS_MAXR + 1]; };
+
+#define QD_CELL_PROLOGUE(geo)                                         \
+  const int b = blockIdx.y;                                           \
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;              \
+  const bool active = idx < (geo).ncell;                              \
+  const int j = active ? idx / (geo).nlon : 0;                        \
+  const int i = active ? idx - j * (geo).nlon : 0;                    \
+  const size_t off = (size_t)b * (geo).ncell;                         \
+  (void)i; (void)j; (void)off;
+
+QD_HD const double* qd_row(const QdGeo& g, int id) { return g.rows + (size_t)id * g.nlat; }
+QD_HD double qd_prm(const QdGeo& g, int b, int id) { return g.prm[(size_t)b * QD_P_COUNT + id]; }
+
+// ------------------------------------------------------------------------------ Laplacian
+// dynamics.py:144-173 / ocean.py:100-117: (1/a^2)[(1/c) d_phi(c d_phi F) + d2_lambda F / c^2],
+// np.gradient in phi (one-sided at rows 0, n-1), periodic-n 3-point in lambda, nan_to_num(F) first.
+struct QdCleanLoad {
+  const double* p; int nlon;
+  QD_HD double operator()(int jj, int ii) const { return qd_nan_to_num(p[(size_t)jj * nlon + ii]); }
+};
+
+template <class Acc>
+QD_HD double qd_lap_cell(const Acc& F, int j, int i, int nlat, int nlon, double dphi, double dlmb_sq,
+                         double a_sq, const double* c) {
+  const int jm = j > 0 ? j - 1 : 0, jp = j < nlat - 1 ? j + 1 : nlat - 1;
+  // G(jj): np.gradient(F, dphi, axis=0) at row jj
+  auto G = [&](int jj) -> double {
+    if (jj == 0) return (F(1, i) - F(0, i)) / dphi;
+    if (jj == nlat - 1) return (F(nlat - 1, i) - F(nlat - 2, i)) / dphi;
+    return (F(jj + 1, i) - F(jj - 1, i)) / (2.0 * dphi);
+  };
+  double gphi;
+  if (j == 0) gphi = (c[1] * G(1) - c[0] * G(0)) / dphi;
+  else if (j == nlat - 1) gphi = (c[j] * G(j) - c[j - 1] * G(j - 1)) / dphi;
+  else gphi = (c[jp] * G(jp) - c[jm] * G(jm)) / (2.0 * dphi);
+  const double term_phi = (1.0 / c[j]) * gphi;
+  const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+  const double d2 = ((F(j, ip) - 2.0 * F(j, i)) + F(j, im)) / dlmb_sq;
+  const double term_lam = d2 / (c[j] * c[j]);
+  return (term_phi + term_lam) / a_sq;
+}
+
+// out[k] = lap(src[k]) for k < n fields; aux[0] = cosine row table (floored by the caller).
+__global__ void __launch_bounds__(QD_THREADS) k_laplacian(QdGeo g, QdFields f, const double* cosr) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  for (int k = 0; k < f.n; ++k) {
+    QdCleanLoad F{f.src[k] + off, g.nlon};
+    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+  }
+}
+
+// F <- nan_to_num(nan_to_num(F) - k4*lap(L)*sub_dt)   (dynamics.py:205-212).  src = L, dst = F (in
+// place), aux = k4 row table, scale = multiplier applied to the table (1, 0.5, 0.25 are exact).
+// If k4_over_dt >= 0 the coefficient is (aux*scale)/k4_over_dt... see ocean: k4 = s4dx4 / sub_dt.
+__global__ void __launch_bounds__(QD_THREADS) k_hyper_update(QdGeo g, QdFields f, const double* cosr,
+                                                            double sub_dt, double k4_div) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  for (int k = 0; k < f.n; ++k) {
+    QdCleanLoad L{f.src[k] + off, g.nlon};
+    const double L2 = qd_lap_cell(L, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    double k4 = f.aux[k][j];
+    if (k4_div > 0.0) k4 = k4 / k4_div;        // ocean.py:347  sigma4*dx^4 / max(1e-12, sub_dt)
+    k4 = f.scale[k] * k4;                      // 0.5*k4_map etc. (dynamics.py:568-570, ocean.py:352)
+    const double cur = qd_nan_to_num(f.dst[k][off + idx]);
+    f.dst[k][off + idx] = qd_nan_to_num(cur - k4 * L2 * sub_dt);
+  }
+}
+
+// ------------------------------------------------------------------------------ semi-Lagrangian gather
+// scipy map_coordinates(order=1, mode='wrap') semantics (see oracle/ops.py:bilinear_wrap):
+// legacy wrap with period n-1 on BOTH axes, weights w0 = 1-t, w1 = 1-w0, fixed accumulation order.
+QD_HD double qd_wrap_coord(double x, int n) {
+  if (n <= 1) return 0.0;
+  const double sz = (double)(n - 1);
+  if (!(fabs(x) < 1.0e15)) return 0.0;          // NaN / absurd departure points: reference is UB here
+  if (x < 0.0) x += sz * ((double)(long long)(-x / sz) + 1.0);
+  else if (x > sz) x -= sz * (double)(long long)(x / sz);
+  return x;
+}
+QD_HD int qd_wrap_next(int k, int n) {           // index k+1 reduced like scipy does for the 2nd tap
+  const int k1 = k + 1;
+  if (n <= 1) return 0;
+  if (k1 > n - 1) return k1 - (n - 1) * (k1 / (n - 1));
+  return k1;
+}
+QD_HD double qd_bilinear_wrap(const double* F, int nlat, int nlon, double y, double x) {
+  y = qd_wrap_coord(y, nlat);
+  x = qd_wrap_coord(x, nlon);
+  const double fy = floor(y), fx = floor(x);
+  int j0 = (int)fy, i0 = (int)fx;
+  if (j0 > nlat - 1) j0 = nlat - 1;
+  if (i0 > nlon - 1) i0 = nlon - 1;
+  const int j1 = qd_wrap_next(j0, nlat), i1 = qd_wrap_next(i0, nlon);
+  const double wy0 = 1.0 - (y - fy), wx0 = 1.0 - (x - fx);
+  const double wy1 = 1.0 - wy0, wx1 = 1.0 - wx0;
+  const double* r0 = F + (size_t)j0 * nlon;
+  const double* r1 = F + (size_t)j1 * nlon;
+  double t = r0[i0] * wy0 * wx0;
+  t = t + r0[i1] * wy0 * wx1;
+  t = t + r1[i0] * wy1 * wx0;
+  t = t + r1[i1] * wy1 * wx1;
+  return t;
+}
+// departure point of cell (j,i): dynamics.py:104-115
+QD_HD void qd_departure(double u, double v, double dt, double a, double cosj, double dlat, double dlon,
+                        int j, int i, double* y, double* x) {
+  const double dx = (u * dt / (a * cosj)) / dlon;
+  const double dy = (v * dt / a) / dlat;
+  *y = (double)j - dy;
+  *x = (double)i - dx;
+}
+
+__global__ void __launch_bounds__(QD_THREADS) k_advect(QdGeo g, QdFields f, const double* u, const double* v,
+                                                      double dt, const double* cosr) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  double y, x;
+  qd_departure(u[off + idx], v[off + idx], dt, g.a, cosr[j], g.dlat, g.dlon, j, i, &y, &x);
+  for (int k = 0; k < f.n; ++k)
+    f.dst[k][off + idx] = qd_bilinear_wrap(f.src[k] + off, g.nlat, g.nlon, y, x);
+}
+
+// ------------------------------------------------------------------------------ Shapiro 1-2-1
+// dynamics.py:215-231: lon pass periodic (period n_lon), lat pass edge-replicate; scipy's
+// accumulation order (x[k-1]*.25 + x[k]*.5) + x[k+1]*.25.  clean=1 applies nan_to_num on load.
+__global__ void __launch_bounds__(QD_THREADS) k_shapiro_lon(QdGeo g, QdFields f, int clean) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  const int ip = i + 1 < g.nlon ? i + 1 : 0, im = i > 0 ? i - 1 : g.nlon - 1;
+  for (int k = 0; k < f.n; ++k) {
+    const double* r = f.src[k] + off + (size_t)j * g.nlon;
+    double xm = r[im], x0 = r[i], xp = r[ip];
+    if (clean) { xm = qd_nan_to_num(xm); x0 = qd_nan_to_num(x0); xp = qd_nan_to_num(xp); }
+    f.dst[k][off + idx] = (xm * 0.25 + x0 * 0.5) + xp * 0.25;
+  }
+}
+__global__ void __launch_bounds__(QD_THREADS) k_shapiro_lat(QdGeo g, QdFields f) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  const int jm = j > 0 ? j - 1 : 0, jp = j < g.nlat - 1 ? j + 1 : g.nlat - 1;
+  for (int k = 0; k < f.n; ++k) {
+    const double* p = f.src[k] + off;
+    f.dst[k][off + idx] = (p[(size_t)jm * g.nlon + i] * 0.25 + p[idx] * 0.5) + p[(size_t)jp * g.nlon + i] * 0.25;
+  }
+}
+
+// ------------------------------------------------------------------------------ Gaussian (separable)
+// scipy gaussian_filter1d -> NI_Correlate1D symmetric branch: centre*w0, then pairs from the outermost
+// tap inwards.  reflect = (d c b a | a b c d | d c b a); wrap = period n.
+QD_HD int qd_extend(int k, int n, int wrap) {
+  if (wrap) { k %= n; return k < 0 ? k + n : k; }
+  const int p = 2 * n;
+  k %= p; if (k < 0) k += p;
+  return k >= n ? p - 1 - k : k;
+}
+template <class Load>
+QD_HD double qd_gauss_tap(const Load& E, int c, int n, const QdGaussW& w) {
+  double out = E(c) * w.w[w.r];
+  for (int jj = -w.r; jj < 0; ++jj)
+    out = out + (E(qd_extend(c + jj, n, w.wrap)) + E(qd_extend(c - jj, n, w.wrap))) * w.w[w.r + jj];
+  return out;
+}
+__global__ void __launch_bounds__(QD_THREADS) k_gauss_lat(QdGeo g, QdFields f, QdGaussW w) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  for (int k = 0; k < f.n; ++k) {
+    const double* p = f.src[k] + off + i;
+    const int nlon = g.nlon;
+    auto E = [&](int jj) -> double { return p[(size_t)jj * nlon]; };
+    f.dst[k][off + idx] = qd_gauss_tap(E, j, g.nlat, w);
+  }
+}
+__global__ void __launch_bounds__(QD_THREADS) k_gauss_lon(QdGeo g, QdFields f, QdGaussW w) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  for (int k = 0; k < f.n; ++k) {
+    const double* p = f.src[k] + off + (size_t)j * g.nlon;
+    auto E = [&](int ii) -> double { return p[ii]; };
+    f.dst[k][off + idx] = qd_gauss_tap(E, i, g.nlon, w);
+  }
+}
+
+// ------------------------------------------------------------------------------ divergence / vorticity
+// grid.py:41-88: np.roll centred differences; the phi-term is zeroed on rows 0 and n-1.
+QD_HD double qd_div_cell(const double* u, const double* v, int j, int i, const QdGeo& g) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const double* cosr = qd_row(g, QD_R_COS);
+  const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+  const double du = (u[(size_t)j * nlon + ip] - u[(size_t)j * nlon + im]) / (2 * g.dlon);
+  double dv = 0.0;
+  if (j > 0 && j < nlat - 1)
+    dv = (v[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - v[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) / (2 * g.dlat);
+  return (1 / (g.a * qd_row(g, QD_R_COS_CAP)[j])) * (du + dv);
+}
+QD_HD double qd_vort_cell(const double* u, const double* v, int j, int i, const QdGeo& g) {
+  const int nlon = g.nlon, nlat = g.nlat;
+  const double* cosr = qd_row(g, QD_R_COS);
+  const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+  const double dv = (v[(size_t)j * nlon + ip] - v[(size_t)j * nlon + im]) / (2 * g.dlon);
+  double du = 0.0;
+  if (j > 0 && j < nlat - 1)
+    du = (u[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - u[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) / (2 * g.dlat);
+  return (1 / (g.a * qd_row(g, QD_R_COS_CAP)[j])) * (dv - du);
+}
+__global__ void __launch_bounds__(QD_THREADS) k_divvort(QdGeo g, const double* u, const double* v, double* out, int vort) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  out[off + idx] = vort ? qd_vort_cell(u + off, v + off, j, i, g) : qd_div_cell(u + off, v + off, j, i, g);
+}
+
+// ------------------------------------------------------------------------------ zonal band-stop
+// dynamics.py:233-258: rfft -> bins >= kcut scaled by (1-damp) -> irfft.  Row-local equivalent used
+// here: y = x - d * HP(x), HP = projection on the stop band kcut..kN, evaluated as a real DFT
+// restricted to that band (n_lon*n_stop MACs forward and back per row); d = 1 - max(0, 1-min(1,damp)).
+// One block per (row, member).  twid = cos|sin(2 pi m / n) [2][nlon] from the host.
+__global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* f, const double* twid,
+                                                              int kcut, double d, double* coef, double* outbuf) {
+  const int b = blockIdx.y, j = blockIdx.x, n = g.nlon;
+  double* row = f + (size_t)b * g.ncell + (size_t)j * n;
+  const int kN = n / 2;                                   // rfft bins = n/2 + 1
+  const int nstop = kN - kcut + 1;
+  double* re = coef + ((size_t)b * g.nlat + j) * 2 * (size_t)(kN + 1);
+  double* im = re + (kN + 1);
+  double* orow = outbuf + (size_t)b * g.ncell + (size_t)j * n;
+  const double* ct = twid;
+  const double* st = twid + n;
+  QD_BLOCK_FIRST_FOR(k, nstop) {
+    const int kk = kcut + k;
+    double sr = 0.0, si = 0.0;
+    for (int m = 0; m < n; ++m) {
+      const int ph = (int)(((long long)kk * m) % n);
+      const double x = qd_nan_to_num(row[m]);
+      sr = sr + x * ct[ph];
+      si = si - x * st[ph];
+    }
+    re[k] = sr; im[k] = si;
+  }
+  __syncthreads();
+  QD_BLOCK_FIRST_FOR(m, n) {
+    double acc = 0.0;
+    for (int k = 0; k < nstop; ++k) {
+      const int kk = kcut + k;
+      const int ph = (int)(((long long)kk * m) % n);
+      const bool nyq = (2 * kk == n);
+      const double wgt = (kk == 0 || nyq) ? 1.0 : 2.0;
+      // Re(X_k e^{+i 2 pi k m / n}); irfft drops the imaginary part of the Nyquist bin
+      const double term = nyq ? re[k] * ct[ph] : (re[k] * ct[ph] - im[k] * st[ph]);
+      acc = acc + wgt * term;
+    }
+    orow[m] = qd_nan_to_num(qd_nan_to_num(row[m]) - d * (acc / (double)n));
+  }
+  __syncthreads();
+  QD_BLOCK_FIRST_FOR(m, n) { row[m] = orow[m]; }
+}
+
+// ------------------------------------------------------------------------------ reductions
+// sum over cells of x * w[j] (energy.py:524, hydrology.py:267) -> out[b*stride]; deterministic: block
+// partials are combined in a fixed order by the last block to finish.
+__global__ void __launch_bounds__(QD_THREADS) k_wsum(QdGeo g, const double* x, const double* wrow,
+                                                    double* partial, unsigned* ticket, double* out, int out_stride) {
+  QD_CELL_PROLOGUE(g)
+  double v = 0.0;
+  if (active) v = x[off + idx] * (wrow ? wrow[j] : 1.0);
+  double tot;
+  double* part = partial + (size_t)b * gridDim.x;
+  if (qd_block_sum<0>(v, &tot)) part[blockIdx.x] = tot;
+  if (qd_block_is_last(ticket + b, gridDim.x)) {
+    if (qd_final_sum<1>(part, gridDim.x, &tot)) out[(size_t)b * out_stride] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------ exact median of positives
+// np.median(x[x>0]) (physics.py:298-301, run_simulation.py:1872-1873, dynamics.py:344-348) as a 4-pass
+// MSD radix select on the IEEE bit pattern (positive doubles order like uint64), 16 bits per pass,
+// plus one closing pass that finds the upper middle element when the count is even.
+struct QdSelState {          // per member
+  unsigned long long prefix; // bits decided so far
+  unsigned long long rank;   // 0-based rank still to find inside the prefix bucket
+  unsigned long long count;  // number of positives
+  unsigned long long cnt_le; // closing pass: #(x <= L)
+  unsigned long long min_gt; // closing pass: bit pattern of min(x > L)
+  double lower;              // value at the lower-middle rank
+  double result;
+};
+#define QD_SEL_BINS 65536
+#define QD_SEL_CHUNKS 256
+
+__global__ void __launch_bounds__(QD_THREADS) k_select_hist(QdGeo g, const double* x, int pass, unsigned* hist,
+                                                           QdSelState* st, unsigned* ticket) {
+  QD_CELL_PROLOGUE(g)
+  const int shift = 48 - 16 * pass;
+  unsigned* h = hist + (size_t)b * QD_SEL_BINS;
+  if (active) {
+    const double v = x[off + idx];
+    if (v > 0.0) {
+      const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+      bool match = true;
+      if (pass > 0) match = (key >> (shift + 16)) == (st[b].prefix >> (shift + 16));
+      if (match) atomicAdd(h + ((key >> shift) & 0xffffull), 1u);
+    }
+  }
+  if (qd_block_is_last(ticket + b, gridDim.x)) {
+    __shared__ unsigned long long chunk[QD_SEL_CHUNKS];
+    QD_BLOCK_LAST_FOR(c, QD_SEL_CHUNKS) {
+      unsigned long long s = 0;
+      for (int k = 0; k < QD_SEL_BINS / QD_SEL_CHUNKS; ++k) s += QD_LDCG(h + c * (QD_SEL_BINS / QD_SEL_CHUNKS) + k);
+      chunk[c] = s;
+    }
+    __syncthreads();
+    QD_BLOCK_LAST_ONE {
+      QdSelState s = st[b];
+      if (pass == 0) {
+        unsigned long long n = 0;
+        for (int c = 0; c < QD_SEL_CHUNKS; ++c) n += chunk[c];
+        s.count = n; s.prefix = 0; s.rank = n ? (n - 1) / 2 : 0;
+      }
+      if (s.count > 0) {
+        unsigned long long cum = 0;
+        int c = 0;
+        for (; c < QD_SEL_CHUNKS - 1; ++c) { if (cum + chunk[c] > s.rank) break; cum += chunk[c]; }
+        int k = c * (QD_SEL_BINS / QD_SEL_CHUNKS);
+        const int kend = k + QD_SEL_BINS / QD_SEL_CHUNKS - 1;
+        for (; k < kend; ++k) { const unsigned long long hk = QD_LDCG(h + k); if (cum + hk > s.rank) break; cum += hk; }
+        s.prefix |= ((unsigned long long)k) << shift;
+        s.rank -= cum;
+        if (pass == 3) s.lower = __longlong_as_double((long long)s.prefix);
+      }
+      s.cnt_le = 0; s.min_gt = ~0ull;
+      st[b] = s;
+    }
+    __syncthreads();
+    QD_BLOCK_LAST_FOR(k, QD_SEL_BINS) { h[k] = 0; }
+  }
+}
+__global__ void __launch_bounds__(QD_THREADS) k_select_close(QdGeo g, const double* x, QdSelState* st,
+                                                            unsigned* ticket, double empty_value,
+                                                            double* out, double* cnt_out, int out_stride) {
+  QD_CELL_PROLOGUE(g)
+  const double L = st[b].lower;
+  const bool any = st[b].count > 0;
+  if (active && any) {
+    const double v = x[off + idx];
+    if (v > 0.0) {
+      if (v <= L) atomicAdd(&st[b].cnt_le, 1ull);
+      else atomicMin(&st[b].min_gt, (unsigned long long)__double_as_longlong(v));
+    }
+  }
+  if (qd_block_is_last(ticket + b, gridDim.x)) {
+    QD_BLOCK_LAST_ONE {
+      QdSelState s;
+      s.count = st[b].count; s.lower = st[b].lower;
+      s.cnt_le = QD_LDCG(&st[b].cnt_le); s.min_gt = QD_LDCG(&st[b].min_gt);
+      double r = empty_value;
+      if (s.count > 0) {
+        if (s.count & 1ull) r = s.lower;
+        else {
+          const unsigned long long ku = s.count / 2;          // 0-based upper-middle rank
+          const double U = (s.cnt_le > ku) ? s.lower : __longlong_as_double((long long)s.min_gt);
+          r = (s.lower + U) / 2.0;                            // np.mean of the two middle values
+        }
+      }
+      st[b].result = r;
+      out[(size_t)b * out_stride] = r;
+      if (cnt_out) cnt_out[(size_t)b * out_stride] = (double)s.count;
+    }
+  }
+}

@@ -1,0 +1,94 @@
+"""Fused script loop: the per-step body of scripts/run_simulation.py:1760-2344 on the device.
+
+``Simulation`` is what ``qingdai_b200.run_simulation.main`` drives and what bench.py times: state
+lives in HBM, each step consumes one ``qd_forcing_t`` (10 doubles) and nothing comes back unless
+asked for (diagnostics / plots / autosave pull fields through the C ABI on demand).
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import constants as const
+from ._binding import Forcing
+from .engine import Engine
+from .forcing import OrbitalSystem, ThermalForcing
+from .grid import SphericalGrid
+from .params import QDParams
+
+DAY_SECONDS = 2 * np.pi / const.PLANET_OMEGA          # run_simulation.py:1594
+
+
+def q_sat_host(T, p0):
+    """humidity.py:85-101, host evaluation for the initial q only (dynamics.py:84)."""
+    Tc = np.clip(np.asarray(T, dtype=float) - 273.15, -80.0, 60.0)
+    es = 610.94 * np.exp(17.625 * Tc / (Tc + 243.04))
+    den = np.maximum(p0 - (1.0 - 0.622) * es, 1.0)
+    return np.clip(0.622 * es / den, 0.0, 0.5)
+
+
+class Simulation:
+    def __init__(self, nlat, nlon, topo: dict | Sequence[dict], params: Optional[QDParams | Sequence[QDParams]] = None,
+                 dt=300, batch=1, with_ocean=True, with_hydrology=True, with_eco=False, loop_with_albedo=False,
+                 device=None, lib=None, t0=0.0):
+        self.grid = SphericalGrid(nlat, nlon)
+        plist = list(params) if isinstance(params, (list, tuple)) else [params or QDParams.from_env()] * batch
+        self.engine = Engine(nlat, nlon, batch=batch, params=plist, dt=dt, device=device, lib=lib)
+        self.dt = dt
+        self.t = float(t0)
+        self.step_index = 0
+        self.forcing = ThermalForcing(self.grid, OrbitalSystem())
+        self.cfg = dict(with_ocean=with_ocean, with_hydrology=with_hydrology, with_eco=with_eco,
+                        loop_with_albedo=loop_with_albedo, with_routing=False)
+        topos = list(topo) if isinstance(topo, (list, tuple)) else [topo] * batch
+        e = self.engine
+        for b, tp in enumerate(topos):
+            e.set_mask("land", tp["land_mask"], member=b)
+            e.set("friction", tp["friction"], member=b)
+            e.set("base_albedo", tp["base_albedo"], member=b)
+            land = np.asarray(tp["land_mask"])
+            e.set("cs_map", np.where(land == 1, plist[b].Cs_land, plist[b].Cs_ocean).astype(float), member=b)
+        if topos[0].get("elevation") is not None:
+            for b, tp in enumerate(topos):
+                e.set_elevation(tp["elevation"], member=b)
+        self.reset_state()
+
+    def reset_state(self):
+        """SpectralModel.__init__ / WindDrivenSlabOcean.__init__ initial fields (dynamics.py:56-88, ocean.py:85-94)."""
+        e, g = self.engine, self.grid
+        zeros = np.zeros(e.shape)
+        lat_rad = np.deg2rad(g.lat_mesh)
+        for b, p in enumerate(e.params):
+            Ts = np.full(e.shape, 288.0)
+            e.set("u", zeros, b); e.set("v", zeros, b)
+            e.set("h", np.full(e.shape, float(p.H)) + 300 * (np.sin(lat_rad) ** 2), b)
+            e.set("ts", Ts, b); e.set("cloud", zeros, b); e.set("hice", zeros, b)
+            e.set("q", float(np.clip(p.q_init_rh, 0.0, 1.0)) * q_sat_host(Ts, p.p0), b)
+            for k in ("uo", "vo", "eta", "wland", "ssnow", "eflux", "pcond", "lh", "lhrel", "eday"):
+                e.set(k, zeros, b)
+            land = e._land[b] if e._land[b] is not None else np.zeros(e.shape, dtype=np.uint8)
+            e.set("sst", np.where(land == 0, Ts, 288.0), b)
+        e.set_counters(0, 0, 0)
+
+    def forcing_for(self, t):
+        (fa, sa, ca, aa), (fb, sb, cb, ab) = self.forcing.star_geometry(t)[0]
+        return Forcing(t, fa, sa, ca, aa, fb, sb, cb, ab, self.forcing.star_geometry(t)[1])
+
+    def step(self, nsteps=1):
+        fl = [self.forcing_for(self.t + k * self.dt) for k in range(nsteps)]
+        self.engine.loop_steps(fl, self.dt, **self.cfg)
+        self.t += nsteps * self.dt
+        self.step_index += nsteps
+
+    def diagnostics(self, member=0):
+        """Area-weighted means used by the reference's periodic prints (energy.py:494-538 style)."""
+        e = self.engine
+        w = np.maximum(np.cos(np.deg2rad(self.grid.lat_mesh)), 0.0)
+        ws = float(np.sum(w) + 1e-15)
+        out = {}
+        for name in ("ts", "h", "q", "cloud", "precip", "albedo", "sst"):
+            x = e.get(name, member)
+            out[name + "_mean"] = float(np.sum(x * w) / ws)
+        out["u_absmax"] = float(np.max(np.abs(e.get("u", member))))
+        return out

@@ -1,0 +1,70 @@
+"""Parity tests proper: the CUDA library (sm_100a) called through the C ABI on a real B200, checked
+against the golden vectors recorded from the reference and against the oracle (tests/qdcheck.py)."""
+import numpy as np
+import pytest
+
+import qdcheck
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from qingdai_b200._binding import default_library
+    return default_library()
+
+
+@pytest.fixture(scope="module")
+def G(golden):
+    return golden("ops_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def C(golden):
+    return golden("cores_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def L(golden):
+    return golden("loop_golden.npz")
+
+
+@pytest.mark.parametrize("tag,shape", [("a", (22, 40)), ("b", (15, 27))])
+def test_ops_vs_golden(lib, G, tag, shape):
+    qdcheck.check_ops_vs_golden(lib, G, tag, shape)
+
+
+def test_median_edge_cases(lib):
+    qdcheck.check_median_edge_cases(lib)
+
+
+@pytest.mark.parametrize("shape", [(37, 72), (181, 360)])
+def test_ops_random(lib, shape):
+    qdcheck.check_ops_random(lib, shape)
+
+
+@pytest.mark.parametrize("tag", list(qdcheck.CASES))
+def test_atmos_step(lib, C, tag):
+    qdcheck.check_atmos_step(lib, C, tag)
+
+
+@pytest.mark.parametrize("tag", list(qdcheck.CASES))
+def test_ocean_step(lib, C, tag):
+    qdcheck.check_ocean_step(lib, C, tag)
+
+
+def test_ocean_storm(lib, C):
+    qdcheck.check_ocean_storm(lib, C)
+
+
+@pytest.mark.parametrize("tag", ["base", "banded"])
+def test_loop_teacher_forced(lib, L, tag):
+    qdcheck.check_loop_teacher_forced(lib, L, tag)
+
+
+@pytest.mark.parametrize("tag", ["base", "banded"])
+def test_loop_free_running(lib, L, tag):
+    qdcheck.check_loop_free_running(lib, L, tag)

@@ -1,0 +1,65 @@
+"""CPU-only CI: run the parity checks of tests/qdcheck.py against the host-compiled check build of the
+kernel sources (tests/hostcheck).  This validates kernel LOGIC (indexing, operand order, boundary
+semantics, step orchestration through the C ABI); the same checks run on the B200 in test_gpu.py."""
+import numpy as np
+import pytest
+
+import qdcheck
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from hostcheck import library
+    return library()
+
+
+@pytest.fixture(scope="module")
+def G(golden):
+    return golden("ops_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def C(golden):
+    return golden("cores_golden.npz")
+
+
+@pytest.fixture(scope="module")
+def L(golden):
+    return golden("loop_golden.npz")
+
+
+@pytest.mark.parametrize("tag,shape", [("a", (22, 40)), ("b", (15, 27))])
+def test_ops_vs_golden(lib, G, tag, shape):
+    qdcheck.check_ops_vs_golden(lib, G, tag, shape)
+
+
+def test_median_edge_cases(lib):
+    qdcheck.check_median_edge_cases(lib)
+
+
+def test_ops_random(lib):
+    qdcheck.check_ops_random(lib)
+
+
+@pytest.mark.parametrize("tag", list(qdcheck.CASES))
+def test_atmos_step(lib, C, tag):
+    qdcheck.check_atmos_step(lib, C, tag)
+
+
+@pytest.mark.parametrize("tag", list(qdcheck.CASES))
+def test_ocean_step(lib, C, tag):
+    qdcheck.check_ocean_step(lib, C, tag)
+
+
+def test_ocean_storm(lib, C):
+    qdcheck.check_ocean_storm(lib, C)
+
+
+@pytest.mark.parametrize("tag", ["base", "banded"])
+def test_loop_teacher_forced(lib, L, tag):
+    qdcheck.check_loop_teacher_forced(lib, L, tag)
+
+
+@pytest.mark.parametrize("tag", ["base", "banded"])
+def test_loop_free_running(lib, L, tag):
+    qdcheck.check_loop_free_running(lib, L, tag)
