@@ -75,8 +75,13 @@ typedef enum { QD_M_LAND = 0, QD_M_ICE, QD_M_GLACIER, QD_M_COUNT } qd_mask_id;
 typedef enum {
   QD_R_LAT_DEG = 0, QD_R_COS, QD_R_SIN, QD_R_FCOR, QD_R_W,
   QD_R_COS_ADV_ATM,   /* max(1e-6, cos)          */
+  /* a cosine table used by the Laplacian is followed by its 1/c and 1/c^2 rows (the stencil kernels
+   * multiply by reciprocals: fp64 division is ~20 instructions on sm_100 and the step is otherwise
+   * fp64-issue bound; differences to true division are <= 1 ulp per operation) */
   QD_R_COS_ADV_HALF,  /* max(cos, 0.5)           */
+  QD_R_ICOS_HALF, QD_R_ICOS2_HALF,
   QD_R_COS_LAP_ATM,   /* max(cos, 0.2)           */
+  QD_R_ICOS_LAP_ATM, QD_R_ICOS2_LAP_ATM,
   QD_R_COS_CAP,       /* max(cos, 1e-6)          */
   QD_R_FSAFE,         /* regularised Coriolis    */
   QD_R_K4_U, QD_R_K4_V, QD_R_K4_H, QD_R_K4_Q, QD_R_K4_C,
@@ -206,7 +211,9 @@ int  qd_median_pos(qd_ctx* ctx, const double* in_dev, double empty_value, double
 int  qd_wsum(qd_ctx* ctx, const double* in_dev, double* out_host /* [B] sum(x*w) */);                    /* sync */
 /* device row tables for the operator calls above */
 const double* qd_row_dev(qd_ctx* ctx, int row_id);
-/* upload an arbitrary [nlat] row table into one of 4 user row slots, returns its device pointer */
+/* upload an arbitrary [nlat] row table into one of 6 user row slots (0/1 are used by the *_host operator
+ * forms, 2..4 hold the QD_OCEAN_K4_U/V/ETA overrides) (the library appends the 1/x and
+ * 1/x^2 rows the Laplacian kernels expect right behind it), returns its device pointer */
 const double* qd_user_row(qd_ctx* ctx, int slot, const double* rows_host);
 
 /* host-buffer convenience forms of the three jax_compat seam kernels (H2D + kernel + D2H, sync);
@@ -222,6 +229,9 @@ int  qd_atmos_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* Teq in QD_F_TEQ,
 int  qd_ocean_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* winds QD_F_U/V, Q in QD_F_QNET, ice in QD_M_ICE */
 int  qd_loop_step(qd_ctx* ctx, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps);
 int  qd_last_nsub(qd_ctx* ctx, int* out_host /* [B] */);      /* sync */
+/* 1 (default): the ocean's data-dependent sub-step loop runs as a CUDA-graph WHILE node (no host
+ * round trip); 0: host loop with one scalar read-back per step */
+int  qd_use_graphs(qd_ctx* ctx, int enable);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */

@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <string>
 
 #ifdef QD_HOST_EMU
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -22,7 +24,7 @@ void qd_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
 }
 #endif
 
-#define QD_NUSER_ROWS 4
+#define QD_NUSER_ROWS 6
 #define QD_NPART 4
 
 struct qd_route {
@@ -45,7 +47,7 @@ struct qd_ctx {
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
   double* fields; uint8_t* masks;
   double* d_part[QD_NPART]; unsigned* d_ticket;
-  unsigned* d_hist; QdSelState* d_sel;
+  unsigned* d_hist; unsigned long long* d_mingt; int sel_gx;
   qd_forcing_t* d_forcing; int forcing_cap; int* d_step_idx; double* d_hcos;
   double *d_twid, *d_spec_coef, *d_spec_out;
   double* d_stage[5];
@@ -53,6 +55,14 @@ struct qd_ctx {
   int atm_counter, oc_counter, has_cloud_eff;
   int last_nsub_max;
   QdGaussW w_sigma1, w_cloud; int w_set;
+  int* d_sub_ctr; int use_graphs;
+#ifndef QD_HOST_EMU
+  cudaStream_t cap_stream;
+  std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
+  long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
+    return 4 + (do_hyper ? 2 * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
+  }
+#endif
   char err[512];
   qd_route route;
   void* prof;
@@ -119,6 +129,7 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
 
 #ifndef QD_HOST_EMU
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
+static bool qd_prof_on(qd_ctx* c) { return c->prof && qd_prof_of(c)->on; }
 #endif
 extern "C" int qd_profile(qd_ctx* c, int enable) {
   if (!c) return QD_E_INVALID;
@@ -178,8 +189,11 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
-  c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr;
-  const size_t nrows = (size_t)(QD_R_COUNT + QD_NUSER_ROWS) * nlat;
+  c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 1;
+#ifndef QD_HOST_EMU
+  c->cap_stream = nullptr;
+#endif
+  const size_t nrows = (size_t)(QD_R_COUNT + 3 * QD_NUSER_ROWS) * nlat;
 #define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
   QD_ALLOC(c->d_rows, nrows * 8);
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
@@ -187,9 +201,22 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   QD_ALLOC(c->d_scal, (size_t)batch * QD_S_COUNT * 8);
   for (int k = 0; k < QD_NPART; ++k) QD_ALLOC(c->d_part[k], (size_t)batch * c->nblk * 8);
   QD_ALLOC(c->d_ticket, (size_t)batch * 8 * sizeof(unsigned));
-  QD_ALLOC(c->d_hist, (size_t)batch * QD_SEL_BINS * sizeof(unsigned));
-  QD_ALLOC(c->d_sel, (size_t)batch * sizeof(QdSelState));
+  QD_ALLOC(c->d_hist, (size_t)QD_SEL_PASSES * batch * QD_SEL_MAXBINS * sizeof(unsigned));
+  QD_ALLOC(c->d_mingt, (size_t)batch * sizeof(unsigned long long));
+  c->sel_gx = 1;
+#ifndef QD_HOST_EMU
+  {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select_coop, QD_SEL_THREADS, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int resident = std::max(1, per_sm * sms);
+    const int want = (c->ncell + QD_SEL_THREADS - 1) / QD_SEL_THREADS;
+    c->sel_gx = std::max(1, std::min(want, resident / batch));
+    if ((long long)c->sel_gx * batch > resident) { delete c; return QD_E_INVALID; }   // ensemble too large for one cooperative grid
+  }
+#endif
   QD_ALLOC(c->d_step_idx, sizeof(int));
+  QD_ALLOC(c->d_sub_ctr, sizeof(int));
   QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
   QD_ALLOC(c->d_twid, (size_t)2 * nlon * 8);
   QD_ALLOC(c->d_spec_coef, (size_t)batch * nlat * 2 * (nlon / 2 + 1) * 8);
@@ -212,6 +239,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   QdGeo& g = c->geo;
   g.nlat = nlat; g.nlon = nlon; g.ncell = c->ncell; g.batch = batch;
   g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
+  g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.rows = c->d_rows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
   *out = c;
@@ -230,13 +258,15 @@ extern "C" int qd_destroy(qd_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal);
   for (int k = 0; k < QD_NPART; ++k) cudaFree(c->d_part[k]);
-  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_sel); cudaFree(c->d_step_idx); cudaFree(c->d_hcos);
+  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
   cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
+  for (auto& kv : c->ocean_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
 #endif
   delete c;
   return QD_OK;
@@ -268,12 +298,18 @@ extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
   QD_CUDA(c, cudaMemcpy(out, c->d_scal, (size_t)c->batch * QD_S_COUNT * 8, cudaMemcpyDeviceToHost));
   return QD_OK;
 }
-extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
+extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + 3 * QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
+#define QD_USER_ROW(c, slot) ((c)->d_rows + (size_t)(QD_R_COUNT + 3 * (slot)) * (c)->nlat)
 extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_host) {
   if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host) return nullptr;
   cudaStreamSynchronize(c->stream);
-  double* dst = c->d_rows + (size_t)(QD_R_COUNT + slot) * c->nlat;
-  if (cudaMemcpy(dst, rows_host, (size_t)c->nlat * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  std::vector<double> tmp(3 * (size_t)c->nlat);
+  for (int j = 0; j < c->nlat; ++j) {
+    const double x = rows_host[j];
+    tmp[j] = x; tmp[c->nlat + j] = 1.0 / x; tmp[2 * (size_t)c->nlat + j] = 1.0 / (x * x);
+  }
+  double* dst = QD_USER_ROW(c, slot);
+  if (cudaMemcpy(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   return dst;
 }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
@@ -375,9 +411,20 @@ static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
 }
 // exact median of positives of x -> dst[b*stride] (and count -> cnt[b*stride])
 static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst, double* cnt, int stride) {
-  for (int pass = 0; pass < 4; ++pass) QD_K(c, k_select_hist, c->geo, x, pass, c->d_hist, c->d_sel, c->d_ticket + 0 * c->batch);
-  QD_K(c, k_select_close, c->geo, x, c->d_sel, c->d_ticket + 1 * c->batch, empty_value, dst, cnt, stride);
-  QD_CHECK_LAUNCH(c);
+  QdSelOut out; out.value = dst; out.count = cnt; out.stride = stride; out.empty_value = empty_value;
+#ifdef QD_HOST_EMU
+  qd_select_host(c->geo, x, out);
+  c->launches++;
+#else
+  QD_CUDA(c, cudaMemsetAsync(c->d_hist, 0, (size_t)QD_SEL_PASSES * c->batch * QD_SEL_MAXBINS * sizeof(unsigned), c->stream));
+  QD_CUDA(c, cudaMemsetAsync(c->d_mingt, 0xff, (size_t)c->batch * sizeof(unsigned long long), c->stream));
+  QdGeo geo = c->geo;
+  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_mingt, (void*)&out};
+  const int pi = qd_prof_begin(c, "k_select_coop");
+  QD_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_select_coop, dim3(c->sel_gx, c->batch), dim3(QD_SEL_THREADS), args, 0, c->stream));
+  qd_prof_end(c, pi);
+  c->launches++;
+#endif
   return QD_OK;
 }
 
@@ -616,6 +663,102 @@ extern "C" int qd_atmos_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
 }
 
 // ------------------------------------------------------------------------------ ocean step
+// One CFL sub-step body (ocean.py:305-444).  Launched either from a host loop (stream mode) or captured
+// once as the body of a CUDA-graph WHILE node (graph mode); the sub-step index is read from device memory.
+static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap) {
+  const double* P = c->h_prm;   // K4 overrides are shared by all ensemble members (switch-like)
+  const int ovu = P[QD_P_OC_K4_U] == P[QD_P_OC_K4_U], ovv = P[QD_P_OC_K4_V] == P[QD_P_OC_K4_V], ove = P[QD_P_OC_K4_ETA] == P[QD_P_OC_K4_ETA];
+  QdSubCtl sc{c->d_sub_ctr};
+  QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
+  Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
+  Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
+  QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+  if (do_hyper) {
+    const int ns = std::max(1, cfg->oc_k4_nsub);
+    for (int q = 0; q < ns; ++q) {
+      QdFields f = mk_fields(3);
+      f.src[0] = F(c, QD_F_X2); f.src[1] = F(c, QD_F_X3); f.src[2] = F(c, QD_F_ETA);
+      f.dst[0] = F(c, QD_F_X4); f.dst[1] = F(c, QD_F_X5); f.dst[2] = F(c, QD_F_X6);
+      QD_K(c, k_ocean_lap, c->geo, f, sc);
+      QdFields u = mk_fields(3);
+      u.src[0] = F(c, QD_F_X4); u.src[1] = F(c, QD_F_X5); u.src[2] = F(c, QD_F_X6);
+      u.dst[0] = F(c, QD_F_X2); u.dst[1] = F(c, QD_F_X3); u.dst[2] = F(c, QD_F_ETA);
+      // rows: sigma4*dx^4 (divided by sub_dt on device) or user rows 2..4 holding the QD_OCEAN_K4_* overrides
+      u.aux[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4);
+      u.aux[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4);
+      u.aux[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4);
+      u.scale[2] = 0.5;
+      QD_K(c, k_ocean_hyper, c->geo, u, sc, ns, ovu, ovv, ove);
+    }
+  }
+  if (do_shap) {
+    // optional (QD_OCEAN_SHAPIRO_N, off by default); valid when every member shares n_sub
+    double* fl[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
+    double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    int rc = op_shapiro(c, 3, fl, sx, cfg->oc_shapiro_n); if (rc) return rc;
+  }
+  QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
+  Co.ub = F(c, QD_F_X2); Co.vb = F(c, QD_F_X3); Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
+  Co.ticket = c->d_ticket + 5 * c->batch;
+  QD_K(c, k_ocean_continuity, c->geo, Co, sc);
+  QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
+  Sa.sst = F(c, QD_F_SST); Sa.ub = F(c, QD_F_X2); Sa.vb = F(c, QD_F_X3); Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
+  QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
+  QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
+  Sb.tb = F(c, QD_F_X7); Sb.ub = F(c, QD_F_X2); Sb.vb = F(c, QD_F_X3); Sb.qnet = F(c, QD_F_QNET);
+  Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
+  Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
+  Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
+  QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
+  return QD_OK;
+}
+
+#ifndef QD_HOST_EMU
+// WHILE-node graph around the sub-step body, keyed by the switches baked into the captured launches.
+static cudaGraphExec_t ocean_while_graph(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap) {
+  const unsigned long long key = ((unsigned long long)inject) | ((unsigned long long)do_hyper << 1) | ((unsigned long long)do_shap << 2) |
+                                 ((unsigned long long)(cfg->oc_has_q & 1) << 3) | ((unsigned long long)(cfg->oc_has_ice & 1) << 4) |
+                                 ((unsigned long long)(cfg->oc_k4_nsub & 0xff) << 8) | ((unsigned long long)(cfg->oc_shapiro_n & 0xff) << 16);
+  auto it = c->ocean_graphs.find(key);
+  if (it != c->ocean_graphs.end()) return it->second;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaStream_t saved = c->stream;
+  const long long saved_launches = c->launches;
+  bool ok = false;
+  do {
+    if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) break;
+    if (cudaGraphCreate(&graph, 0) != cudaSuccess) break;
+    cudaGraphConditionalHandle handle;
+    if (cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) != cudaSuccess) break;
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    if (cudaGraphAddNode(&node, graph, nullptr, 0, &np) != cudaSuccess) break;
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    if (cudaStreamBeginCaptureToGraph(c->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+    c->stream = c->cap_stream;
+    int rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap);
+    QD_LAUNCH(k_ocean_sub_advance, dim3(1), dim3(32), c->stream, c->geo, c->d_sub_ctr, handle, 1);
+    c->stream = saved;
+    cudaGraph_t dummy = nullptr;
+    if (cudaStreamEndCapture(c->cap_stream, &dummy) != cudaSuccess || rc != QD_OK) break;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; break; }
+    ok = true;
+  } while (0);
+  c->stream = saved;
+  c->launches = saved_launches;
+  cudaGetLastError();
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) exec = nullptr;
+  c->ocean_graphs[key] = exec;       // nullptr = graphs unavailable -> host loop with one read-back
+  return exec;
+}
+#endif
+
 static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   const double dt = cfg->dt;
   c->oc_counter += 1;                        // ocean.py:281
@@ -624,61 +767,34 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
   QD_K(c, k_ocean_prep, c->geo, P0);
-  QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt);
+  QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
   QD_CHECK_LAUNCH(c);
-  // data-dependent sub-step count: one small read-back per step
-  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
-  int rc = qd_get_scalars(c, s.data()); if (rc) return rc;
-  int nmax = 1;
-  for (int b = 0; b < c->batch; ++b) nmax = std::max(nmax, (int)s[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
-  c->last_nsub_max = nmax;
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
   const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
-  const double* P = c->h_prm;   // overrides are taken from member 0 (ensemble members share the switches)
-  const int ovu = P[QD_P_OC_K4_U] == P[QD_P_OC_K4_U], ovv = P[QD_P_OC_K4_V] == P[QD_P_OC_K4_V], ove = P[QD_P_OC_K4_ETA] == P[QD_P_OC_K4_ETA];
-  for (int sub = 0; sub < nmax; ++sub) {
-    QdSubCtl sc{sub, 1};
-    QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
-    Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
-    Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
-    QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
-    if (do_hyper) {
-      const int ns = std::max(1, cfg->oc_k4_nsub);
-      for (int q = 0; q < ns; ++q) {
-        QdFields f = mk_fields(3);
-        f.src[0] = F(c, QD_F_X2); f.src[1] = F(c, QD_F_X3); f.src[2] = F(c, QD_F_ETA);
-        f.dst[0] = F(c, QD_F_X4); f.dst[1] = F(c, QD_F_X5); f.dst[2] = F(c, QD_F_X6);
-        QD_K(c, k_ocean_lap, c->geo, f, sc);
-        QdFields u = mk_fields(3);
-        u.src[0] = F(c, QD_F_X4); u.src[1] = F(c, QD_F_X5); u.src[2] = F(c, QD_F_X6);
-        u.dst[0] = F(c, QD_F_X2); u.dst[1] = F(c, QD_F_X3); u.dst[2] = F(c, QD_F_ETA);
-        // rows: sigma4*dx^4 (divided by sub_dt on device) or user rows 2/3 holding constant overrides
-        u.aux[0] = ovu ? ROW(c, QD_R_COUNT + 2) : ROW(c, QD_R_OC_S4DX4);
-        u.aux[1] = ovv ? ROW(c, QD_R_COUNT + 2) : ROW(c, QD_R_OC_S4DX4);
-        u.aux[2] = ove ? ROW(c, QD_R_COUNT + 3) : ROW(c, QD_R_OC_S4DX4);
-        u.scale[2] = 0.5;
-        QD_K(c, k_ocean_hyper, c->geo, u, sc, ns, ovu, ovv, ove);
-      }
+  int rc;
+  bool launched = false;
+#ifndef QD_HOST_EMU
+  if (c->use_graphs && !qd_prof_on(c)) {
+    cudaGraphExec_t exec = ocean_while_graph(c, cfg, inject, do_hyper, do_shap);
+    if (exec) {
+      QD_CUDA(c, cudaGraphLaunch(exec, c->stream));
+      c->launches += c->ocean_body_launches(do_hyper, do_shap, cfg);      // per executed sub-step; n_sub is known only on the device
+      c->last_nsub_max = -1;
+      launched = true;
     }
-    if (do_shap) {
-      // members that are done must not be filtered again: only valid when every member shares n_sub
-      double* fl[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
-      double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
-      rc = op_shapiro(c, 3, fl, sx, cfg->oc_shapiro_n); if (rc) return rc;
+  }
+#endif
+  if (!launched) {
+    // stream mode: the data-dependent sub-step count costs one small read-back per step
+    std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+    rc = qd_get_scalars(c, s.data()); if (rc) return rc;
+    int nmax = 1;
+    for (int b = 0; b < c->batch; ++b) nmax = std::max(nmax, (int)s[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
+    c->last_nsub_max = nmax;
+    for (int sub = 0; sub < nmax; ++sub) {
+      rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap); if (rc) return rc;
+      QD_KG(c, k_ocean_sub_advance, dim3(1), dim3(32), c->geo, c->d_sub_ctr, 0, 0);
     }
-    QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
-    Co.ub = F(c, QD_F_X2); Co.vb = F(c, QD_F_X3); Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
-    Co.ticket = c->d_ticket + 5 * c->batch;
-    QD_K(c, k_ocean_continuity, c->geo, Co, sc);
-    QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
-    Sa.sst = F(c, QD_F_SST); Sa.ub = F(c, QD_F_X2); Sa.vb = F(c, QD_F_X3); Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
-    QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
-    QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
-    Sb.tb = F(c, QD_F_X7); Sb.ub = F(c, QD_F_X2); Sb.vb = F(c, QD_F_X3); Sb.qnet = F(c, QD_F_QNET);
-    Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
-    Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
-    Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
-    QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
   }
   QdOcPolarArgs Po; memset(&Po, 0, sizeof(Po));
   Po.sst = F(c, QD_F_SST); Po.uo = F(c, QD_F_UO); Po.vo = F(c, QD_F_VO); Po.ts_atm = F(c, QD_F_TS);
@@ -693,6 +809,7 @@ extern "C" int qd_ocean_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   QD_BOUND(c);
   return ocean_core(c, cfg, 0);
 }
+extern "C" int qd_use_graphs(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->use_graphs = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_last_nsub(qd_ctx* c, int* out) {
   if (!c || !out) return QD_E_INVALID;
   std::vector<double> s((size_t)c->batch * QD_S_COUNT);

@@ -9,10 +9,12 @@
 #pragma once
 #include "qd_phys.cuh"
 
-struct QdSubCtl { int sub; int active; };    // active=0: not an ocean sub-step kernel (no early exit)
+// The current sub-step index lives in device memory (reset by k_ocean_nsub, advanced by
+// k_ocean_sub_advance) so that the sub-step body can be the body of a CUDA-graph WHILE node.
+struct QdSubCtl { const int* ctr; };
 
 QD_HD bool qd_sub_done(const QdGeo& g, int b, const QdSubCtl& sc) {
-  return sc.active && (sc.sub >= (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
+  return *sc.ctr >= (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB];
 }
 
 // Wind stress (ocean.py:285-290) + the two maxima behind n_sub (ocean.py:298-299).
@@ -55,8 +57,9 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs
 }
 
 // n_sub = clip(ceil(max(c, uadv) * (dt / max(1e-12, dx_min)) / max(1e-3, cfl)), 1, 500)  (ocean.py:297-303)
-__global__ void k_ocean_nsub(QdGeo g, double dt) {
+__global__ void k_ocean_nsub(QdGeo g, double dt, int* sub_ctr) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *sub_ctr = 0;
   if (b >= g.batch) return;
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   double* S = g.scal + (size_t)b * QD_S_COUNT;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_lap(QdGeo g, QdFields f, Q
   const double* cosr = qd_row(g, QD_R_COS_ADV_HALF);
   for (int k = 0; k < f.n; ++k) {
     QdCleanLoad F{f.src[k] + off, g.nlon};
-    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g, cosr);
   }
 }
 // aux[k] = row table (sigma4*dx^4, or a constant row for QD_OCEAN_K4_* overrides with over[k]=1)
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_hyper(QdGeo g, QdFields f,
   const int over[3] = {over0, over1, over2};
   for (int k = 0; k < f.n; ++k) {
     QdCleanLoad L{f.src[k] + off, g.nlon};
-    const double L2 = qd_lap_cell(L, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    const double L2 = qd_lap_cell(L, j, i, g, cosr);
     double k4 = f.aux[k][j];
     if (!over[k]) { k4 = k4 / fmax(1e-12, sub_dt); k4 = f.scale[k] * k4; }
     const double cur = qd_nan_to_num(f.dst[k][off + idx]);
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   double T = A.tb[c];
   if (P[QD_P_OC_K_H] > 0.0) {
     QdCleanLoad F{A.tb + off, nlon};
-    const double lap = qd_lap_cell(F, j, i, nlat, nlon, g.dlat, g.dlon_sq, g.a_sq, qd_row(g, QD_R_COS_ADV_HALF));
+    const double lap = qd_lap_cell(F, j, i, g, qd_row(g, QD_R_COS_ADV_HALF));
     T = qd_nan_to_num(T) + sub_dt * P[QD_P_OC_K_H] * lap;
   }
   const bool ocean = A.land[c] != 1;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   }
   A.uo[c] = uo;
   A.vo[c] = vo;
-  const bool last = sc.active ? (sc.sub == (int)S[QD_S_NSUB] - 1) : true;
+  const bool last = (*sc.ctr == (int)S[QD_S_NSUB] - 1);
   if (last && j > 0 && j < nlat - 1) {
     T = qd_clip(T, P[QD_P_OC_TS_MIN], P[QD_P_OC_TS_MAX]);
     if (A.inject && ocean && !ice) A.ts_atm[c] = T;
@@ -308,3 +311,22 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarAr
     if (A.inject && land[k] != 1 && !ice) A.ts_atm[base + k] = t;
   }
 }
+
+// End of one sub-step: advance the device-side counter and, inside a CUDA graph, tell the WHILE node
+// whether any ensemble member still has sub-steps to do.
+#if !QD_EMU
+__global__ void k_ocean_sub_advance(QdGeo g, int* sub_ctr, cudaGraphConditionalHandle handle, int use_handle) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int s = *sub_ctr + 1;
+  *sub_ctr = s;
+  int nmax = 1;
+  for (int b = 0; b < g.batch; ++b) { const int n = (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB]; if (n > nmax) nmax = n; }
+  if (use_handle) cudaGraphSetConditional(handle, s < nmax ? 1u : 0u);
+}
+#else
+__global__ void k_ocean_sub_advance(QdGeo g, int* sub_ctr, unsigned long long handle, int use_handle) {
+  (void)g; (void)handle; (void)use_handle;
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  *sub_ctr = *sub_ctr + 1;
+}
+#endif

@@ -17,6 +17,7 @@
 struct QdGeo {
   int nlat, nlon, ncell, batch;
   double a, dlat, dlon, a_sq, dlon_sq;
+  double inv_dlat, inv_2dlat, inv_dlon_sq, inv_a_sq;      // reciprocals used by the stencil kernels
   const double* rows;    // [QD_R_COUNT + 4 user][nlat]
   const double* cols;    // [QD_C_COUNT][nlon]
   const double* prm;     // [B][QD_P_COUNT]
@@ -53,25 +54,28 @@ struct QdCleanLoad {
   QD_HD double operator()(int jj, int ii) const { return qd_nan_to_num(p[(size_t)jj * nlon + ii]); }
 };
 
+// `c` points at a cosine row table that is followed by its 1/c and 1/c^2 rows (QD_R_*COS* layout).
 template <class Acc>
-QD_HD double qd_lap_cell(const Acc& F, int j, int i, int nlat, int nlon, double dphi, double dlmb_sq,
-                         double a_sq, const double* c) {
+QD_HD double qd_lap_cell(const Acc& F, int j, int i, const QdGeo& g, const double* c) {
+  const int nlat = g.nlat, nlon = g.nlon;
+  const double* ic = c + nlat;
+  const double* ic2 = c + 2 * nlat;
   const int jm = j > 0 ? j - 1 : 0, jp = j < nlat - 1 ? j + 1 : nlat - 1;
-  // G(jj): np.gradient(F, dphi, axis=0) at row jj
+  // G(jj): np.gradient(F, dphi, axis=0) at row jj (edge_order=1)
   auto G = [&](int jj) -> double {
-    if (jj == 0) return (F(1, i) - F(0, i)) / dphi;
-    if (jj == nlat - 1) return (F(nlat - 1, i) - F(nlat - 2, i)) / dphi;
-    return (F(jj + 1, i) - F(jj - 1, i)) / (2.0 * dphi);
+    if (jj == 0) return (F(1, i) - F(0, i)) * g.inv_dlat;
+    if (jj == nlat - 1) return (F(nlat - 1, i) - F(nlat - 2, i)) * g.inv_dlat;
+    return (F(jj + 1, i) - F(jj - 1, i)) * g.inv_2dlat;
   };
   double gphi;
-  if (j == 0) gphi = (c[1] * G(1) - c[0] * G(0)) / dphi;
-  else if (j == nlat - 1) gphi = (c[j] * G(j) - c[j - 1] * G(j - 1)) / dphi;
-  else gphi = (c[jp] * G(jp) - c[jm] * G(jm)) / (2.0 * dphi);
-  const double term_phi = (1.0 / c[j]) * gphi;
+  if (j == 0) gphi = (c[1] * G(1) - c[0] * G(0)) * g.inv_dlat;
+  else if (j == nlat - 1) gphi = (c[j] * G(j) - c[j - 1] * G(j - 1)) * g.inv_dlat;
+  else gphi = (c[jp] * G(jp) - c[jm] * G(jm)) * g.inv_2dlat;
+  const double term_phi = ic[j] * gphi;
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
-  const double d2 = ((F(j, ip) - 2.0 * F(j, i)) + F(j, im)) / dlmb_sq;
-  const double term_lam = d2 / (c[j] * c[j]);
-  return (term_phi + term_lam) / a_sq;
+  const double d2 = ((F(j, ip) - 2.0 * F(j, i)) + F(j, im)) * g.inv_dlon_sq;
+  const double term_lam = d2 * ic2[j];
+  return (term_phi + term_lam) * g.inv_a_sq;
 }
 
 // out[k] = lap(src[k]) for k < n fields; aux[0] = cosine row table (floored by the caller).
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_laplacian(QdGeo g, QdFields f, c
   if (!active) return;
   for (int k = 0; k < f.n; ++k) {
     QdCleanLoad F{f.src[k] + off, g.nlon};
-    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    f.dst[k][off + idx] = qd_lap_cell(F, j, i, g, cosr);
   }
 }
 
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_hyper_update(QdGeo g, QdFields f
   if (!active) return;
   for (int k = 0; k < f.n; ++k) {
     QdCleanLoad L{f.src[k] + off, g.nlon};
-    const double L2 = qd_lap_cell(L, j, i, g.nlat, g.nlon, g.dlat, g.dlon_sq, g.a_sq, cosr);
+    const double L2 = qd_lap_cell(L, j, i, g, cosr);
     double k4 = f.aux[k][j];
     if (k4_div > 0.0) k4 = k4 / k4_div;        // ocean.py:347  sigma4*dx^4 / max(1e-12, sub_dt)
     k4 = f.scale[k] * k4;                      // 0.5*k4_map etc. (dynamics.py:568-570, ocean.py:352)
@@ -302,102 +306,5 @@ __global__ void __launch_bounds__(QD_THREADS) k_wsum(QdGeo g, const double* x, c
   if (qd_block_sum<0>(v, &tot)) part[blockIdx.x] = tot;
   if (qd_block_is_last(ticket + b, gridDim.x)) {
     if (qd_final_sum<1>(part, gridDim.x, &tot)) out[(size_t)b * out_stride] = tot;
-  }
-}
-
-// ------------------------------------------------------------------------------ exact median of positives
-// np.median(x[x>0]) (physics.py:298-301, run_simulation.py:1872-1873, dynamics.py:344-348) as a 4-pass
-// MSD radix select on the IEEE bit pattern (positive doubles order like uint64), 16 bits per pass,
-// plus one closing pass that finds the upper middle element when the count is even.
-struct QdSelState {          // per member
-  unsigned long long prefix; // bits decided so far
-  unsigned long long rank;   // 0-based rank still to find inside the prefix bucket
-  unsigned long long count;  // number of positives
-  unsigned long long cnt_le; // closing pass: #(x <= L)
-  unsigned long long min_gt; // closing pass: bit pattern of min(x > L)
-  double lower;              // value at the lower-middle rank
-  double result;
-};
-#define QD_SEL_BINS 65536
-#define QD_SEL_CHUNKS 256
-
-__global__ void __launch_bounds__(QD_THREADS) k_select_hist(QdGeo g, const double* x, int pass, unsigned* hist,
-                                                           QdSelState* st, unsigned* ticket) {
-  QD_CELL_PROLOGUE(g)
-  const int shift = 48 - 16 * pass;
-  unsigned* h = hist + (size_t)b * QD_SEL_BINS;
-  if (active) {
-    const double v = x[off + idx];
-    if (v > 0.0) {
-      const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-      bool match = true;
-      if (pass > 0) match = (key >> (shift + 16)) == (st[b].prefix >> (shift + 16));
-      if (match) atomicAdd(h + ((key >> shift) & 0xffffull), 1u);
-    }
-  }
-  if (qd_block_is_last(ticket + b, gridDim.x)) {
-    __shared__ unsigned long long chunk[QD_SEL_CHUNKS];
-    QD_BLOCK_LAST_FOR(c, QD_SEL_CHUNKS) {
-      unsigned long long s = 0;
-      for (int k = 0; k < QD_SEL_BINS / QD_SEL_CHUNKS; ++k) s += QD_LDCG(h + c * (QD_SEL_BINS / QD_SEL_CHUNKS) + k);
-      chunk[c] = s;
-    }
-    __syncthreads();
-    QD_BLOCK_LAST_ONE {
-      QdSelState s = st[b];
-      if (pass == 0) {
-        unsigned long long n = 0;
-        for (int c = 0; c < QD_SEL_CHUNKS; ++c) n += chunk[c];
-        s.count = n; s.prefix = 0; s.rank = n ? (n - 1) / 2 : 0;
-      }
-      if (s.count > 0) {
-        unsigned long long cum = 0;
-        int c = 0;
-        for (; c < QD_SEL_CHUNKS - 1; ++c) { if (cum + chunk[c] > s.rank) break; cum += chunk[c]; }
-        int k = c * (QD_SEL_BINS / QD_SEL_CHUNKS);
-        const int kend = k + QD_SEL_BINS / QD_SEL_CHUNKS - 1;
-        for (; k < kend; ++k) { const unsigned long long hk = QD_LDCG(h + k); if (cum + hk > s.rank) break; cum += hk; }
-        s.prefix |= ((unsigned long long)k) << shift;
-        s.rank -= cum;
-        if (pass == 3) s.lower = __longlong_as_double((long long)s.prefix);
-      }
-      s.cnt_le = 0; s.min_gt = ~0ull;
-      st[b] = s;
-    }
-    __syncthreads();
-    QD_BLOCK_LAST_FOR(k, QD_SEL_BINS) { h[k] = 0; }
-  }
-}
-__global__ void __launch_bounds__(QD_THREADS) k_select_close(QdGeo g, const double* x, QdSelState* st,
-                                                            unsigned* ticket, double empty_value,
-                                                            double* out, double* cnt_out, int out_stride) {
-  QD_CELL_PROLOGUE(g)
-  const double L = st[b].lower;
-  const bool any = st[b].count > 0;
-  if (active && any) {
-    const double v = x[off + idx];
-    if (v > 0.0) {
-      if (v <= L) atomicAdd(&st[b].cnt_le, 1ull);
-      else atomicMin(&st[b].min_gt, (unsigned long long)__double_as_longlong(v));
-    }
-  }
-  if (qd_block_is_last(ticket + b, gridDim.x)) {
-    QD_BLOCK_LAST_ONE {
-      QdSelState s;
-      s.count = st[b].count; s.lower = st[b].lower;
-      s.cnt_le = QD_LDCG(&st[b].cnt_le); s.min_gt = QD_LDCG(&st[b].min_gt);
-      double r = empty_value;
-      if (s.count > 0) {
-        if (s.count & 1ull) r = s.lower;
-        else {
-          const unsigned long long ku = s.count / 2;          // 0-based upper-middle rank
-          const double U = (s.cnt_le > ku) ? s.lower : __longlong_as_double((long long)s.min_gt);
-          r = (s.lower + U) / 2.0;                            // np.mean of the two middle values
-        }
-      }
-      st[b].result = r;
-      out[(size_t)b * out_stride] = r;
-      if (cnt_out) cnt_out[(size_t)b * out_stride] = (double)s.count;
-    }
   }
 }

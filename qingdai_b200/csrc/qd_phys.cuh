@@ -6,6 +6,7 @@
 // (medians, area sums, stencils of freshly written fields) allow.
 #pragma once
 #include "qd_ops.cuh"
+#include "qd_select.cuh"
 
 // ------------------------------------------------------------------------------ humidity (humidity.py)
 QD_HD double qd_qsat(double T, double p0) {                       // humidity.py:85-101

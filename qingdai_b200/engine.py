@@ -61,6 +61,10 @@ def row_tables(nlat, nlon, p: QDParams, dt):
     rows[R["cos_adv_atm"]] = np.maximum(1e-6, cos)                     # dynamics.py:104
     rows[R["cos_adv_half"]] = np.maximum(cos, 0.5)                     # ocean.py:82, run_simulation.py:1145
     rows[R["cos_lap_atm"]] = np.maximum(cos, 0.2)                      # dynamics.py:164
+    for base in ("half", "lap_atm"):                                   # reciprocal rows for the stencil kernels
+        c_ = rows[R["cos_adv_half" if base == "half" else "cos_lap_atm"]]
+        rows[R["icos_" + base]] = 1.0 / c_
+        rows[R["icos2_" + base]] = 1.0 / (c_ ** 2)
     rows[R["cos_cap"]] = np.maximum(cos, 1e-6)                         # dynamics.py:490, grid.py:52
     f_min = 2.0 * const.PLANET_OMEGA * np.sin(np.deg2rad(5.0))         # dynamics.py:516-518
     sgn = np.where(f >= 0.0, 1.0, -1.0)
@@ -240,10 +244,18 @@ class Engine:
         self._chk(self.lib.qd_set_rows(self.ctx, _ptr(rows)), "qd_set_rows")
         pv = self._param_block()
         self._chk(self.lib.qd_set_params(self.ctx, _ptr(pv)), "qd_set_params")
+        p = self.params[0]
+        for slot, ov in ((2, p.oc_k4_u), (3, p.oc_k4_v), (4, p.oc_k4_eta)):      # ocean.py:350-352
+            if ov is not None:
+                self._user_row(slot, np.full(self.nlat, float(ov)))
 
     def set_params(self, params):
         self.params = list(params) if isinstance(params, (list, tuple)) else [params] * self.batch
         self.refresh_params()
+
+    def use_graphs(self, enable=True):
+        """Ocean sub-step loop as a CUDA-graph WHILE node (default) or as a host loop with a read-back."""
+        self._chk(self.lib.qd_use_graphs(self.ctx, int(bool(enable))), "qd_use_graphs")
 
     def sync(self):
         self._chk(self.lib.qd_synchronize(self.ctx), "qd_synchronize")

@@ -400,6 +400,63 @@ def gen_loop():
     print("loop_golden.npz:", len(out), "arrays")
 
 
+def gen_routing():
+    """Network from the reference's own builder (scripts/generate_hydrology_maps.py:85-273) on a small
+    procedural elevation, then pygcm.routing.RiverRouting (unmodified, fed through an in-memory stand-in
+    for netCDF4.Dataset) driven for several events with random runoff / precip / evaporation."""
+    import scripts.generate_hydrology_maps as hm
+    import pygcm.routing as routing
+    from pygcm.grid import SphericalGrid
+    from pygcm.topography import generate_elevation_map, create_land_sea_mask_from_elevation
+    out = {}
+    set_env()
+    for tag, (nlat, nlon) in {"r1": (25, 48), "r2": (31, 60)}.items():
+        grid = SphericalGrid(nlat, nlon)
+        with quiet():
+            elev = generate_elevation_map(grid, seed=11 + nlat)
+            land, sea = create_land_sea_mask_from_elevation(elev, grid, target_land_frac=0.45)
+            elev = elev - sea
+            filled = hm.pit_fill(elev.copy(), land.astype(np.uint8), max_iters=200, eps=1e-3)
+            flow_to = hm.compute_flow_to_index(grid, filled, land)
+            lake_mask, lake_id, n_lakes = hm.identify_lakes(flow_to, land)
+            outlet = hm.compute_lake_outlets(grid, filled, lake_mask, lake_id, land) if n_lakes > 0 else None
+            order = hm.topo_sort_flow_order(flow_to, land)
+        net = {"land_mask": land.astype(np.uint8), "flow_to_index": flow_to.astype(np.int32),
+               "flow_order": order.astype(np.int32), "lake_mask": lake_mask.astype(np.uint8), "lake_id": lake_id.astype(np.int32)}
+        if n_lakes > 0:
+            net["lake_outlet_index"] = outlet.astype(np.int32)
+        path = f"/virtual/{tag}.nc"
+        MemDataset.store[path] = net
+        for k, v in net.items():
+            out[f"{tag}_{k}"] = v
+        out[f"{tag}_n_lakes"] = np.array(n_lakes)
+        out[f"{tag}_elev_filled"] = filled
+        out[f"{tag}_elev_in"] = elev
+        rng = np.random.default_rng(5)
+        dt, nsub = 1800.0, 4                                  # dt_hydro = 2 h -> event every 4 steps
+        with mock.patch.object(routing, "Dataset", MemDataset), mock.patch.object(routing.os.path, "exists", lambda p: True), quiet():
+            rr = routing.RiverRouting(grid, path, dt_hydro_hours=2.0, diag=False)
+            ev = 0
+            for step in range(12):
+                R = np.where(land == 1, rng.uniform(0, 2e-5, (nlat, nlon)), 0.0)
+                P = rng.uniform(0, 5e-5, (nlat, nlon))
+                E = rng.uniform(0, 4e-5, (nlat, nlon))
+                out[f"{tag}_R{step}"], out[f"{tag}_P{step}"], out[f"{tag}_E{step}"] = R, P, E
+                rr.step(R, dt, precip_flux=P, evap_flux=E)
+                if (step + 1) % nsub == 0:
+                    d = rr.diagnostics()
+                    out[f"{tag}_ev{ev}_flow"] = d["flow_accum_kgps"].copy()
+                    out[f"{tag}_ev{ev}_ocean"] = np.array(d["ocean_inflow_kgps"])
+                    out[f"{tag}_ev{ev}_err"] = np.array(d["mass_closure_error_kg"])
+                    if d["lake_volume_kg"] is not None:
+                        out[f"{tag}_ev{ev}_lake"] = d["lake_volume_kg"].copy()
+                    ev += 1
+        out[f"{tag}_dt"] = np.array(dt)
+        print(tag, "land", int(land.sum()), "lakes", n_lakes, "ocean inflow", float(out[f"{tag}_ev2_ocean"]))
+    np.savez_compressed(os.path.join(OUT, "routing_golden.npz"), **out)
+    print("routing_golden.npz:", len(out), "arrays")
+
+
 def main():
     _install_stubs()
     which = sys.argv[1:] or ["ops", "cores", "loop"]

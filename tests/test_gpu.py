@@ -68,3 +68,23 @@ def test_loop_teacher_forced(lib, L, tag):
 @pytest.mark.parametrize("tag", ["base", "banded"])
 def test_loop_free_running(lib, L, tag):
     qdcheck.check_loop_free_running(lib, L, tag)
+
+
+def test_loop_energy_branch(lib):
+    qdcheck.check_loop_energy_branch(lib)
+
+
+def test_dropin_classes(lib, C):
+    qdcheck.check_dropin_classes(lib, C)
+
+
+def test_jax_compat_seam(lib, G):
+    qdcheck.check_jax_compat_seam(lib, G)
+
+
+def test_graph_and_stream_modes_agree_bitwise(lib, C):
+    """The CUDA-graph WHILE loop and the host loop run the same kernels: results must be bit-identical."""
+    a = qdcheck.check_ocean_storm(lib, C, graphs=True)
+    b = qdcheck.check_ocean_storm(lib, C, graphs=False)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k

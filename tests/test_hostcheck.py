@@ -63,3 +63,15 @@ def test_loop_teacher_forced(lib, L, tag):
 @pytest.mark.parametrize("tag", ["base", "banded"])
 def test_loop_free_running(lib, L, tag):
     qdcheck.check_loop_free_running(lib, L, tag)
+
+
+def test_loop_energy_branch(lib):
+    qdcheck.check_loop_energy_branch(lib)
+
+
+def test_dropin_classes(lib, C):
+    qdcheck.check_dropin_classes(lib, C)
+
+
+def test_jax_compat_seam(lib, G):
+    qdcheck.check_jax_compat_seam(lib, G)
