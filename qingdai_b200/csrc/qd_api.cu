@@ -37,6 +37,7 @@ struct qd_route {
   int *d_ocean_list = nullptr; long long n_ocean = 0;     // ocean-draining cells in flow_order order
   int *d_lake_list = nullptr, *d_lake_of = nullptr; long long n_lake_store = 0;
   unsigned char* d_in_order = nullptr;
+  unsigned char* d_land = nullptr;                  // the NETWORK's land mask (routing.py:112,232)
   double *d_buffer = nullptr, *d_mass = nullptr, *d_after = nullptr, *d_out = nullptr;
 };
 
@@ -248,7 +249,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 
 static void qd_route_free(qd_route& r) {
   cudaFree(r.d_level_cells); cudaFree(r.d_don_off); cudaFree(r.d_don); cudaFree(r.d_late_off); cudaFree(r.d_late);
-  cudaFree(r.d_ocean_list); cudaFree(r.d_lake_list); cudaFree(r.d_lake_of); cudaFree(r.d_in_order);
+  cudaFree(r.d_ocean_list); cudaFree(r.d_lake_list); cudaFree(r.d_lake_of); cudaFree(r.d_in_order); cudaFree(r.d_land);
   cudaFree(r.d_buffer); cudaFree(r.d_mass); cudaFree(r.d_after); cudaFree(r.d_out);
   r = qd_route();
 }
@@ -889,7 +890,7 @@ extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcin
     if ((rc = atmos_core(c, cfg, 1))) return rc;
     if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
     if (cfg->with_routing && c->route.ready) {
-      QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), M(c, QD_M_LAND), c->route.d_buffer, cfg->dt);
+      QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, cfg->dt);
     }
     QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
   }

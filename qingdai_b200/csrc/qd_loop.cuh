@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_route_accumulate(QdGeo g, const 
   QD_CELL_PROLOGUE(g)
   if (!active) return;
   const size_t c = off + idx;
-  const double incr = (land[c] == 1) ? rland[c] * qd_row(g, QD_R_AREA)[j] * dt : 0.0;
+  const double incr = (land[idx] == 1) ? rland[c] * qd_row(g, QD_R_AREA)[j] * dt : 0.0;   // network mask, shared by members
   buffer[c] = buffer[c] + incr;
 }
 

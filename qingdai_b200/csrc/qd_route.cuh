@@ -136,6 +136,7 @@ extern "C" int qd_route_setup(qd_ctx* c, int n_order, const int64_t* flow_order,
   if ((rc = up_vec(c, &R.d_lake_list, lake_list))) return rc;
   if ((rc = up_vec(c, &R.d_lake_of, lake_of))) return rc;
   if ((rc = up_vec(c, &R.d_in_order, in_order))) return rc;
+  { std::vector<unsigned char> lv(land, land + n); if ((rc = up_vec(c, &R.d_land, lv))) return rc; }
   const size_t fb = (size_t)c->batch * n * 8;
   QD_CUDA(c, cudaMalloc((void**)&R.d_buffer, fb)); QD_CUDA(c, cudaMemset(R.d_buffer, 0, fb));
   QD_CUDA(c, cudaMalloc((void**)&R.d_mass, (size_t)n * 8));
@@ -151,7 +152,7 @@ extern "C" int qd_route_accumulate(qd_ctx* c, double dt) {
   if (!c) return QD_E_INVALID;
   QD_BOUND(c);
   if (!c->route.ready) return qd_fail(c, QD_E_STATE, "qd_route_setup was not called", cudaSuccess);
-  QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), M(c, QD_M_LAND), c->route.d_buffer, dt);
+  QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, dt);
   QD_CHECK_LAUNCH(c);
   return QD_OK;
 }

@@ -88,3 +88,8 @@ def test_graph_and_stream_modes_agree_bitwise(lib, C):
     b = qdcheck.check_ocean_storm(lib, C, graphs=False)
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_routing(lib, golden, tag):
+    qdcheck.check_routing(lib, golden("routing_golden.npz"), tag)

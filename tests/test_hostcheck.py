@@ -75,3 +75,8 @@ def test_dropin_classes(lib, C):
 
 def test_jax_compat_seam(lib, G):
     qdcheck.check_jax_compat_seam(lib, G)
+
+
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_routing(lib, golden, tag):
+    qdcheck.check_routing(lib, golden("routing_golden.npz"), tag)
