@@ -4,6 +4,7 @@
 // (medians, renormalisation sums, the weak-humidity fallback, the ocean's CFL sub-step count)
 // stays on the device in the per-member scalar table and is consumed by later kernels.
 #include "qd_loop.cuh"
+#include "qd_hyper4.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -15,12 +16,13 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 void qd_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
   gridDim = grid; blockDim = block;
-  for (unsigned by = 0; by < grid.y; ++by)
-    for (unsigned bx = 0; bx < grid.x; ++bx) {
-      blockIdx = dim3(bx, by, 0);
-      for (unsigned ty = 0; ty < block.y; ++ty)
-        for (unsigned tx = 0; tx < block.x; ++tx) { threadIdx = dim3(tx, ty, 0); body(); }
-    }
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        blockIdx = dim3(bx, by, bz);
+        for (unsigned ty = 0; ty < block.y; ++ty)
+          for (unsigned tx = 0; tx < block.x; ++tx) { threadIdx = dim3(tx, ty, 0); body(); }
+      }
 }
 #endif
 
@@ -61,7 +63,7 @@ struct qd_ctx {
   cudaStream_t cap_stream;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
-    return 4 + (do_hyper ? 2 * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
+    return 4 + (do_hyper ? std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
   }
 #endif
   char err[512];
@@ -347,21 +349,37 @@ static int op_laplacian(qd_ctx* c, int n, const double* const* src, double* cons
   QD_CHECK_LAUNCH(c);
   return QD_OK;
 }
-// n fields in place: F <- F - k4*lap(lap F)*sub, repeated nsub times (dynamics.py:205-212)
+// Fused del^4 (csrc/qd_hyper4.cuh): n fields, src[k] -> dst[k] (out of place), nsub sub-divisions
+// ping-ponging between the two buffer sets; returns in *final_in_dst whether the result ended in dst.
+static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
+  const int tiles_i = (c->nlon + QD_H4_TI - 1) / QD_H4_TI;
+  const long long blocks32 = (long long)tiles_i * ((c->nlat + 31) / 32) * c->batch * H.n;
+  if (blocks32 >= 2 * 148) {
+    QD_KG(c, k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_THREADS), c->geo, H);
+  } else {
+    QD_KG(c, k_hyper4_tile<8>, dim3(tiles_i * ((c->nlat + 7) / 8), c->batch, H.n), dim3(QD_THREADS), c->geo, H);
+  }
+  return QD_OK;
+}
 static int op_hyper(qd_ctx* c, int n, double* const* fld, double* const* scratch, const double* const* k4rows,
-                    const double* scale, double dt, int nsub, const double* cosr) {
+                    const double* scale, double dt, int nsub, const double* cosr, bool* final_in_scratch) {
+  if (final_in_scratch) *final_in_scratch = false;
   if (dt <= 0.0 || n <= 0) return QD_OK;
   const int ns = nsub > 1 ? nsub : 1;
-  const double sub = dt / ns;
+  bool in_scratch = false;
   for (int s = 0; s < ns; ++s) {
-    QdFields f = mk_fields(n);
-    for (int k = 0; k < n; ++k) { f.src[k] = fld[k]; f.dst[k] = scratch[k]; }
-    QD_K(c, k_laplacian, c->geo, f, cosr);
-    QdFields u = mk_fields(n);
-    for (int k = 0; k < n; ++k) { u.src[k] = scratch[k]; u.dst[k] = fld[k]; u.aux[k] = k4rows[k]; u.scale[k] = scale ? scale[k] : 1.0; }
-    QD_K(c, k_hyper_update, c->geo, u, cosr, sub, 0.0);
+    QdHyper4Args H; memset(&H, 0, sizeof(H));
+    H.n = n; H.cosr = cosr; H.dt = dt; H.nsub = ns; H.ocean = 0; H.sc.ctr = nullptr;
+    for (int k = 0; k < n; ++k) {
+      H.src[k] = in_scratch ? scratch[k] : fld[k];
+      H.dst[k] = in_scratch ? fld[k] : scratch[k];
+      H.k4rows[k] = k4rows[k]; H.scale[k] = scale ? scale[k] : 1.0; H.raw_k4[k] = 1;
+    }
+    int rc = launch_hyper4(c, H); if (rc) return rc;
+    in_scratch = !in_scratch;
   }
   QD_CHECK_LAUNCH(c);
+  if (final_in_scratch) *final_in_scratch = in_scratch;
   return QD_OK;
 }
 static int op_shapiro(qd_ctx* c, int n, double* const* fld, double* const* scratch, int passes) {
@@ -438,7 +456,11 @@ extern "C" int qd_laplacian(qd_ctx* c, const double* in, double* out, const doub
 extern "C" int qd_hyperdiffuse(qd_ctx* c, double* f, double* scratch, const double* k4rows, double k4_scale, double dt, int nsub, const double* cosr) {
   if (!c || !f || !scratch || !k4rows || !cosr) return QD_E_INVALID;
   double* fl[1] = {f}; double* sc[1] = {scratch}; const double* kr[1] = {k4rows}; double s[1] = {k4_scale};
-  return op_hyper(c, 1, fl, sc, kr, s, dt, nsub, cosr);
+  bool in_scratch = false;
+  int rc = op_hyper(c, 1, fl, sc, kr, s, dt, nsub, cosr, &in_scratch);
+  if (rc) return rc;
+  if (in_scratch) QD_CUDA(c, cudaMemcpyAsync(f, scratch, (size_t)c->batch * c->ncell * 8, cudaMemcpyDeviceToDevice, c->stream));
+  return QD_OK;
 }
 extern "C" int qd_advect(qd_ctx* c, const double* in, const double* u, const double* v, double* out, double dt, const double* cosr) {
   if (!c || !in || !u || !v || !out || !cosr) return QD_E_INVALID;
@@ -605,48 +627,61 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   AM.ts = F(c, QD_F_TS); AM.q = F(c, QD_F_Q); AM.u = F(c, QD_F_U); AM.v = F(c, QD_F_V); AM.dt = dt;
   QD_K(c, k_advect_momentum, c->geo, AM);
 
+  // From here on u, v, h, q, cloud may live in scratch slots (the fused del^4 kernel is out of place);
+  // cur[] tracks where each field currently is, k_tail writes everything back to its home slot.
   const double* cos_lap = ROW(c, QD_R_COS_LAP_ATM);
+  enum { iU, iV, iH, iQ, iC };
+  double* home[5] = {F(c, QD_F_U), F(c, QD_F_V), F(c, QD_F_H), F(c, QD_F_Q), F(c, QD_F_CLOUD)};
+  double* alt[5] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6), F(c, QD_F_X7), F(c, QD_F_X8)};
+  double* cur[5] = {home[0], home[1], home[2], home[3], home[4]};
+  auto other = [&](int k) { return cur[k] == home[k] ? alt[k] : home[k]; };
   if (cfg->diff_enable && (sc % std::max(1, cfg->diff_every) == 0)) {
-    double* uvh[3] = {F(c, QD_F_U), F(c, QD_F_V), F(c, QD_F_H)};
-    double* sx[5] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6), F(c, QD_F_X7), F(c, QD_F_X8)};
     const double* kr[5] = {ROW(c, QD_R_K4_U), ROW(c, QD_R_K4_V), ROW(c, QD_R_K4_H), ROW(c, QD_R_K4_Q), ROW(c, QD_R_K4_C)};
+    auto run = [&](const int* ids, int n, int nsub) -> int {
+      double* fl[5]; double* ot[5]; const double* kk[5];
+      for (int k = 0; k < n; ++k) { fl[k] = cur[ids[k]]; ot[k] = other(ids[k]); kk[k] = kr[ids[k]]; }
+      bool moved = false;
+      int rc = op_hyper(c, n, fl, ot, kk, nullptr, dt, nsub, cos_lap, &moved);
+      if (rc) return rc;
+      if (moved) for (int k = 0; k < n; ++k) cur[ids[k]] = ot[k];
+      return QD_OK;
+    };
+    int ids[5] = {iU, iV, iH, 0, 0}; int n = 3, rc;
     if (cfg->k4_nsub <= 1) {
-      double* fl[5] = {uvh[0], uvh[1], uvh[2], nullptr, nullptr};
-      const double* kk[5] = {kr[0], kr[1], kr[2], nullptr, nullptr};
-      int n = 3;
-      if (cfg->apply_q) { fl[n] = F(c, QD_F_Q); kk[n] = kr[3]; ++n; }
-      if (cfg->apply_cloud) { fl[n] = F(c, QD_F_CLOUD); kk[n] = kr[4]; ++n; }
-      int rc = op_hyper(c, n, fl, sx, kk, nullptr, dt, 1, cos_lap); if (rc) return rc;
+      if (cfg->apply_q) ids[n++] = iQ;
+      if (cfg->apply_cloud) ids[n++] = iC;
+      if ((rc = run(ids, n, 1))) return rc;
     } else {
-      int rc = op_hyper(c, 3, uvh, sx, kr, nullptr, dt, cfg->k4_nsub, cos_lap); if (rc) return rc;
-      double* fl[2]; const double* kk[2]; int n = 0;
-      if (cfg->apply_q) { fl[n] = F(c, QD_F_Q); kk[n] = kr[3]; ++n; }
-      if (cfg->apply_cloud) { fl[n] = F(c, QD_F_CLOUD); kk[n] = kr[4]; ++n; }
-      if (n) { rc = op_hyper(c, n, fl, sx, kk, nullptr, dt, 1, cos_lap); if (rc) return rc; }
+      if ((rc = run(ids, 3, cfg->k4_nsub))) return rc;
+      int id2[2]; int m = 0;
+      if (cfg->apply_q) id2[m++] = iQ;
+      if (cfg->apply_cloud) id2[m++] = iC;
+      if (m && (rc = run(id2, m, 1))) return rc;
     }
   }
   if (cfg->shapiro_every > 0 && (sc % cfg->shapiro_every == 0)) {
-    double* fl[3] = {F(c, QD_F_U), F(c, QD_F_V), F(c, QD_F_H)};
-    double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    double* fl[3] = {cur[iU], cur[iV], cur[iH]};
+    double* sx[3] = {F(c, QD_F_X0), F(c, QD_F_X1), F(c, QD_F_X2)};
     int rc = op_shapiro(c, 3, fl, sx, cfg->shapiro_n); if (rc) return rc;
     double* f2[2]; int n = 0;
-    if (cfg->shapiro_q) f2[n++] = F(c, QD_F_Q);
-    if (cfg->shapiro_cloud) f2[n++] = F(c, QD_F_CLOUD);
+    if (cfg->shapiro_q) f2[n++] = cur[iQ];
+    if (cfg->shapiro_cloud) f2[n++] = cur[iC];
     if (n) { rc = op_shapiro(c, n, f2, sx, std::max(1, cfg->shapiro_n - 1)); if (rc) return rc; }
   }
   if (cfg->spec_every > 0 && (sc % cfg->spec_every == 0)) {
     int rc;
-    if ((rc = op_bandstop(c, F(c, QD_F_U), cfg->spec_cutoff, cfg->spec_damp))) return rc;
-    if ((rc = op_bandstop(c, F(c, QD_F_V), cfg->spec_cutoff, cfg->spec_damp))) return rc;
-    if ((rc = op_bandstop(c, F(c, QD_F_H), cfg->spec_cutoff, cfg->spec_damp))) return rc;
+    if ((rc = op_bandstop(c, cur[iU], cfg->spec_cutoff, cfg->spec_damp))) return rc;
+    if ((rc = op_bandstop(c, cur[iV], cfg->spec_cutoff, cfg->spec_damp))) return rc;
+    if ((rc = op_bandstop(c, cur[iH], cfg->spec_cutoff, cfg->spec_damp))) return rc;
   }
   // cloud tail: advect with the NEW winds, then dissipation / damping / hygiene (+ Q_net in loop mode)
   {
-    QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X4);
-    QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_ATM));
+    QdFields f = mk_fields(1); f.src[0] = cur[iC]; f.dst[0] = F(c, QD_F_X9);
+    QD_K(c, k_advect, c->geo, f, cur[iU], cur[iV], dt, ROW(c, QD_R_COS_ADV_ATM));
     QdTailArgs T; memset(&T, 0, sizeof(T));
+    T.u_in = cur[iU]; T.v_in = cur[iV]; T.h_in = cur[iH]; T.q_in = cur[iQ];
     T.u = F(c, QD_F_U); T.v = F(c, QD_F_V); T.h = F(c, QD_F_H); T.ts = F(c, QD_F_TS); T.q = F(c, QD_F_Q); T.cloud = F(c, QD_F_CLOUD);
-    T.cloud_adv = F(c, QD_F_X4); T.hice = F(c, QD_F_HICE); T.isr = F(c, QD_F_ISR); T.albedo = F(c, QD_F_ALBEDO);
+    T.cloud_adv = F(c, QD_F_X9); T.hice = F(c, QD_F_HICE); T.isr = F(c, QD_F_ISR); T.albedo = F(c, QD_F_ALBEDO);
     T.cloud_eff = F(c, QD_F_CLOUD_EFF); T.lh = F(c, QD_F_LH); T.uo = F(c, QD_F_UO); T.vo = F(c, QD_F_VO);
     T.qnet = F(c, QD_F_QNET); T.ice = M(c, QD_M_ICE); T.land = M(c, QD_M_LAND);
     T.part_max_u = c->d_part[0]; T.part_max_va = c->d_part[1]; T.ticket = c->d_ticket + 3 * c->batch;
@@ -674,39 +709,41 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
   Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
   QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+  double* ub = F(c, QD_F_X2); double* vb = F(c, QD_F_X3); double* eta_cur = F(c, QD_F_ETA);
   if (do_hyper) {
     const int ns = std::max(1, cfg->oc_k4_nsub);
+    double* A3[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
+    double* B3[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    bool inB = false;
     for (int q = 0; q < ns; ++q) {
-      QdFields f = mk_fields(3);
-      f.src[0] = F(c, QD_F_X2); f.src[1] = F(c, QD_F_X3); f.src[2] = F(c, QD_F_ETA);
-      f.dst[0] = F(c, QD_F_X4); f.dst[1] = F(c, QD_F_X5); f.dst[2] = F(c, QD_F_X6);
-      QD_K(c, k_ocean_lap, c->geo, f, sc);
-      QdFields u = mk_fields(3);
-      u.src[0] = F(c, QD_F_X4); u.src[1] = F(c, QD_F_X5); u.src[2] = F(c, QD_F_X6);
-      u.dst[0] = F(c, QD_F_X2); u.dst[1] = F(c, QD_F_X3); u.dst[2] = F(c, QD_F_ETA);
+      QdHyper4Args H; memset(&H, 0, sizeof(H));
+      H.n = 3; H.cosr = ROW(c, QD_R_COS_ADV_HALF); H.dt = 0.0; H.nsub = ns; H.ocean = 1; H.sc = sc;
+      for (int k = 0; k < 3; ++k) { H.src[k] = inB ? B3[k] : A3[k]; H.dst[k] = inB ? A3[k] : B3[k]; H.scale[k] = 1.0; }
       // rows: sigma4*dx^4 (divided by sub_dt on device) or user rows 2..4 holding the QD_OCEAN_K4_* overrides
-      u.aux[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4);
-      u.aux[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4);
-      u.aux[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4);
-      u.scale[2] = 0.5;
-      QD_K(c, k_ocean_hyper, c->geo, u, sc, ns, ovu, ovv, ove);
+      H.k4rows[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[0] = ovu;
+      H.k4rows[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[1] = ovv;
+      H.k4rows[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[2] = ove;
+      if (!ove) H.scale[2] = 0.5;                                       // ocean.py:352
+      int rc = launch_hyper4(c, H); if (rc) return rc;
+      inB = !inB;
     }
+    if (inB) { ub = B3[0]; vb = B3[1]; eta_cur = B3[2]; }
   }
   if (do_shap) {
     // optional (QD_OCEAN_SHAPIRO_N, off by default); valid when every member shares n_sub
-    double* fl[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
-    double* sx[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    double* fl[3] = {ub, vb, eta_cur};
+    double* sx[3] = {F(c, QD_F_X7), F(c, QD_F_X8), F(c, QD_F_X9)};
     int rc = op_shapiro(c, 3, fl, sx, cfg->oc_shapiro_n); if (rc) return rc;
   }
   QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
-  Co.ub = F(c, QD_F_X2); Co.vb = F(c, QD_F_X3); Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
+  Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
   Co.ticket = c->d_ticket + 5 * c->batch;
   QD_K(c, k_ocean_continuity, c->geo, Co, sc);
   QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
-  Sa.sst = F(c, QD_F_SST); Sa.ub = F(c, QD_F_X2); Sa.vb = F(c, QD_F_X3); Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
+  Sa.sst = F(c, QD_F_SST); Sa.ub = ub; Sa.vb = vb; Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
   QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
-  Sb.tb = F(c, QD_F_X7); Sb.ub = F(c, QD_F_X2); Sb.vb = F(c, QD_F_X3); Sb.qnet = F(c, QD_F_QNET);
+  Sb.tb = F(c, QD_F_X7); Sb.ub = ub; Sb.vb = vb; Sb.qnet = F(c, QD_F_QNET);
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;

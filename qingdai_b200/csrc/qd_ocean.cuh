@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_hyper(QdGeo g, QdFields f,
 
 // Continuity (ocean.py:364-367) + the area-weighted ocean sum of eta for the mean removal (:369-375).
 struct QdOcContArgs {
-  const double *ub, *vb;
+  const double *ub, *vb, *eta_in;      // eta_in: where del^4 left eta (may be a scratch slot)
   double *eta, *part;
   const uint8_t* land;
   unsigned* ticket;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
     const size_t c = off + idx;
     const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
     const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);
-    double e = A.eta[c] + (-sub_dt * P[QD_P_OC_H] * div);
+    double e = A.eta_in[c] + (-sub_dt * P[QD_P_OC_H] * div);
     const bool land = A.land[c] == 1;
     if (land) e = 0.0;
     A.eta[c] = e;

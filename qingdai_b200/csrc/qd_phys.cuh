@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
       double alpha_e = NAN;
       if (land) {
         const double fc = A.fcanopy[c];
-        alpha_e = P[QD_P_ECO_ALPHA_LEAF] * fc + (1.0 - fc) * P[QD_P_ECO_SOIL_REFLECT];
+        alpha_e = qd_clip(P[QD_P_ECO_ALPHA_LEAF] * fc + (1.0 - fc) * P[QD_P_ECO_SOIL_REFLECT], 0.0, 1.0);
       }
       A.alpha_eco[c] = alpha_e;
       if (land && !glacier && isfinite(alpha_e))
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_advect_momentum(QdGeo g, QdAdvMo
 // nan_to_num on all six; fused with the loop's surface heat flux (run_simulation.py:2201-2239)
 // and the block maxima that decide the ocean sub-step count (ocean.py:285-303).
 struct QdTailArgs {
+  const double *u_in, *v_in, *h_in, *q_in;      // where del^4 / filters left the fields
   double *u, *v, *h, *ts, *q, *cloud;
   const double *cloud_adv, *hice, *isr, *albedo, *cloud_eff, *lh, *uo, *vo;
   double *qnet; uint8_t* ice; const uint8_t* land;
@@ -411,8 +412,8 @@ __global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
     const size_t c = off + idx;
     const double df = P[QD_P_DIFF_FACTOR];
     const double rate = A.dt / (2.0 * 24 * 3600);
-    const double u = qd_nan_to_num(A.u[c] * df), v = qd_nan_to_num(A.v[c] * df), h = qd_nan_to_num(A.h[c] * df);
-    const double q = qd_nan_to_num(A.q[c] * df), ts = qd_nan_to_num(A.ts[c]);
+    const double u = qd_nan_to_num(A.u_in[c] * df), v = qd_nan_to_num(A.v_in[c] * df), h = qd_nan_to_num(A.h_in[c] * df);
+    const double q = qd_nan_to_num(A.q_in[c] * df), ts = qd_nan_to_num(A.ts[c]);
     const double cl = qd_nan_to_num((A.cloud_adv[c] * (1 - rate)) * df);
     A.u[c] = u; A.v[c] = v; A.h[c] = h; A.q[c] = q; A.ts[c] = ts; A.cloud[c] = cl;
     if (A.with_qnet) {
