@@ -229,8 +229,9 @@ int  qd_atmos_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* Teq in QD_F_TEQ,
 int  qd_ocean_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* winds QD_F_U/V, Q in QD_F_QNET, ice in QD_M_ICE */
 int  qd_loop_step(qd_ctx* ctx, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps);
 int  qd_last_nsub(qd_ctx* ctx, int* out_host /* [B] */);      /* sync */
-/* 1 (default): the ocean's data-dependent sub-step loop runs as a CUDA-graph WHILE node (no host
- * round trip); 0: host loop with one scalar read-back per step */
+/* 2 (default): a whole loop step is one CUDA graph (kernels, memsets, cooperative selects, WHILE node
+ * for the ocean's data-dependent sub-step loop); 1: stream launches + WHILE-node graph for the ocean
+ * loop only; 0: stream launches and a host loop with one scalar read-back per step */
 int  qd_use_graphs(qd_ctx* ctx, int enable);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);

@@ -60,8 +60,10 @@ struct qd_ctx {
   QdGaussW w_sigma1, w_cloud; int w_set;
   int* d_sub_ctr; int use_graphs;
 #ifndef QD_HOST_EMU
-  cudaStream_t cap_stream;
+  cudaStream_t cap_stream, cap_stream2;
+  cudaGraph_t capture_graph;                        // non-null while a whole loop step is being captured
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
+  std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
     return 4 + (do_hyper ? std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
   }
@@ -192,9 +194,9 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
-  c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 1;
+  c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
 #ifndef QD_HOST_EMU
-  c->cap_stream = nullptr;
+  c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
 #endif
   const size_t nrows = (size_t)(QD_R_COUNT + 3 * QD_NUSER_ROWS) * nlat;
 #define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
@@ -269,7 +271,9 @@ extern "C" int qd_destroy(qd_ctx* c) {
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
   for (auto& kv : c->ocean_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : c->step_graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+  if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
 #endif
   delete c;
   return QD_OK;
@@ -355,9 +359,9 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   const int tiles_i = (c->nlon + QD_H4_TI - 1) / QD_H4_TI;
   const long long blocks32 = (long long)tiles_i * ((c->nlat + 31) / 32) * c->batch * H.n;
   if (blocks32 >= 2 * 148) {
-    QD_KG(c, k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_THREADS), c->geo, H);
+    QD_KG(c, k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
   } else {
-    QD_KG(c, k_hyper4_tile<8>, dim3(tiles_i * ((c->nlat + 7) / 8), c->batch, H.n), dim3(QD_THREADS), c->geo, H);
+    QD_KG(c, k_hyper4_tile<8>, dim3(tiles_i * ((c->nlat + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
   }
   return QD_OK;
 }
@@ -812,7 +816,33 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   int rc;
   bool launched = false;
 #ifndef QD_HOST_EMU
-  if (c->use_graphs && !qd_prof_on(c)) {
+  if (c->capture_graph) {
+    // whole-step capture: splice a WHILE node into the graph being captured (CUDA programming guide,
+    // "conditional nodes with stream capture"): current capture dependencies -> node -> rest of the step
+    cudaStreamCaptureStatus st; unsigned long long id; cudaGraph_t gg; const cudaGraphNode_t* deps = nullptr; size_t ndeps = 0;
+    QD_CUDA(c, cudaStreamGetCaptureInfo_v2(c->stream, &st, &id, &gg, &deps, &ndeps));
+    cudaGraphConditionalHandle handle;
+    QD_CUDA(c, cudaGraphConditionalHandleCreate(&handle, c->capture_graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+    np.conditional.handle = handle; np.conditional.type = cudaGraphCondTypeWhile; np.conditional.size = 1;
+    cudaGraphNode_t node;
+    QD_CUDA(c, cudaGraphAddNode(&node, c->capture_graph, deps, ndeps, &np));
+    QD_CUDA(c, cudaStreamUpdateCaptureDependencies(c->stream, &node, 1, cudaStreamSetCaptureDependencies));
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    if (!c->cap_stream2) QD_CUDA(c, cudaStreamCreateWithFlags(&c->cap_stream2, cudaStreamNonBlocking));
+    QD_CUDA(c, cudaStreamBeginCaptureToGraph(c->cap_stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    cudaStream_t outer = c->stream;
+    c->stream = c->cap_stream2;
+    rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap);
+    QD_LAUNCH(k_ocean_sub_advance, dim3(1), dim3(32), c->stream, c->geo, c->d_sub_ctr, handle, 1);
+    c->stream = outer;
+    cudaGraph_t dummy = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(c->cap_stream2, &dummy);
+    if (rc) return rc;
+    if (ee != cudaSuccess) return qd_fail(c, QD_E_CUDA, "capture of the ocean sub-step body", ee);
+    c->last_nsub_max = -1;
+    launched = true;
+  } else if (c->use_graphs && !qd_prof_on(c)) {
     cudaGraphExec_t exec = ocean_while_graph(c, cfg, inject, do_hyper, do_shap);
     if (exec) {
       QD_CUDA(c, cudaGraphLaunch(exec, c->stream));
@@ -847,7 +877,7 @@ extern "C" int qd_ocean_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   QD_BOUND(c);
   return ocean_core(c, cfg, 0);
 }
-extern "C" int qd_use_graphs(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->use_graphs = enable ? 1 : 0; return QD_OK; }
+extern "C" int qd_use_graphs(qd_ctx* c, int level) { if (!c) return QD_E_INVALID; c->use_graphs = level < 0 ? 0 : (level > 2 ? 2 : level); return QD_OK; }
 extern "C" int qd_last_nsub(qd_ctx* c, int* out) {
   if (!c || !out) return QD_E_INVALID;
   std::vector<double> s((size_t)c->batch * QD_S_COUNT);
@@ -910,6 +940,76 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   return QD_OK;
 }
 
+static int loop_step_enqueue(qd_ctx* c, const qd_step_cfg_t* cfg) {
+  int rc;
+  if ((rc = loop_physics(c, cfg))) return rc;
+  if ((rc = atmos_core(c, cfg, 1))) return rc;
+  if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
+  if (cfg->with_routing && c->route.ready) {
+    QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, cfg->dt);
+  }
+  QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
+  return QD_OK;
+}
+
+#ifndef QD_HOST_EMU
+// One whole loop step as ONE CUDA graph (kernels, memsets, the cooperative selects and the ocean WHILE
+// node).  Variants differ only in host-known cadences and switches, which form the cache key.
+static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
+  const int an = c->atm_counter + 1, on = c->oc_counter + 1;
+  const bool a_hyp = cfg->diff_enable && (an % std::max(1, cfg->diff_every) == 0);
+  const bool a_shp = cfg->shapiro_every > 0 && (an % cfg->shapiro_every == 0);
+  const bool a_spc = cfg->spec_every > 0 && (an % cfg->spec_every == 0);
+  const bool o_hyp = (cfg->oc_diff_every > 0) && (on % cfg->oc_diff_every == 0);
+  const bool o_shp = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (on % cfg->oc_shapiro_every == 0);
+  unsigned long long key = 1469598103934665603ull;
+  auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+  mix(a_hyp); mix(a_shp); mix(a_spc); mix(o_hyp); mix(o_shp); mix(c->has_cloud_eff); mix(c->route.ready);
+  { const unsigned char* p = (const unsigned char*)cfg; for (size_t k = 0; k < sizeof(*cfg); ++k) mix(p[k]); }
+  auto it = c->step_graphs.find(key);
+  if (it != c->step_graphs.end()) {
+    if (!it->second.first) return QD_E_STATE;
+    QD_CUDA(c, cudaGraphLaunch(it->second.first, c->stream));
+    c->atm_counter = an;
+    if (cfg->with_ocean) c->oc_counter = on;
+    if (cfg->loop_with_albedo) c->has_cloud_eff = 1;
+    c->launches += it->second.second;
+    return QD_OK;
+  }
+  // build: capture this step once, then launch it
+  const int sa = c->atm_counter, so = c->oc_counter, sce = c->has_cloud_eff;
+  const long long sl = c->launches;
+  cudaStream_t saved = c->stream;
+  cudaGraph_t G = nullptr; cudaGraphExec_t exec = nullptr;
+  bool ok = false;
+  int rc = QD_OK;
+  do {
+    if (!c->cap_stream && cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) break;
+    if (cudaGraphCreate(&G, 0) != cudaSuccess) break;
+    if (cudaStreamBeginCaptureToGraph(c->cap_stream, G, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
+    c->stream = c->cap_stream; c->capture_graph = G;
+    rc = loop_step_enqueue(c, cfg);
+    c->stream = saved; c->capture_graph = nullptr;
+    cudaGraph_t out = nullptr;
+    if (cudaStreamEndCapture(c->cap_stream, &out) != cudaSuccess || rc != QD_OK) break;
+    if (cudaGraphInstantiate(&exec, G, 0) != cudaSuccess) { exec = nullptr; break; }
+    ok = true;
+  } while (0);
+  c->stream = saved; c->capture_graph = nullptr;
+  cudaGetLastError();
+  if (G) cudaGraphDestroy(G);
+  const long long per_step = c->launches - sl;
+  if (!ok) {
+    c->atm_counter = sa; c->oc_counter = so; c->has_cloud_eff = sce; c->launches = sl;
+    c->step_graphs[key] = std::make_pair((cudaGraphExec_t) nullptr, 0ll);
+    return QD_E_STATE;
+  }
+  c->step_graphs[key] = std::make_pair(exec, per_step);
+  QD_CUDA(c, cudaGraphLaunch(exec, c->stream));     // counters were advanced by the capture pass
+  return QD_OK;
+}
+#endif
+
 extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps) {
   if (!c || !cfg || !forcing || nsteps < 1) return QD_E_INVALID;
   QD_BOUND(c);
@@ -923,13 +1023,14 @@ extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcin
   QD_CUDA(c, cudaMemsetAsync(c->d_step_idx, 0, sizeof(int), c->stream));
   for (int s = 0; s < nsteps; ++s) {
     int rc;
-    if ((rc = loop_physics(c, cfg))) return rc;
-    if ((rc = atmos_core(c, cfg, 1))) return rc;
-    if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
-    if (cfg->with_routing && c->route.ready) {
-      QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, cfg->dt);
+#ifndef QD_HOST_EMU
+    if (c->use_graphs >= 2 && !qd_prof_on(c)) {
+      rc = loop_step_graph(c, cfg);
+      if (rc == QD_OK) continue;
+      if (rc != QD_E_STATE) return rc;        // QD_E_STATE: graphs unavailable for this variant -> stream mode
     }
-    QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
+#endif
+    if ((rc = loop_step_enqueue(c, cfg))) return rc;
   }
   QD_CHECK_LAUNCH(c);
   return QD_OK;

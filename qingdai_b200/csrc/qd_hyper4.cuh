@@ -48,12 +48,33 @@ QD_HD double qd_lap_rel(const Acc& A, int j, int c, const QdGeo& g, const double
   return (term_phi + d2 * ic2[j]) * g.inv_a_sq;
 }
 
+// 2-D cooperative tile loops: strided over the (x, y) threads of the block on the GPU, run completely
+// by the first thread in the sequential host check build.
+#if QD_EMU
+#define QD_TILE_FIRST_LOOP(r, R, cc, Cn) \
+  if (threadIdx.x == 0 && threadIdx.y == 0) for (int r = 0; r < (R); ++r) for (int cc = 0; cc < (Cn); ++cc)
+#define QD_TILE_FIRST_ROWS(r, R) if (threadIdx.x == 0 && threadIdx.y == 0) for (int r = 0; r < (R); ++r)
+#else
+#define QD_TILE_FIRST_LOOP(r, R, cc, Cn) \
+  for (int r = threadIdx.y; r < (R); r += blockDim.y) for (int cc = threadIdx.x; cc < (Cn); cc += blockDim.x)
+#define QD_TILE_FIRST_ROWS(r, R) for (int r = threadIdx.y * blockDim.x + threadIdx.x; r < (R); r += blockDim.x * blockDim.y)
+#endif
+#define QD_H4_NX 64
+#define QD_H4_NY 4
+
+QD_HD double qd_clean_fast(double x) { return (fabs(x) <= DBL_MAX) ? x : qd_nan_to_num(x); }
+
+// Interior rows (2 <= j <= n_lat-3, every np.gradient centred) use three per-row coefficients staged in
+// shared memory:  lap F = ap*(F[j+2]-F[j]) - am*(F[j]-F[j-2]) + bl*((F[i+1]-2F)+F[i-1])  with
+//   ap = (1/c_j)(1/2dphi)(c_{j+1}/2dphi)/a^2,  am = (1/c_j)(1/2dphi)(c_{j-1}/2dphi)/a^2,  bl = (1/c_j^2)(1/dlam^2)/a^2.
+// The four rows next to the poles take the general one-sided form (qd_lap_rel).
 template <int TJ>
-__global__ void __launch_bounds__(QD_THREADS) k_hyper4_tile(QdGeo g, QdHyper4Args A) {
+__global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, QdHyper4Args A) {
   constexpr int TI = QD_H4_TI;
   constexpr int RF = TJ + 8, CF = TI + 4, RL = TJ + 4, CL = TI + 2;
   __shared__ double Fs[RF * CF];
   __shared__ double Ls[RL * CL];
+  __shared__ double cap[RF], cam[RF], cbl[RF], k4s[TJ];
   const int b = blockIdx.y;
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;
   const int tiles_i = (g.nlon + TI - 1) / TI;
@@ -65,38 +86,77 @@ __global__ void __launch_bounds__(QD_THREADS) k_hyper4_tile(QdGeo g, QdHyper4Arg
   double sub_dt = A.dt;
   if (A.ocean) sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
   const double inner = sub_dt / (double)(A.nsub > 1 ? A.nsub : 1);
-  {
-    const int k = blockIdx.z;                 // one field per block (gridDim.z = number of fields)
-    const double* F = A.src[k] + off;
-    QD_BLOCK_FIRST_FOR(e, RF * CF) {
-      const int r = e / CF, cc = e - r * CF;
-      const int gj = jF0 + r;
-      if (gj >= 0 && gj < nlat) {
-        int gi = (iF0 + cc) % nlon;
-        if (gi < 0) gi += nlon;
-        Fs[e] = qd_nan_to_num(F[(size_t)gj * nlon + gi]);
-      }
+  const int k = blockIdx.z;                   // one field per block (gridDim.z = number of fields)
+  const double* F = A.src[k] + off;
+  const double* cr = A.cosr;
+  QD_TILE_FIRST_ROWS(r, RF) {
+    const int gj = jF0 + r;
+    double ap = 0.0, am = 0.0, bl = 0.0;
+    if (gj >= 2 && gj <= nlat - 3) {
+      const double icj = cr[nlat + gj] * g.inv_2dlat;
+      ap = (icj * (cr[gj + 1] * g.inv_2dlat)) * g.inv_a_sq;
+      am = (icj * (cr[gj - 1] * g.inv_2dlat)) * g.inv_a_sq;
+      bl = (cr[2 * nlat + gj] * g.inv_dlon_sq) * g.inv_a_sq;
     }
-    __syncthreads();
-    auto AF = [&](int jj, int c) -> double { return Fs[(jj - jF0) * CF + c]; };
-    QD_BLOCK_FIRST_FOR(e, RL * CL) {
-      const int r = e / CL, cc = e - r * CL;
-      const int gj = jL0 + r;
-      if (gj >= 0 && gj < nlat) Ls[e] = qd_nan_to_num(qd_lap_rel(AF, gj, cc + 1, g, A.cosr));
-    }
-    __syncthreads();
-    auto AL = [&](int jj, int c) -> double { return Ls[(jj - jL0) * CL + c]; };
-    const double* k4r = A.k4rows[k];
-    for (int e = threadIdx.x; e < TJ * TI; e += blockDim.x) {
-      const int r = e / TI, cc = e - r * TI;
-      const int gj = j0 + r, gi = i0 + cc;
-      if (gj < nlat && gi < nlon) {
-        const double L2 = qd_lap_rel(AL, gj, cc + 1, g, A.cosr);
-        double k4 = k4r[gj];
+    cap[r] = ap; cam[r] = am; cbl[r] = bl;
+    if (r < TJ) {
+      const int oj = j0 + r;
+      double k4 = 0.0;
+      if (oj < nlat) {
+        k4 = A.k4rows[k][oj];
         if (!A.raw_k4[k]) k4 = k4 / fmax(1e-12, sub_dt);       // ocean.py:347
         k4 = A.scale[k] * k4;
-        const double cur = Fs[(r + 4) * CF + cc + 2];
-        A.dst[k][off + (size_t)gj * nlon + gi] = qd_nan_to_num(cur - k4 * L2 * inner);
+      }
+      k4s[r] = k4;
+    }
+  }
+  QD_TILE_FIRST_LOOP(r, RF, cc, CF) {
+    const int gj = jF0 + r;
+    double v = 0.0;
+    if (gj >= 0 && gj < nlat) {
+      int gi = iF0 + cc;
+      while (gi < 0) gi += nlon;
+      while (gi >= nlon) gi -= nlon;
+      v = qd_clean_fast(F[(size_t)gj * nlon + gi]);
+    }
+    Fs[r * CF + cc] = v;
+  }
+  __syncthreads();
+  auto AF = [&](int jj, int c) -> double { return Fs[(jj - jF0) * CF + c]; };
+  QD_TILE_FIRST_LOOP(r, RL, cc, CL) {
+    const int gj = jL0 + r;
+    double L = 0.0;
+    if (gj >= 0 && gj < nlat) {
+      const int fr = r + 2, e = fr * CF + cc + 1;
+      if (gj >= 2 && gj <= nlat - 3) {
+        const double f0 = Fs[e];
+        L = (cap[fr] * (Fs[e + 2 * CF] - f0) - cam[fr] * (f0 - Fs[e - 2 * CF])) + cbl[fr] * ((Fs[e + 1] - 2.0 * f0) + Fs[e - 1]);
+      } else {
+        L = qd_lap_rel(AF, gj, cc + 1, g, cr);
+      }
+      L = qd_clean_fast(L);
+    }
+    Ls[r * CL + cc] = L;
+  }
+  __syncthreads();
+  auto AL = [&](int jj, int c) -> double { return Ls[(jj - jL0) * CL + c]; };
+  const int cc = threadIdx.x;
+  const int gi = i0 + cc;
+  if (gi < nlon) {
+#pragma unroll 4
+    for (int r = threadIdx.y; r < TJ; r += QD_H4_NY) {
+      const int gj = j0 + r;
+      if (gj < nlat) {
+        const int lr = r + 2, e = lr * CL + cc + 1, fr = r + 4;
+        double L2;
+        if (gj >= 2 && gj <= nlat - 3) {
+          const double l0 = Ls[e];
+          L2 = (cap[fr] * (Ls[e + 2 * CL] - l0) - cam[fr] * (l0 - Ls[e - 2 * CL])) + cbl[fr] * ((Ls[e + 1] - 2.0 * l0) + Ls[e - 1]);
+        } else {
+          L2 = qd_lap_rel(AL, gj, cc + 1, g, cr);
+        }
+        const double cur = Fs[fr * CF + cc + 2];
+        A.dst[k][off + (size_t)gj * nlon + gi] = qd_clean_fast(cur - k4s[r] * L2 * inner);
       }
     }
   }

@@ -255,7 +255,7 @@ class Engine:
 
     def use_graphs(self, enable=True):
         """Ocean sub-step loop as a CUDA-graph WHILE node (default) or as a host loop with a read-back."""
-        self._chk(self.lib.qd_use_graphs(self.ctx, int(bool(enable))), "qd_use_graphs")
+        self._chk(self.lib.qd_use_graphs(self.ctx, int(enable) if not isinstance(enable, bool) else (2 if enable else 0)), "qd_use_graphs")
 
     def sync(self):
         self._chk(self.lib.qd_synchronize(self.ctx), "qd_synchronize")

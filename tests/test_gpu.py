@@ -93,3 +93,7 @@ def test_graph_and_stream_modes_agree_bitwise(lib, C):
 @pytest.mark.parametrize("tag", ["r1", "r2"])
 def test_routing(lib, golden, tag):
     qdcheck.check_routing(lib, golden("routing_golden.npz"), tag)
+
+
+def test_graph_levels_agree_bitwise(lib, L):
+    qdcheck.check_graph_levels_agree(lib, L)

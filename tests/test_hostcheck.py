@@ -80,3 +80,7 @@ def test_jax_compat_seam(lib, G):
 @pytest.mark.parametrize("tag", ["r1", "r2"])
 def test_routing(lib, golden, tag):
     qdcheck.check_routing(lib, golden("routing_golden.npz"), tag)
+
+
+def test_graph_levels_are_noops_in_host_build(lib, L):
+    qdcheck.check_graph_levels_agree(lib, L, nsteps=7)
