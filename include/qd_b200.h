@@ -89,6 +89,8 @@ typedef enum {
   QD_R_OC_SPONGE,     /* polar_gain * s^2        */
   QD_R_POLAR,         /* 1.0 where |lat| >= QD_POLAR_LAT_THRESH */
   QD_R_AREA,          /* cell area m^2 (routing) */
+  QD_R_INV_ACOS_HALF, /* 1/(a*max(cos,0.5)): ocean pressure-gradient metric (ocean.py:309) */
+  QD_R_INV_ACOS_CAP,  /* 1/(a*max(cos,1e-6)): divergence / vorticity metric (grid.py:66,87) */
   QD_R_COUNT
 } qd_row_id;
 
@@ -128,6 +130,8 @@ typedef enum {
   QD_P_ECO_ENABLE, QD_P_ECO_W_LAI, QD_P_ECO_SOIL_REFLECT, QD_P_ECO_ALPHA_LEAF,
   /* host-evaluated sums (np.sum over the 2-D weight arrays, energy.py:522, ocean.py:374) */
   QD_P_WSUM_ALL, QD_P_OC_WSUM_OCEAN, QD_P_OC_ANY_OCEAN,
+  /* host-evaluated reciprocals of parameter-only divisors */
+  QD_P_OC_INV_RHO_H, QD_P_OC_INV_RHO_CP_H,
   QD_P_COUNT
 } qd_param_id;
 

@@ -245,6 +245,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.nlat = nlat; g.nlon = nlon; g.ncell = c->ncell; g.batch = batch;
   g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
+  g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
   g.rows = c->d_rows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
   *out = c;

@@ -68,6 +68,148 @@ QD_HD double qd_clean_fast(double x) { return (fabs(x) <= DBL_MAX) ? x : qd_nan_
 // shared memory:  lap F = ap*(F[j+2]-F[j]) - am*(F[j]-F[j-2]) + bl*((F[i+1]-2F)+F[i-1])  with
 //   ap = (1/c_j)(1/2dphi)(c_{j+1}/2dphi)/a^2,  am = (1/c_j)(1/2dphi)(c_{j-1}/2dphi)/a^2,  bl = (1/c_j^2)(1/dlam^2)/a^2.
 // The four rows next to the poles take the general one-sided form (qd_lap_rel).
+#if !QD_EMU
+// GPU kernel.  64 x 4 threads; a warp is 32 consecutive longitudes of ONE tile row, so every row
+// predicate (inside the domain? interior?) is warp-uniform.  All loops have compile-time trip counts
+// and shared-memory offsets are immediates (ncu showed the first, generic version spending >70 % of
+// its issue slots on index arithmetic and branch bookkeeping: profiles/r01_ncu_hyper4.md).
+template <int TJ>
+__global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, QdHyper4Args A) {
+  constexpr int TI = QD_H4_TI, NX = QD_H4_NX, NY = QD_H4_NY;
+  constexpr int RF = TJ + 8, CF = TI + 4, RL = TJ + 4, CL = TI + 2;
+  static_assert(RF % NY == 0 && RL % NY == 0 && TJ % NY == 0 && TI == NX, "tile shape");
+  __shared__ double Fs[RF * CF];
+  __shared__ double Ls[RL * CL];
+  __shared__ double cap[RF], cam[RF], cbl[RF], k4s[TJ];
+  const int b = blockIdx.y;
+  if (A.ocean && qd_sub_done(g, b, A.sc)) return;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * NX + tx;
+  const int tiles_i = (g.nlon + TI - 1) / TI;
+  const int tj = blockIdx.x / tiles_i, ti = blockIdx.x - tj * tiles_i;
+  const int j0 = tj * TJ, i0 = ti * TI;
+  const int jF0 = j0 - 4, jL0 = j0 - 2, iF0 = i0 - 2;
+  const int nlat = g.nlat, nlon = g.nlon;
+  const size_t off = (size_t)b * g.ncell;
+  double sub_dt = A.dt;
+  if (A.ocean) sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
+  const double inner = sub_dt / (double)(A.nsub > 1 ? A.nsub : 1);
+  const int k = blockIdx.z;                   // one field per block (gridDim.z = number of fields)
+  const double* __restrict__ F = A.src[k] + off;
+  double* __restrict__ D = A.dst[k] + off;
+  const double* __restrict__ cr = A.cosr;
+  if (tid < RF) {
+    const int gj = jF0 + tid;
+    double ap = 0.0, am = 0.0, bl = 0.0;
+    if (gj >= 2 && gj <= nlat - 3) {
+      const double icj = cr[nlat + gj] * g.inv_2dlat;
+      ap = (icj * (cr[gj + 1] * g.inv_2dlat)) * g.inv_a_sq;
+      am = (icj * (cr[gj - 1] * g.inv_2dlat)) * g.inv_a_sq;
+      bl = (cr[2 * nlat + gj] * g.inv_dlon_sq) * g.inv_a_sq;
+    }
+    cap[tid] = ap; cam[tid] = am; cbl[tid] = bl;
+    if (tid < TJ) {
+      const int oj = j0 + tid;
+      double k4 = 0.0;
+      if (oj < nlat) {
+        k4 = A.k4rows[k][oj];
+        if (!A.raw_k4[k]) k4 = k4 / fmax(1e-12, sub_dt);       // ocean.py:347
+        k4 = A.scale[k] * k4;
+      }
+      k4s[tid] = k4;
+    }
+  }
+  // columns of this thread: main column and (first 4 threads of a row) one halo column; periodic wrap
+  int gi0 = iF0 + tx;
+  while (gi0 < 0) gi0 += nlon;
+  while (gi0 >= nlon) gi0 -= nlon;
+  int gi1 = iF0 + NX + (tx & 3);
+  while (gi1 >= nlon) gi1 -= nlon;
+  // ---- phase 1: halo tile of the field.  np.nan_to_num is applied lazily: values are staged raw, a
+  // block-wide flag records whether anything non-finite was seen, and only then a cleaning pass runs
+  // (identical results; the common all-finite case costs one compare per element instead of a branchy clean).
+  const bool rows_ok = (jF0 >= 0) && (jF0 + RF <= nlat);          // block-uniform: no pole in this tile
+  const size_t rstride = (size_t)NY * nlon;
+  int bad = 0;
+  {
+    const double* p0 = F + (size_t)(rows_ok ? jF0 + ty : 0) * nlon + gi0;
+    const double* p1 = F + (size_t)(rows_ok ? jF0 + ty : 0) * nlon + gi1;
+#pragma unroll
+    for (int m = 0; m < RF / NY; ++m) {
+      const int r = ty + m * NY;
+      double v0 = 0.0, v1 = 0.0;
+      if (rows_ok) {
+        v0 = p0[0];
+        if (tx < 4) v1 = p1[0];
+        p0 += rstride; p1 += rstride;
+      } else {
+        const int gj = jF0 + r;
+        if (gj >= 0 && gj < nlat) {
+          const double* row = F + (size_t)gj * nlon;
+          v0 = row[gi0];
+          if (tx < 4) v1 = row[gi1];
+        }
+      }
+      bad |= !(fabs(v0) <= DBL_MAX) | !(fabs(v1) <= DBL_MAX);
+      Fs[r * CF + tx] = v0;
+      if (tx < 4) Fs[r * CF + NX + tx] = v1;
+    }
+  }
+  if (__syncthreads_or(bad)) {
+    for (int e = tid; e < RF * CF; e += NX * NY) Fs[e] = qd_nan_to_num(Fs[e]);
+    __syncthreads();
+  }
+  auto AF = [&](int jj, int c) -> double { return Fs[(jj - jF0) * CF + c]; };
+  // ---- phase 2: L = lap(F) on the ring needed by the second Laplacian (cleaned lazily like F)
+  bad = 0;
+#pragma unroll
+  for (int m = 0; m < RL / NY; ++m) {
+    const int r = ty + m * NY, gj = jL0 + r, fr = r + 2;
+    const bool valid = gj >= 0 && gj < nlat, inter = gj >= 2 && gj <= nlat - 3;
+    const double ap = cap[fr], am = cam[fr], bl = cbl[fr];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && tx >= 2) break;
+      const int cc = h ? NX + tx : tx;
+      const int e = fr * CF + cc + 1;
+      double L = 0.0;
+      if (inter) {
+        const double f0 = Fs[e];
+        L = (ap * (Fs[e + 2 * CF] - f0) - am * (f0 - Fs[e - 2 * CF])) + bl * ((Fs[e + 1] - 2.0 * f0) + Fs[e - 1]);
+      } else if (valid) {
+        L = qd_lap_rel(AF, gj, cc + 1, g, cr);
+      }
+      bad |= !(fabs(L) <= DBL_MAX);
+      Ls[r * CL + cc] = L;
+    }
+  }
+  if (__syncthreads_or(bad)) {
+    for (int e = tid; e < RL * CL; e += NX * NY) Ls[e] = qd_nan_to_num(Ls[e]);
+    __syncthreads();
+  }
+  auto AL = [&](int jj, int c) -> double { return Ls[(jj - jL0) * CL + c]; };
+  // ---- phase 3: lap(L) and the update on the tile interior
+  const int gi = i0 + tx;
+  if (gi < nlon) {
+#pragma unroll
+    for (int m = 0; m < TJ / NY; ++m) {
+      const int r = ty + m * NY, gj = j0 + r;
+      if (gj < nlat) {
+        const int e = (r + 2) * CL + tx + 1, fr = r + 4;
+        double L2;
+        if (gj >= 2 && gj <= nlat - 3) {
+          const double l0 = Ls[e];
+          L2 = (cap[fr] * (Ls[e + 2 * CL] - l0) - cam[fr] * (l0 - Ls[e - 2 * CL])) + cbl[fr] * ((Ls[e + 1] - 2.0 * l0) + Ls[e - 1]);
+        } else {
+          L2 = qd_lap_rel(AL, gj, tx + 1, g, cr);
+        }
+        D[(size_t)gj * nlon + gi] = qd_clean_fast(Fs[fr * CF + tx + 2] - k4s[r] * L2 * inner);
+      }
+    }
+  }
+}
+#else
+// Host check build: the same tile algorithm with cooperative loops written so that one sequential
+// "thread" can run a whole phase (see qd_rt.h); the GPU kernel above is exercised by tests/test_gpu.py.
 template <int TJ>
 __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, QdHyper4Args A) {
   constexpr int TI = QD_H4_TI;
@@ -161,3 +303,4 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
     }
   }
 }
+#endif

@@ -89,15 +89,16 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_momentum(QdGeo g, QdOcMomA
   const double* eta = A.eta + off;
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
   const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;     // np.roll wraps pole to pole
-  const double de_dl = (eta[(size_t)j * nlon + ip] - eta[(size_t)j * nlon + im]) / (2.0 * g.dlon);
-  const double de_dp = (eta[(size_t)jp * nlon + i] - eta[(size_t)jm * nlon + i]) / (2.0 * g.dlat);
-  const double gx = de_dl / (g.a * qd_row(g, QD_R_COS_ADV_HALF)[j]);
-  const double gy = de_dp / g.a;
+  // metric divisions as reciprocal multiplies (<= 1 ulp each): /(2 dlon), /(2 dphi), /(a cos), /a, /(rho_w H)
+  const double de_dl = (eta[(size_t)j * nlon + ip] - eta[(size_t)j * nlon + im]) * g.inv_2dlon;
+  const double de_dp = (eta[(size_t)jp * nlon + i] - eta[(size_t)jm * nlon + i]) * g.inv_2dlat;
+  const double gx = de_dl * qd_row(g, QD_R_INV_ACOS_HALF)[j];
+  const double gy = de_dp * g.inv_a;
   const double f = qd_row(g, QD_R_FCOR)[j];
   double uo = A.uo[c], vo = A.vo[c];
-  const double rH = P[QD_P_OC_RHO_W] * P[QD_P_OC_H];
-  const double du = (f * vo - P[QD_P_OC_G] * gx + A.taux[c] / rH - P[QD_P_OC_R_BOT] * uo);
-  const double dv = (-f * uo - P[QD_P_OC_G] * gy + A.tauy[c] / rH - P[QD_P_OC_R_BOT] * vo);
+  const double irH = P[QD_P_OC_INV_RHO_H];
+  const double du = (f * vo - P[QD_P_OC_G] * gx + A.taux[c] * irH - P[QD_P_OC_R_BOT] * uo);
+  const double dv = (-f * uo - P[QD_P_OC_G] * gy + A.tauy[c] * irH - P[QD_P_OC_R_BOT] * vo);
   uo = uo + sub_dt * du;
   vo = vo + sub_dt * dv;
   if (A.land[c] == 1) { uo = 0.0; vo = 0.0; }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   const bool ocean = A.land[c] != 1;
   const bool ice = A.has_ice ? (A.ice[c] != 0) : false;
   if (P[QD_P_OC_USE_QNET] != 0.0 && A.has_q) {
-    const double tend = A.qnet[c] / (P[QD_P_OC_RHO_W] * P[QD_P_OC_CP_W] * P[QD_P_OC_H]);
+    const double tend = A.qnet[c] * P[QD_P_OC_INV_RHO_CP_H];      // Q / (rho_w cp_w H), reciprocal from the host
     if (ocean && !ice) T = T + sub_dt * tend;
     else if (ocean && ice && A.has_ice && P[QD_P_OC_ICE_QFAC] > 0.0) T = T + sub_dt * P[QD_P_OC_ICE_QFAC] * tend;
   }

@@ -18,6 +18,7 @@ struct QdGeo {
   int nlat, nlon, ncell, batch;
   double a, dlat, dlon, a_sq, dlon_sq;
   double inv_dlat, inv_2dlat, inv_dlon_sq, inv_a_sq;      // reciprocals used by the stencil kernels
+  double inv_2dlon, inv_a;
   const double* rows;    // [QD_R_COUNT + 4 user][nlat]
   const double* cols;    // [QD_C_COUNT][nlon]
   const double* prm;     // [B][QD_P_COUNT]
@@ -221,26 +222,27 @@ __global__ void __launch_bounds__(QD_THREADS) k_gauss_lon(QdGeo g, QdFields f, Q
 }
 
 // ------------------------------------------------------------------------------ divergence / vorticity
-// grid.py:41-88: np.roll centred differences; the phi-term is zeroed on rows 0 and n-1.
+// grid.py:41-88: np.roll centred differences; the phi-term is zeroed on rows 0 and n-1.  The three
+// divisions (/(2 dlon), /(2 dphi), the 1/(a cos) factor) are reciprocal multiplies (<= 1 ulp each).
 QD_HD double qd_div_cell(const double* u, const double* v, int j, int i, const QdGeo& g) {
   const int nlon = g.nlon, nlat = g.nlat;
   const double* cosr = qd_row(g, QD_R_COS);
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
-  const double du = (u[(size_t)j * nlon + ip] - u[(size_t)j * nlon + im]) / (2 * g.dlon);
+  const double du = (u[(size_t)j * nlon + ip] - u[(size_t)j * nlon + im]) * g.inv_2dlon;
   double dv = 0.0;
   if (j > 0 && j < nlat - 1)
-    dv = (v[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - v[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) / (2 * g.dlat);
-  return (1 / (g.a * qd_row(g, QD_R_COS_CAP)[j])) * (du + dv);
+    dv = (v[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - v[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) * g.inv_2dlat;
+  return qd_row(g, QD_R_INV_ACOS_CAP)[j] * (du + dv);
 }
 QD_HD double qd_vort_cell(const double* u, const double* v, int j, int i, const QdGeo& g) {
   const int nlon = g.nlon, nlat = g.nlat;
   const double* cosr = qd_row(g, QD_R_COS);
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
-  const double dv = (v[(size_t)j * nlon + ip] - v[(size_t)j * nlon + im]) / (2 * g.dlon);
+  const double dv = (v[(size_t)j * nlon + ip] - v[(size_t)j * nlon + im]) * g.inv_2dlon;
   double du = 0.0;
   if (j > 0 && j < nlat - 1)
-    du = (u[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - u[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) / (2 * g.dlat);
-  return (1 / (g.a * qd_row(g, QD_R_COS_CAP)[j])) * (dv - du);
+    du = (u[(size_t)(j + 1) * nlon + i] * cosr[j + 1] - u[(size_t)(j - 1) * nlon + i] * cosr[j - 1]) * g.inv_2dlat;
+  return qd_row(g, QD_R_INV_ACOS_CAP)[j] * (dv - du);
 }
 __global__ void __launch_bounds__(QD_THREADS) k_divvort(QdGeo g, const double* u, const double* v, double* out, int vort) {
   QD_CELL_PROLOGUE(g)

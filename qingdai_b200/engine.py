@@ -85,6 +85,8 @@ def row_tables(nlat, nlon, p: QDParams, dt):
     dlam = np.deg2rad(abs(lon[1] - lon[0]))
     band = np.sin(np.clip(lat_rad + 0.5 * dphi, -0.5 * np.pi, 0.5 * np.pi)) - np.sin(np.clip(lat_rad - 0.5 * dphi, -0.5 * np.pi, 0.5 * np.pi))
     rows[R["area"]] = (a * a) * dlam * band
+    rows[R["inv_acos_half"]] = 1.0 / (a * rows[R["cos_adv_half"]])
+    rows[R["inv_acos_cap"]] = 1 / (a * rows[R["cos_cap"]])            # grid.py:66 evaluates exactly this factor
     cols = np.zeros((NC, nlon), dtype=np.float64)
     lon_rad = np.deg2rad(lon)
     cols[ENUM["QD_C_LON_RAD"]] = lon_rad
@@ -158,6 +160,7 @@ def param_vector(p: QDParams, nlat, nlon, land_mask=None, has_elevation=False, e
         eco_enable=float(eco_enable), eco_w_lai=p.eco_lai_albedo_weight, eco_soil_reflect=p.eco_soil_reflect,
         eco_alpha_leaf=float(eco_alpha_leaf),
         wsum_all=wsum_all, oc_wsum_ocean=wsum_ocean, oc_any_ocean=any_ocean,
+        oc_inv_rho_h=1.0 / (p.oc_rho_w * p.oc_H), oc_inv_rho_cp_h=1.0 / (p.oc_rho_w * p.oc_cp_w * p.oc_H),
     )
     missing = set(P) - set(vals)
     extra = set(vals) - set(P)
