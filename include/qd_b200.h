@@ -185,7 +185,10 @@ int  qd_synchronize(qd_ctx* ctx);
 /* caller-owned device storage: fields [QD_F_COUNT][B][nlat][nlon] f64, masks [QD_M_COUNT][B][nlat][nlon] u8 */
 int  qd_bind(qd_ctx* ctx, double* fields_dev, uint8_t* masks_dev);
 int  qd_set_params(qd_ctx* ctx, const double* params_host);     /* re-snapshot (sync) */
-int  qd_set_rows(qd_ctx* ctx, const double* rows_host);         /* e.g. K4 rows after a dt change */
+int  qd_set_rows(qd_ctx* ctx, const double* rows_host);         /* e.g. K4 rows after a dt change; every member */
+/* one member's row table: the K4, ocean sponge and polar rows follow that member's QD_* parameters
+ * (dynamics.py:557-570, ocean.py:332-347, run_simulation.py:1956) -- ensemble parameter sweeps */
+int  qd_set_rows_member(qd_ctx* ctx, int member, const double* rows_host);
 int  qd_get_scalars(qd_ctx* ctx, double* out_host /* [batch][QD_S_COUNT] */);   /* sync */
 /* host <-> device field transfer through the C ABI (sync); member b or -1 for all members */
 int  qd_upload_field(qd_ctx* ctx, int field, int member, const double* host);
@@ -218,7 +221,8 @@ const double* qd_row_dev(qd_ctx* ctx, int row_id);
 /* upload an arbitrary [nlat] row table into one of 6 user row slots (0/1 are used by the *_host operator
  * forms, 2..4 hold the QD_OCEAN_K4_U/V/ETA overrides) (the library appends the 1/x and
  * 1/x^2 rows the Laplacian kernels expect right behind it), returns its device pointer */
-const double* qd_user_row(qd_ctx* ctx, int slot, const double* rows_host);
+const double* qd_user_row(qd_ctx* ctx, int slot, const double* rows_host);   /* every member's copy */
+int  qd_user_row_member(qd_ctx* ctx, int slot, int member, const double* rows_host);
 
 /* host-buffer convenience forms of the three jax_compat seam kernels (H2D + kernel + D2H, sync);
  * arrays are single-member [nlat][nlon] */

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "qd_bind": (_I, [_P, _P, _P]),
     "qd_set_params": (_I, [_P, _P]),
     "qd_set_rows": (_I, [_P, _P]),
+    "qd_set_rows_member": (_I, [_P, _I, _P]),
     "qd_get_scalars": (_I, [_P, _P]),
     "qd_upload_field": (_I, [_P, _I, _I, _P]),
     "qd_download_field": (_I, [_P, _I, _I, _P]),
@@ -89,6 +90,7 @@ PROTOTYPES = {
     "qd_minmax": (_I, [_P, _P, _P]),
     "qd_row_dev": (_P, [_P, _I]),
     "qd_user_row": (_P, [_P, _I, _P]),
+    "qd_user_row_member": (_I, [_P, _I, _I, _P]),
     "qd_laplacian_host": (_I, [_P, _P, _P, _P]),
     "qd_hyperdiffuse_host": (_I, [_P, _P, _P, _P, _D, _D, _I, _P]),
     "qd_advect_host": (_I, [_P, _P, _P, _P, _P, _D, _P]),

@@ -175,7 +175,10 @@ extern "C" int qd_profile_report(qd_ctx* c, char* buf, int buflen) {
 
 static inline double* F(qd_ctx* c, int id) { return c->fields + (size_t)id * c->batch * c->ncell; }
 static inline uint8_t* M(qd_ctx* c, int id) { return c->masks + (size_t)id * c->batch * c->ncell; }
-static inline const double* ROW(qd_ctx* c, int id) { return c->d_rows + (size_t)id * c->nlat; }
+static inline const double* ROW(qd_ctx* c, int id) { return c->d_rows + (size_t)id * c->nlat; }   // member 0's copy
+static inline bool qd_in_row_table(qd_ctx* c, const double* p) {
+  return p >= c->d_rows && p < c->d_rows + (size_t)c->batch * c->geo.row_bstride;
+}
 
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" int qd_version(void) { return 100; }
@@ -198,9 +201,9 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
 #endif
-  const size_t nrows = (size_t)(QD_R_COUNT + 3 * QD_NUSER_ROWS) * nlat;
+  const size_t nrows = (size_t)(QD_R_COUNT + 3 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
 #define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
-  QD_ALLOC(c->d_rows, nrows * 8);
+  QD_ALLOC(c->d_rows, (size_t)batch * nrows * 8);
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
   QD_ALLOC(c->d_prm, (size_t)batch * QD_P_COUNT * 8);
   QD_ALLOC(c->d_scal, (size_t)batch * QD_S_COUNT * 8);
@@ -230,7 +233,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #undef QD_ALLOC
   c->h_prm = (double*)malloc((size_t)batch * QD_P_COUNT * 8);
   memcpy(c->h_prm, params_host, (size_t)batch * QD_P_COUNT * 8);
-  cudaMemcpy(c->d_rows, rows_host, (size_t)QD_R_COUNT * nlat * 8, cudaMemcpyHostToDevice);
+  for (int b = 0; b < batch; ++b) cudaMemcpy(c->d_rows + (size_t)b * nrows, rows_host, (size_t)QD_R_COUNT * nlat * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_cols, cols_host, (size_t)QD_C_COUNT * nlon * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_prm, params_host, (size_t)batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice);
   {
@@ -246,7 +249,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
-  g.rows = c->d_rows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
+  g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
   *out = c;
   return QD_OK;
@@ -297,7 +300,14 @@ extern "C" int qd_set_params(qd_ctx* c, const double* p) {
 extern "C" int qd_set_rows(qd_ctx* c, const double* rows) {
   if (!c || !rows) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  QD_CUDA(c, cudaMemcpy(c->d_rows, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
+  for (int b = 0; b < c->batch; ++b)
+    QD_CUDA(c, cudaMemcpy(c->d_rows + (size_t)b * c->geo.row_bstride, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
+  return QD_OK;
+}
+extern "C" int qd_set_rows_member(qd_ctx* c, int member, const double* rows) {
+  if (!c || !rows || member < 0 || member >= c->batch) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QD_CUDA(c, cudaMemcpy(c->d_rows + (size_t)member * c->geo.row_bstride, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
   return QD_OK;
 }
 extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
@@ -317,8 +327,20 @@ extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_hos
     tmp[j] = x; tmp[c->nlat + j] = 1.0 / x; tmp[2 * (size_t)c->nlat + j] = 1.0 / (x * x);
   }
   double* dst = QD_USER_ROW(c, slot);
-  if (cudaMemcpy(dst, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  for (int b = 0; b < c->batch; ++b)
+    if (cudaMemcpy(dst + (size_t)b * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   return dst;
+}
+extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double* rows_host) {
+  if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host || member < 0 || member >= c->batch) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<double> tmp(3 * (size_t)c->nlat);
+  for (int j = 0; j < c->nlat; ++j) {
+    const double x = rows_host[j];
+    tmp[j] = x; tmp[c->nlat + j] = 1.0 / x; tmp[2 * (size_t)c->nlat + j] = 1.0 / (x * x);
+  }
+  QD_CUDA(c, cudaMemcpy(QD_USER_ROW(c, slot) + (size_t)member * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
+  return QD_OK;
 }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
@@ -379,6 +401,7 @@ static int op_hyper(qd_ctx* c, int n, double* const* fld, double* const* scratch
       H.src[k] = in_scratch ? scratch[k] : fld[k];
       H.dst[k] = in_scratch ? fld[k] : scratch[k];
       H.k4rows[k] = k4rows[k]; H.scale[k] = scale ? scale[k] : 1.0; H.raw_k4[k] = 1;
+      H.k4_bstride[k] = qd_in_row_table(c, k4rows[k]) ? c->geo.row_bstride : 0;
     }
     int rc = launch_hyper4(c, H); if (rc) return rc;
     in_scratch = !in_scratch;
@@ -728,6 +751,7 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
       H.k4rows[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[0] = ovu;
       H.k4rows[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[1] = ovv;
       H.k4rows[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[2] = ove;
+      H.k4_bstride[0] = H.k4_bstride[1] = H.k4_bstride[2] = c->geo.row_bstride;
       if (!ove) H.scale[2] = 0.5;                                       // ocean.py:352
       int rc = launch_hyper4(c, H); if (rc) return rc;
       inB = !inB;

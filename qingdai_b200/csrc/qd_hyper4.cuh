@@ -19,6 +19,7 @@ struct QdHyper4Args {
   const double* src[QD_MAX_FIELDS];
   double* dst[QD_MAX_FIELDS];
   const double* k4rows[QD_MAX_FIELDS];     // per-row coefficient table
+  long long k4_bstride[QD_MAX_FIELDS];     // member stride of that table (0: one table shared by every member)
   double scale[QD_MAX_FIELDS];             // multiplier on the table (0.5 for eta)
   int raw_k4[QD_MAX_FIELDS];               // 1: table already holds k4 (atmosphere / overrides); 0: k4 = table / max(1e-12, sub_dt)
   const double* cosr;                      // cosine rows followed by 1/c and 1/c^2
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
       const int oj = j0 + tid;
       double k4 = 0.0;
       if (oj < nlat) {
-        k4 = A.k4rows[k][oj];
+        k4 = A.k4rows[k][(size_t)b * A.k4_bstride[k] + oj];
         if (!A.raw_k4[k]) k4 = k4 / fmax(1e-12, sub_dt);       // ocean.py:347
         k4 = A.scale[k] * k4;
       }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
       const int oj = j0 + r;
       double k4 = 0.0;
       if (oj < nlat) {
-        k4 = A.k4rows[k][oj];
+        k4 = A.k4rows[k][(size_t)b * A.k4_bstride[k] + oj];
         if (!A.raw_k4[k]) k4 = k4 / fmax(1e-12, sub_dt);       // ocean.py:347
         k4 = A.scale[k] * k4;
       }

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_momentum(QdGeo g, QdOcMomA
   uo = uo + sub_dt * du;
   vo = vo + sub_dt * dv;
   if (A.land[c] == 1) { uo = 0.0; vo = 0.0; }
-  const double rex = qd_row(g, QD_R_OC_SPONGE)[j];
+  const double rex = qd_mrow(g, QD_R_OC_SPONGE, b)[j];
   uo = uo - sub_dt * rex * uo;
   vo = vo - sub_dt * rex * vo;
   A.ub[c] = uo;

@@ -19,7 +19,8 @@ struct QdGeo {
   double a, dlat, dlon, a_sq, dlon_sq;
   double inv_dlat, inv_2dlat, inv_dlon_sq, inv_a_sq;      // reciprocals used by the stencil kernels
   double inv_2dlon, inv_a;
-  const double* rows;    // [QD_R_COUNT + 4 user][nlat]
+  const double* rows;    // [B][QD_R_COUNT + 3*QD_NUSER_ROWS][nlat]; member 0's copy serves the geometry rows
+  long long row_bstride; // doubles between two members' tables
   const double* cols;    // [QD_C_COUNT][nlon]
   const double* prm;     // [B][QD_P_COUNT]
   double* scal;          // [B][QD_S_COUNT]
@@ -45,6 +46,8 @@ struct QdGaussW { int r; int wrap; double w[2 * QD_GAUSS_MAXR + 1]; };
   (void)i; (void)j; (void)off;
 
 QD_HD const double* qd_row(const QdGeo& g, int id) { return g.rows + (size_t)id * g.nlat; }
+// rows that follow a member's parameters (K4, ocean sponge, polar flag): member b's copy of the table
+QD_HD const double* qd_mrow(const QdGeo& g, int id, int b) { return g.rows + (size_t)b * g.row_bstride + (size_t)id * g.nlat; }
 QD_HD double qd_prm(const QdGeo& g, int b, int id) { return g.prm[(size_t)b * QD_P_COUNT + id]; }
 
 // ------------------------------------------------------------------------------ Laplacian

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     const double Hb = (P[QD_P_HAS_ELEVATION] != 0.0) ? A.elevation[c] : 0.0;
     const double S0 = A.ssnow[c];
     const double hs_geom = land ? qd_max(S0, 0.0) / qd_max(P[QD_P_RHO_SNOW], 1e-6) : 0.0;
-    const double hs_eff = (qd_row(g, QD_R_POLAR)[j] != 0.0) ? qd_min(hs_geom, P[QD_P_POLAR_ICE_THICK_MAX]) : hs_geom;
+    const double hs_eff = (qd_mrow(g, QD_R_POLAR, b)[j] != 0.0) ? qd_min(hs_geom, P[QD_P_POLAR_ICE_THICK_MAX]) : hs_geom;
     const double H_eff = qd_min(Hb + hs_eff, P[QD_P_LAND_ELEV_MAX]);
     const double T_hat = (P[QD_P_LAPSE_ENABLE] != 0.0) ? Ta_proxy - P[QD_P_LAPSE_KPM] * (H_eff / 1000.0) : Ta_proxy;
     const double f_snow = qd_clip(1.0 / (1.0 + exp((T_hat - P[QD_P_SNOW_THRESH]) / qd_max(1e-6, P[QD_P_SNOW_T_BAND]))), 0.0, 1.0);

@@ -220,6 +220,11 @@ class Engine:
             raise RuntimeError(f"qd_create failed with status {rc} (no CUDA device / out of memory?)")
         self.ctx = ctx
         self._chk(self.lib.qd_bind(self.ctx, _ptr(self.fields), _ptr(self.masks)), "qd_bind")
+        self._check_uniform_switches()
+        for b in range(1, self.batch):                                          # K4 / sponge / polar rows are per member
+            if self.params[b] is not self.params[0]:
+                rb, *_ = row_tables(self.nlat, self.nlon, self.params[b], dt)
+                self._chk(self.lib.qd_set_rows_member(self.ctx, b, _ptr(rb)), "qd_set_rows_member")
         if self.device.type == "cuda":
             self._chk(self.lib.qd_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "qd_set_stream")
         r1, w1 = gaussian_taps(1.0)
@@ -228,6 +233,19 @@ class Engine:
         rc_, wc = gaussian_taps(sig if sig > 0 else 0.2)
         self._chk(self.lib.qd_set_gauss(self.ctx, 1, rc_, 1, _ptr(wc)), "qd_set_gauss")
         self._finalizer = weakref.finalize(self, self.lib.qd_destroy, self.ctx)
+
+    # launch structure (which kernels run, cadences) is shared by the members of one batch; every
+    # continuous parameter (P vector, K4 / sponge / polar rows) is per member
+    _SWITCHES = ("diff_enable", "filter_type", "diff_every", "k4_nsub", "diff_q", "diff_cloud", "shapiro_every", "shapiro_n",
+                 "spec_every", "spec_cutoff", "spec_damp", "oc_diff_every", "oc_k4_nsub", "oc_shapiro_n",
+                 "oc_shapiro_every", "cloud_smooth_sigma", "k4_q", "k4_c")
+
+    def _check_uniform_switches(self):
+        p0 = self.params[0]
+        for p in self.params[1:]:
+            for name in self._SWITCHES:
+                if getattr(p, name) != getattr(p0, name):
+                    raise ValueError(f"ensemble members of one batch must share the launch-structure parameter {name!r}")
 
     # ---------------------------------------------------------------- plumbing
     def _chk(self, rc, what=""):
@@ -242,15 +260,22 @@ class Engine:
         """Re-snapshot parameters (and K4 rows when dt changed) into the device tables."""
         if dt is not None and dt != self.dt:
             self.dt = dt
-        rows, *_ = row_tables(self.nlat, self.nlon, self.params[0], self.dt)
-        self._rows = rows
-        self._chk(self.lib.qd_set_rows(self.ctx, _ptr(rows)), "qd_set_rows")
+        self._check_uniform_switches()
+        for b, p in enumerate(self.params):                                     # K4 / sponge / polar rows are per member
+            rows, *_ = row_tables(self.nlat, self.nlon, p, self.dt)
+            if b == 0:
+                self._rows = rows
+            self._chk(self.lib.qd_set_rows_member(self.ctx, b, _ptr(rows)), "qd_set_rows_member")
         pv = self._param_block()
         self._chk(self.lib.qd_set_params(self.ctx, _ptr(pv)), "qd_set_params")
-        p = self.params[0]
-        for slot, ov in ((2, p.oc_k4_u), (3, p.oc_k4_v), (4, p.oc_k4_eta)):      # ocean.py:350-352
-            if ov is not None:
-                self._user_row(slot, np.full(self.nlat, float(ov)))
+        p0 = self.params[0]
+        for slot, name in ((2, "oc_k4_u"), (3, "oc_k4_v"), (4, "oc_k4_eta")):    # ocean.py:350-352
+            if any((getattr(p, name) is None) != (getattr(p0, name) is None) for p in self.params):
+                raise ValueError("QD_OCEAN_K4_* overrides must be set for every ensemble member or for none")
+            if getattr(p0, name) is not None:
+                for b, p in enumerate(self.params):
+                    r = np.full(self.nlat, float(getattr(p, name)))
+                    self._chk(self.lib.qd_user_row_member(self.ctx, slot, b, _ptr(r)), "qd_user_row_member")
 
     def set_params(self, params):
         self.params = list(params) if isinstance(params, (list, tuple)) else [params] * self.batch
