@@ -45,6 +45,14 @@ ALG_BYTES = {
 }
 
 
+def alg_bytes_per_cell(name):
+    """Algorithmic bytes per cell of one launch; the fused del^4 tile kernel reads and writes each of its
+    n fields once (its profile name carries n: ``k_hyper4_tile<32>[3]``)."""
+    if name.startswith("k_hyper4_tile") and name.endswith("]"):
+        return 16 * int(name[name.rindex("[") + 1:-1])
+    return ALG_BYTES.get(name, 16)
+
+
 def workload(name):
     from qingdai_b200.params import QDParams
     full = dict(orog_enabled=True, energy_w=1.0, cloud_couple=True)
@@ -250,7 +258,7 @@ def main():
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         name, cnt, ms = rows[0]
         per_launch_s = ms / cnt * 1e-3
-        alg = ALG_BYTES.get(name, 16) * ncell * members
+        alg = alg_bytes_per_cell(name) * ncell * members
         achieved = alg / per_launch_s / 1e9
         traffic = None
         try:

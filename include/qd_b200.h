@@ -60,7 +60,7 @@ typedef enum {
   /* per-step products of the loop body */
   QD_F_PRECIP, QD_F_ALBEDO, QD_F_TEQ, QD_F_QNET, QD_F_CSNOW, QD_F_RLAND,
   /* ecology sub-daily (adapter.py:140-186) */
-  QD_F_EDAY, QD_F_FCANOPY, QD_F_ALPHA_ECO,
+  QD_F_EDAY, QD_F_FCANOPY, QD_F_ALPHA_ECO, QD_F_LAI_SNAP,
   /* private scratch (ping-pong partners and stencil intermediates) */
   QD_F_X0, QD_F_X1, QD_F_X2, QD_F_X3, QD_F_X4, QD_F_X5, QD_F_X6, QD_F_X7, QD_F_X8, QD_F_X9,
   QD_F_COUNT
@@ -140,6 +140,9 @@ typedef enum {
   QD_S_SUM_PQW = 0, QD_S_SUM_PRAWW, QD_S_MED_POS, QD_S_CNT_POS, QD_S_PREF, QD_S_CNT_PRECIP,
   QD_S_PREF_ATM, QD_S_CNT_PCOND, QD_S_MAX_UOCEAN, QD_S_MAX_VA, QD_S_ETA_NUM, QD_S_SUB_DT,
   QD_S_NSUB, QD_S_WSUM, QD_S_WSUM_OCEAN, QD_S_TMP0, QD_S_TMP1, QD_S_TMP2, QD_S_TMP3,
+  /* ecology canopy-cache clock (population.py:57-71,272-276): accumulated hours, next recompute,
+   * cache present, "recomputed in this step" flag */
+  QD_S_ECO_HOURS, QD_S_ECO_NEXT, QD_S_ECO_CACHED, QD_S_ECO_FLAG,
   QD_S_COUNT
 } qd_scalar_id;
 
@@ -250,6 +253,24 @@ int  qd_profile(qd_ctx* ctx, int enable);
 int  qd_profile_report(qd_ctx* ctx, char* buf, int buflen);   /* "name count total_ms" lines; sync */
 
 /* ------------------------------------------------------------------ routing (routing.py:211-335) */
+/* ------------------------------------------------------------------ ecology sub-daily
+ * Replaces EcologyAdapter.step_subdaily (adapter.py:140-186) + PopulationManager.step_subdaily /
+ * _should_recompute_canopy / _recompute_canopy_cache / canopy_reflectance_factor
+ * (population.py:252-286,831-841,895-915) and get_surface_albedo_bands (population.py:875-892).
+ * lai_layers_dev: caller-owned [B][n_layers][nlat][nlon] f64 = LAI_layers_SK flattened over species x layers
+ * (the daily ecology stays host Python and re-uploads it when it changes). */
+#define QD_ECO_MAX_BANDS 64
+int  qd_eco_bind(qd_ctx* ctx, const double* lai_layers_dev, int n_layers, double k_canopy,
+                 double update_every_hours, double lai_delta, int substep_every_nphys);
+/* clocks as PopulationManager.__init__ leaves them (hours=0, next=update_every_hours, no cache), the LAI
+ * snapshot = total LAI, adapter step counter = 0 */
+int  qd_eco_reset(qd_ctx* ctx, double hours, double next_hours, int cached, int step_count);
+/* one EcologyAdapter.step_subdaily call outside the fused loop: isr_dev [B][nlat][nlon]; alpha_dev receives the
+ * land alpha map (NaN on ocean) when the call is on the QD_ECO_SUBSTEP_EVERY_NPHYS cadence (*produced = 1) */
+int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alpha_dev, int* produced);
+/* A_b^surface [B][nb][nlat][nlon] (NaN on ocean) from the cached canopy factor */
+int  qd_eco_bands(qd_ctx* ctx, int nb, const double* r_eff_host, double soil_ref, double* out_dev);
+
 int  qd_route_setup(qd_ctx* ctx, int n_order, const int64_t* flow_order_host,
                     const int64_t* flow_to_host /* [ncell] */, const uint8_t* land_host,
                     const uint8_t* lake_host, const int32_t* lake_id_host,

@@ -104,6 +104,10 @@ PROTOTYPES = {
     "qd_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "qd_profile": (_I, [_P, _I]),
     "qd_profile_report": (_I, [_P, C.c_char_p, _I]),
+    "qd_eco_bind": (_I, [_P, _P, _I, _D, _D, _D, _I]),
+    "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
+    "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),
+    "qd_eco_bands": (_I, [_P, _I, _P, _D, _P]),
     "qd_route_setup": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "qd_route_levels": (_I, [_P]),
     "qd_route_accumulate": (_I, [_P, _D]),

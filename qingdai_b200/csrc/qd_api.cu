@@ -5,6 +5,7 @@
 // stays on the device in the per-member scalar table and is consumed by later kernels.
 #include "qd_loop.cuh"
 #include "qd_hyper4.cuh"
+#include "qd_eco.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -71,6 +72,9 @@ struct qd_ctx {
   char err[512];
   qd_route route;
   void* prof;
+  // ecology sub-daily (qd_eco.cuh)
+  const double* d_lai; int eco_nl, eco_every_nphys, eco_steps, eco_have_alpha;
+  double eco_k, eco_every_hours, eco_delta;
 };
 
 #ifndef QD_HOST_EMU
@@ -126,6 +130,10 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
 
 // Every launch goes through QD_KG so that launches are counted and, in profiling mode, bracketed by
 // CUDA events on the launching stream (per-kernel device time for bench.py's roofline object).
+#define QD_KGN(c, name, kern, grid, block, ...) do { \
+    const int pi_ = qd_prof_begin((c), (name)); \
+    QD_LAUNCH(kern, (grid), (block), (c)->stream, __VA_ARGS__); \
+    qd_prof_end((c), pi_); (c)->launches++; } while (0)
 #define QD_KG(c, kern, grid, block, ...) do { \
     const int pi_ = qd_prof_begin((c), #kern); \
     QD_LAUNCH(kern, (grid), (block), (c)->stream, __VA_ARGS__); \
@@ -197,6 +205,8 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
+  c->d_lai = nullptr; c->eco_nl = 0; c->eco_every_nphys = 1; c->eco_steps = 0; c->eco_have_alpha = 0;
+  c->eco_k = 0.5; c->eco_every_hours = 6.0; c->eco_delta = 0.05;
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
@@ -381,10 +391,14 @@ static int op_laplacian(qd_ctx* c, int n, const double* const* src, double* cons
 static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   const int tiles_i = (c->nlon + QD_H4_TI - 1) / QD_H4_TI;
   const long long blocks32 = (long long)tiles_i * ((c->nlat + 31) / 32) * c->batch * H.n;
+  // profile names carry the number of fields in the launch (bench.py: 16 B per cell and field)
+  static const char* const nm32[] = {"", "k_hyper4_tile<32>[1]", "k_hyper4_tile<32>[2]", "k_hyper4_tile<32>[3]", "k_hyper4_tile<32>[4]", "k_hyper4_tile<32>[5]"};
+  static const char* const nm8[] = {"", "k_hyper4_tile<8>[1]", "k_hyper4_tile<8>[2]", "k_hyper4_tile<8>[3]", "k_hyper4_tile<8>[4]", "k_hyper4_tile<8>[5]"};
+  const int nn = H.n < 1 ? 1 : (H.n > 5 ? 5 : H.n);
   if (blocks32 >= 2 * 148) {
-    QD_KG(c, k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    QD_KGN(c, nm32[nn], k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
   } else {
-    QD_KG(c, k_hyper4_tile<8>, dim3(tiles_i * ((c->nlat + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((c->nlat + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
   }
   return QD_OK;
 }
@@ -612,6 +626,73 @@ extern "C" int qd_advect_host(qd_ctx* c, const double* in, const double* u, cons
 }
 
 // ------------------------------------------------------------------------------ atmosphere step
+
+// ------------------------------------------------------------------------------ ecology sub-daily
+static QdEcoArgs eco_args(qd_ctx* c, double dt) {
+  QdEcoArgs E; memset(&E, 0, sizeof(E));
+  E.lai = c->d_lai; E.nl = c->eco_nl; E.snap = F(c, QD_F_LAI_SNAP); E.fcanopy = F(c, QD_F_FCANOPY);
+  for (int k = 0; k < 4; ++k) E.part[k] = c->d_part[k];
+  E.ticket = c->d_ticket + 7 * c->batch;
+  E.dt_hours = dt / 3600.0; E.every_hours = c->eco_every_hours; E.delta_thr = c->eco_delta; E.k_canopy = c->eco_k;
+  return E;
+}
+// clock + recompute decision + conditional cache rebuild (no LAI manager bound: QD_ECO_USE_LAI=0, nothing to do)
+static int eco_policy(qd_ctx* c, double dt) {
+  if (!c->d_lai) return QD_OK;
+  QdEcoArgs E = eco_args(c, dt);
+  QD_K(c, k_eco_stats, c->geo, E);
+  QD_K(c, k_eco_canopy, c->geo, E);
+  return QD_OK;
+}
+extern "C" int qd_eco_bind(qd_ctx* c, const double* lai, int nl, double k_canopy, double every_hours, double lai_delta, int every_nphys) {
+  if (!c || (lai && nl < 1)) return QD_E_INVALID;
+  c->d_lai = lai; c->eco_nl = lai ? nl : 0; c->eco_k = k_canopy; c->eco_every_hours = every_hours; c->eco_delta = lai_delta;
+  c->eco_every_nphys = every_nphys > 1 ? every_nphys : 1;
+  return QD_OK;
+}
+extern "C" int qd_eco_reset(qd_ctx* c, double hours, double next_hours, int cached, int step_count) {
+  if (!c) return QD_E_INVALID;
+  QD_BOUND(c);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<double> s((size_t)c->batch * QD_S_COUNT);
+  QD_CUDA(c, cudaMemcpy(s.data(), c->d_scal, s.size() * 8, cudaMemcpyDeviceToHost));
+  for (int b = 0; b < c->batch; ++b) {
+    double* S = s.data() + (size_t)b * QD_S_COUNT;
+    S[QD_S_ECO_HOURS] = hours; S[QD_S_ECO_NEXT] = next_hours; S[QD_S_ECO_CACHED] = cached ? 1.0 : 0.0; S[QD_S_ECO_FLAG] = 0.0;
+  }
+  QD_CUDA(c, cudaMemcpy(c->d_scal, s.data(), s.size() * 8, cudaMemcpyHostToDevice));
+  c->eco_steps = step_count; c->eco_have_alpha = 0;
+  if (c->d_lai) {                                   // _lai_snapshot = total_LAI().copy()  (population.py:70)
+    QdEcoArgs E = eco_args(c, 0.0);
+    QD_K(c, k_eco_snapshot, c->geo, E);
+    QD_CHECK_LAUNCH(c);
+  }
+  return QD_OK;
+}
+extern "C" int qd_eco_subdaily(qd_ctx* c, const double* isr, double dt, double* alpha, int* produced) {
+  if (!c || !isr) return QD_E_INVALID;
+  QD_BOUND(c);
+  int rc = eco_policy(c, dt); if (rc) return rc;
+  c->eco_steps += 1;
+  const int want = (c->eco_steps % std::max(1, c->eco_every_nphys) == 0) && alpha;
+  QdEcoCellArgs A; A.isr = isr; A.fcanopy = F(c, QD_F_FCANOPY); A.eday = F(c, QD_F_EDAY); A.alpha = alpha;
+  A.land = M(c, QD_M_LAND); A.dt = dt; A.want_alpha = want;
+  QD_K(c, k_eco_cell, c->geo, A);
+  QD_CHECK_LAUNCH(c);
+  if (produced) *produced = want;
+  return QD_OK;
+}
+extern "C" int qd_eco_bands(qd_ctx* c, int nb, const double* r_eff, double soil, double* out) {
+  if (!c || nb < 1 || nb > QD_ECO_MAX_BANDS || !r_eff || !out) return QD_E_INVALID;
+  QD_BOUND(c);
+  QdEcoBandArgs A; memset(&A, 0, sizeof(A));
+  A.fcanopy = F(c, QD_F_FCANOPY); A.land = M(c, QD_M_LAND); A.out = out; A.nb = nb; A.soil = soil;
+  for (int k = 0; k < nb; ++k) A.r_eff[k] = r_eff[k];
+  QD_K(c, k_eco_bands, c->geo, A);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+
 static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   const double dt = cfg->dt;
   const int has_alb = mode_loop ? cfg->loop_with_albedo : cfg->has_albedo;
@@ -629,7 +710,15 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   A.land = M(c, QD_M_LAND); A.glacier = M(c, QD_M_GLACIER);
   A.forcing = c->d_forcing; A.step_idx = c->d_step_idx;
   A.dt = dt; A.mode_loop = mode_loop; A.has_albedo = has_alb; A.has_cloud_eff = c->has_cloud_eff;
-  A.with_hydrology = cfg->with_hydrology; A.with_eco = cfg->with_eco; A.store_isr_ab = cfg->store_isr_ab;
+  A.with_hydrology = cfg->with_hydrology; A.with_eco = 0; A.store_isr_ab = cfg->store_isr_ab;
+  if (cfg->with_eco && mode_loop) {
+    // adapter.py:148-157: the adapter's call counter decides whether a new alpha map is produced this step;
+    // otherwise the script keeps using the last one (run_simulation.py:2083-2086)
+    int rc = eco_policy(c, dt); if (rc) return rc;
+    c->eco_steps += 1;
+    if (c->eco_steps % std::max(1, c->eco_every_nphys) == 0) { A.with_eco = 1; c->eco_have_alpha = 1; }
+    else A.with_eco = c->eco_have_alpha ? 2 : 3;
+  }
   QD_K(c, k_column, c->geo, A);
 
   if (has_alb) {
@@ -989,7 +1078,10 @@ static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
   const bool o_shp = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (on % cfg->oc_shapiro_every == 0);
   unsigned long long key = 1469598103934665603ull;
   auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+  const int en = c->eco_steps + 1;
+  const bool eco_new = cfg->with_eco && (en % std::max(1, c->eco_every_nphys) == 0);
   mix(a_hyp); mix(a_shp); mix(a_spc); mix(o_hyp); mix(o_shp); mix(c->has_cloud_eff); mix(c->route.ready);
+  mix(cfg->with_eco ? (eco_new ? 1 : (c->eco_have_alpha ? 2 : 3)) : 0); mix(c->d_lai != nullptr); mix((unsigned long long)c->eco_nl);
   { const unsigned char* p = (const unsigned char*)cfg; for (size_t k = 0; k < sizeof(*cfg); ++k) mix(p[k]); }
   auto it = c->step_graphs.find(key);
   if (it != c->step_graphs.end()) {
@@ -998,11 +1090,12 @@ static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
     c->atm_counter = an;
     if (cfg->with_ocean) c->oc_counter = on;
     if (cfg->loop_with_albedo) c->has_cloud_eff = 1;
+    if (cfg->with_eco) { c->eco_steps = en; if (eco_new) c->eco_have_alpha = 1; }
     c->launches += it->second.second;
     return QD_OK;
   }
   // build: capture this step once, then launch it
-  const int sa = c->atm_counter, so = c->oc_counter, sce = c->has_cloud_eff;
+  const int sa = c->atm_counter, so = c->oc_counter, sce = c->has_cloud_eff, ses = c->eco_steps, sea = c->eco_have_alpha;
   const long long sl = c->launches;
   cudaStream_t saved = c->stream;
   cudaGraph_t G = nullptr; cudaGraphExec_t exec = nullptr;
@@ -1025,7 +1118,7 @@ static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (G) cudaGraphDestroy(G);
   const long long per_step = c->launches - sl;
   if (!ok) {
-    c->atm_counter = sa; c->oc_counter = so; c->has_cloud_eff = sce; c->launches = sl;
+    c->atm_counter = sa; c->oc_counter = so; c->has_cloud_eff = sce; c->launches = sl; c->eco_steps = ses; c->eco_have_alpha = sea;
     c->step_graphs[key] = std::make_pair((cudaGraphExec_t) nullptr, 0ll);
     return QD_E_STATE;
   }

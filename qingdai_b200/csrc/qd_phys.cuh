@@ -223,12 +223,18 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     if (A.with_eco) {
       // adapter.py:140-186: E_day += nan_to_num(isr)*dt; alpha = leaf*f + (1-f)*soil on land, NaN on ocean
       A.eday[c] = A.eday[c] + qd_nan_to_num(isr) * dt;
+      // with_eco: 1 = the adapter produces a new alpha map this step, 2 = the script re-uses the last map
+      // (run_simulation.py:2083-2086), 3 = no map yet
       double alpha_e = NAN;
-      if (land) {
-        const double fc = A.fcanopy[c];
-        alpha_e = qd_clip(P[QD_P_ECO_ALPHA_LEAF] * fc + (1.0 - fc) * P[QD_P_ECO_SOIL_REFLECT], 0.0, 1.0);
+      if (A.with_eco == 1) {
+        if (land) {
+          const double fc = A.fcanopy[c];
+          alpha_e = qd_clip(P[QD_P_ECO_ALPHA_LEAF] * fc + (1.0 - fc) * P[QD_P_ECO_SOIL_REFLECT], 0.0, 1.0);
+        }
+        A.alpha_eco[c] = alpha_e;
+      } else if (A.with_eco == 2) {
+        alpha_e = A.alpha_eco[c];
       }
-      A.alpha_eco[c] = alpha_e;
       if (land && !glacier && isfinite(alpha_e))
         base = (1.0 - P[QD_P_ECO_W_LAI]) * base + P[QD_P_ECO_W_LAI] * alpha_e;
     }

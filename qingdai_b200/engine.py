@@ -350,6 +350,15 @@ class Engine:
         self.set("orog_ny", ny, member)
         self.refresh_params()
 
+    def bind_eco(self, lai_dev, n_layers, k_canopy, every_hours, lai_delta, substep_every=1):
+        """Hand the LAI layers [B, S*K, nlat, nlon] (device tensor, kept alive here) to the library."""
+        self._lai_dev = lai_dev
+        ptr = _ptr(lai_dev) if lai_dev is not None else C.c_void_p(0)
+        self._chk(self.lib.qd_eco_bind(self.ctx, ptr, int(n_layers), float(k_canopy), float(every_hours), float(lai_delta), int(substep_every)), "qd_eco_bind")
+
+    def eco_reset(self, hours, next_hours, cached=False, step_count=0):
+        self._chk(self.lib.qd_eco_reset(self.ctx, float(hours), float(next_hours), int(bool(cached)), int(step_count)), "qd_eco_reset")
+
     def set_eco(self, enabled, alpha_leaf_scalar=0.0):
         self._eco_on, self._eco_leaf = bool(enabled), float(alpha_leaf_scalar)
         self.refresh_params()

@@ -31,7 +31,7 @@ def q_sat_host(T, p0):
 class Simulation:
     def __init__(self, nlat, nlon, topo: dict | Sequence[dict], params: Optional[QDParams | Sequence[QDParams]] = None,
                  dt=300, batch=1, with_ocean=True, with_hydrology=True, with_eco=False, loop_with_albedo=False,
-                 device=None, lib=None, t0=0.0):
+                 device=None, lib=None, t0=0.0, eco_env=None):
         self.grid = SphericalGrid(nlat, nlon)
         plist = list(params) if isinstance(params, (list, tuple)) else [params or QDParams.from_env()] * batch
         self.engine = Engine(nlat, nlon, batch=batch, params=plist, dt=dt, device=device, lib=lib)
@@ -53,6 +53,14 @@ class Simulation:
             for b, tp in enumerate(topos):
                 e.set_elevation(tp["elevation"], member=b)
         self.reset_state()
+        self.eco = None
+        if with_eco:
+            # run_simulation.py:1335-1337 builds the adapter; :1716-1723 calls it once at t=0 before the loop
+            from .ecology import EcologyAdapter
+            if batch != 1:
+                raise ValueError("with_eco drives one ensemble member per Simulation")
+            self.eco = EcologyAdapter(self.grid, topos[0]["land_mask"], engine=e, env=eco_env)
+            self.eco.step_subdaily(self.forcing.calculate_insolation(float(t0)), 0.0, dt)
 
     def reset_state(self):
         """SpectralModel.__init__ / WindDrivenSlabOcean.__init__ initial fields (dynamics.py:56-88, ocean.py:85-94)."""

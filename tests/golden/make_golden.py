@@ -400,6 +400,130 @@ def gen_loop():
     print("loop_golden.npz:", len(out), "arrays")
 
 
+# ------------------------------------------------------------------------------------ ecology sub-daily
+def gen_eco():
+    """EcologyAdapter.step_subdaily / PopulationManager canopy-cache policy / get_surface_albedo_bands
+    (adapter.py:140-186, population.py:252-286,831-915) driven directly, plus the unmodified main()
+    loop with QD_ECO_ENABLE=1 (run_simulation.py:1716-1723,2064-2106)."""
+    from pygcm.grid import SphericalGrid
+    from pygcm.ecology import EcologyAdapter
+    import scripts.run_simulation as rs
+    import tempfile
+    out = {}
+    unit_cases = {
+        "u1": ({}, (19, 36), 1800.0),
+        "u2": ({"QD_ECO_NS": "3", "QD_ECO_SPECIES_WEIGHTS": "0.5,0.3,0.2", "QD_ECO_COHORT_K": "2", "QD_ECO_RAND_SEED": "7",
+                "QD_ECO_LIGHT_UPDATE_EVERY_HOURS": "2", "QD_ECO_TOA_TO_SURF_MODE": "rayleigh", "QD_ECO_SOIL_REFLECT": "0.17",
+                "QD_ECO_LAI_K": "0.65", "QD_ECO_SPECIES_1_PEAKS": "500:35:0.7, 640:25:0.5", "QD_ECO_SUBSTEP_EVERY_NPHYS": "2"},
+               (15, 27), 2700.0),
+    }
+    for tag, (env, (nlat, nlon), dt) in unit_cases.items():
+        set_env(env)
+        rng = np.random.default_rng(300 + nlat)
+        grid = SphericalGrid(nlat, nlon)
+        land = (rng.uniform(size=(nlat, nlon)) < 0.4).astype(np.uint8)
+        with quiet():
+            eco = EcologyAdapter(grid, land)
+        pop = eco.pop
+        out[f"{tag}_land"] = land
+        out[f"{tag}_dt"] = np.array(dt)
+        out[f"{tag}_env"] = np.array(repr(env))
+        out[f"{tag}_alpha_leaf_scalar"] = np.array(eco.alpha_leaf_scalar)
+        out[f"{tag}_w_b"] = np.array(eco.w_b)
+        out[f"{tag}_R_leaf"] = np.array(eco.R_leaf)
+        out[f"{tag}_R_species"] = np.array(pop._species_R_leaf)
+        out[f"{tag}_species_weights"] = np.array(pop.species_weights)
+        out[f"{tag}_lai0"] = np.array(pop.LAI_layers_SK)
+        ncalls = 14
+        out[f"{tag}_ncalls"] = np.array(ncalls)
+        for n in range(ncalls):
+            isr = np.maximum(0.0, rng.standard_normal((nlat, nlon)) * 300.0 + 200.0)
+            if n == 3:
+                isr[1, 2], isr[4, 5] = np.nan, np.inf
+            if n == 5:
+                pop.LAI_layers_SK = pop.LAI_layers_SK * (1.0 + 0.4 * rng.uniform(size=pop.LAI_layers_SK.shape))
+            if n == 9:
+                pop.LAI_layers_SK = pop.LAI_layers_SK * 1.01
+            out[f"{tag}_c{n}_isr"] = isr
+            out[f"{tag}_c{n}_lai"] = np.array(pop.LAI_layers_SK)
+            with quiet():
+                a = eco.step_subdaily(isr, 0.3, dt)
+            out[f"{tag}_c{n}_alpha_is_none"] = np.array(a is None)
+            if a is not None:
+                out[f"{tag}_c{n}_alpha"] = np.array(a)
+            out[f"{tag}_c{n}_E_day"] = np.array(pop.E_day)
+            out[f"{tag}_c{n}_f"] = np.array(pop._canopy_f_cached)
+            out[f"{tag}_c{n}_snap"] = np.array(pop._lai_snapshot)
+            out[f"{tag}_c{n}_clock"] = np.array([pop._hours_accum, pop._next_recompute_hours])
+        A, w = eco.get_surface_albedo_bands()
+        out[f"{tag}_bands_A"], out[f"{tag}_bands_w"] = np.array(A), np.array(w)
+
+    # ---- the unmodified main() with the ecology sub-daily coupling on
+    nlat, nlon = 31, 60
+    tag = "loop"
+    set_env({"QD_ECO_ENABLE": "1", "QD_HYDRO_ENABLE": "0", "QD_ECO_LIGHT_UPDATE_EVERY_HOURS": "0.25"})
+    os.environ["QD_PLOT_EVERY_DAYS"] = "1e-9"
+    dt = 300
+    nsteps = 8
+    os.environ["QD_SIM_DAYS"] = repr((nsteps - 0.5) * dt / (2 * np.pi / 8.726646259971648e-5))
+    rec, holder, statics = [], {}, {}
+    real_adapter = rs.EcologyAdapter
+
+    def make_adapter(grid, land_mask):
+        holder["eco"] = real_adapter(grid, land_mask)
+        return holder["eco"]
+
+    def hook_plot_state(grid, gcm, land_mask, precip, cloud_cover, albedo, t_days, output_dir, ocean=None, routing=None):
+        d = snap_gcm(gcm)
+        d.update(snap_oc(ocean))
+        d["precip"], d["albedo"] = np.array(precip, copy=True), np.array(albedo, copy=True)
+        d["land_mask"] = np.array(land_mask)
+        d["C_snow"] = np.array(gcm.C_snow_map_last, dtype=np.float64)
+        d["glacier"] = np.array(gcm.glacier_mask_last)
+        pop = holder["eco"].pop
+        d["E_day"], d["f_canopy"] = np.array(pop.E_day), np.array(pop._canopy_f_cached)
+        d["eco_clock"] = np.array([pop._hours_accum, pop._next_recompute_hours])
+        rec.append(d)
+
+    real_gen = rs.generate_base_properties
+
+    def hook_gen(mask, *a, **k):
+        alb, fr = real_gen(mask, *a, **k)
+        statics["base_albedo"], statics["friction"] = alb.copy(), fr.copy()
+        return alb, fr
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp, \
+            mock.patch.object(rs, "SphericalGrid", lambda n_lat, n_lon: __import__("pygcm.grid", fromlist=["SphericalGrid"]).SphericalGrid(nlat, nlon)), \
+            mock.patch.object(rs, "plot_state", hook_plot_state), \
+            mock.patch.object(rs, "plot_true_color", lambda *a, **k: None), \
+            mock.patch.object(rs, "plot_ecology", lambda *a, **k: None), \
+            mock.patch.object(rs, "EcologyAdapter", make_adapter), \
+            mock.patch.object(rs, "generate_base_properties", hook_gen):
+        os.chdir(tmp)
+        try:
+            with quiet():
+                rs.main()
+        finally:
+            os.chdir(cwd)
+    assert len(rec) == nsteps, (len(rec), nsteps)
+    eco = holder["eco"]
+    for k, v in statics.items():
+        out[f"{tag}_{k}"] = v
+    out[f"{tag}_land_mask"] = rec[0]["land_mask"]
+    out[f"{tag}_dt"], out[f"{tag}_nsteps"] = np.array(dt), np.array(nsteps)
+    out[f"{tag}_alpha_leaf_scalar"] = np.array(eco.alpha_leaf_scalar)
+    out[f"{tag}_lai"] = np.array(eco.pop.LAI_layers_SK)
+    for i, d in enumerate(rec):
+        for k, v in d.items():
+            if k in ("land_mask", "isr", "olr", "LH_release_last"):
+                continue
+            out[f"{tag}_s{i}_{k}"] = v
+    out["loop_nlat"], out["loop_nlon"] = np.array(nlat), np.array(nlon)
+    np.savez_compressed(os.path.join(OUT, "eco_golden.npz"), **out)
+    print("eco_golden.npz:", len(out), "arrays")
+
+
 def gen_routing():
     """Network from the reference's own builder (scripts/generate_hydrology_maps.py:85-273) on a small
     procedural elevation, then pygcm.routing.RiverRouting (unmodified, fed through an in-memory stand-in
@@ -468,6 +592,8 @@ def main():
         gen_loop()
     if "routing" in which:
         gen_routing()
+    if "eco" in which:
+        gen_eco()
 
 
 if __name__ == "__main__":

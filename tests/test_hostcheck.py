@@ -84,3 +84,12 @@ def test_routing(lib, golden, tag):
 
 def test_graph_levels_are_noops_in_host_build(lib, L):
     qdcheck.check_graph_levels_agree(lib, L, nsteps=7)
+
+
+@pytest.mark.parametrize("tag", ["u1", "u2"])
+def test_ecology_adapter(lib, golden, tag):
+    qdcheck.check_eco_unit(lib, golden("eco_golden.npz"), tag)
+
+
+def test_loop_with_ecology(lib, golden):
+    qdcheck.check_eco_loop(lib, golden("eco_golden.npz"))
