@@ -52,6 +52,7 @@ struct qd_ctx {
   double* fields; uint8_t* masks;
   double* d_part[QD_NPART]; unsigned* d_ticket;
   unsigned* d_hist; unsigned long long* d_mingt; int sel_gx;
+  unsigned long long* d_sel_list; unsigned* d_sel_cnt; int* d_sel_more;
   qd_forcing_t* d_forcing; int forcing_cap; int* d_step_idx; double* d_hcos;
   double *d_twid, *d_spec_coef, *d_spec_out;
   double* d_stage[5];
@@ -221,6 +222,10 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   QD_ALLOC(c->d_ticket, (size_t)batch * 8 * sizeof(unsigned));
   QD_ALLOC(c->d_hist, (size_t)QD_SEL_PASSES * batch * QD_SEL_MAXBINS * sizeof(unsigned));
   QD_ALLOC(c->d_mingt, (size_t)batch * sizeof(unsigned long long));
+  cudaMemset(c->d_mingt, 0xff, (size_t)batch * sizeof(unsigned long long));
+  QD_ALLOC(c->d_sel_list, (size_t)batch * QD_SEL_CAP * sizeof(unsigned long long));
+  QD_ALLOC(c->d_sel_cnt, (size_t)batch * sizeof(unsigned));
+  QD_ALLOC(c->d_sel_more, sizeof(int));
   c->sel_gx = 1;
 #ifndef QD_HOST_EMU
   {
@@ -277,7 +282,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal);
   for (int k = 0; k < QD_NPART; ++k) cudaFree(c->d_part[k]);
-  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
+  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_sel_list); cudaFree(c->d_sel_cnt); cudaFree(c->d_sel_more); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
   cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
@@ -477,10 +482,9 @@ static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst
   qd_select_host(c->geo, x, out);
   c->launches++;
 #else
-  QD_CUDA(c, cudaMemsetAsync(c->d_hist, 0, (size_t)QD_SEL_PASSES * c->batch * QD_SEL_MAXBINS * sizeof(unsigned), c->stream));
-  QD_CUDA(c, cudaMemsetAsync(c->d_mingt, 0xff, (size_t)c->batch * sizeof(unsigned long long), c->stream));
+  // the kernel leaves hist / list counter / mingt reset for the next launch (no memset nodes in the step graph)
   QdGeo geo = c->geo;
-  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_mingt, (void*)&out};
+  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_sel_list, (void*)&c->d_sel_cnt, (void*)&c->d_mingt, (void*)&c->d_sel_more, (void*)&out};
   const int pi = qd_prof_begin(c, "k_select_coop");
   QD_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_select_coop, dim3(c->sel_gx, c->batch), dim3(QD_SEL_THREADS), args, 0, c->stream));
   qd_prof_end(c, pi);

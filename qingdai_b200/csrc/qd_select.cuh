@@ -2,18 +2,19 @@
 //
 // np.median(x[x>0]) (physics.py:298-301, run_simulation.py:1872-1873, dynamics.py:344-348) is an
 // exact order statistic; the loop needs three of them per step.  Positive IEEE doubles order like
-// their 63-bit patterns, so the lower-middle element is found by an MSD radix select with digits
-// of 11 (exponent) + 4 x 13 bits.  Every pass builds a shared-memory histogram per block, merges it
-// into a per-(pass, member) global histogram, and after one grid-wide sync every block locates the
-// digit redundantly (no second sync, no host round trip).  A closing pass finds the smallest
-// element above the lower median for even counts (np.median = mean of the two middle values).
-// The whole selection is ONE persistent cooperative launch: 6 grid syncs instead of ~15 launches.
+// their 63-bit patterns, so the lower-middle element is found by an MSD radix select with 13-bit digits.
+// Every pass builds a shared-memory histogram per block, merges it into a per-(pass, member) global
+// histogram, and after one grid-wide sync every block locates the digit redundantly (no second sync, no
+// host round trip).  As soon as <= QD_SEL_CAP candidates remain they are gathered and sorted by one block,
+// which also yields the upper middle element for even counts (np.median = mean of the two middle values).
+// The whole selection is ONE persistent cooperative launch.
 #pragma once
 #include "qd_ops.cuh"
 
 #define QD_SEL_PASSES 5
 #define QD_SEL_MAXBINS 8192
 #define QD_SEL_THREADS 512
+#define QD_SEL_CAP 2048          // candidates finished by an in-block sort instead of further radix passes
 
 struct QdSelOut { double* value; double* count; int stride; double empty_value; };
 
@@ -21,14 +22,15 @@ struct QdSelOut { double* value; double* count; int stride; double empty_value; 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-// Finds, for one member, the bin holding 0-based rank `rank` in hist[0..nbins), returns the bin and
-// sets *below (elements in lower bins), *inbin (elements in that bin), *total.  Block-cooperative.
-__device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, int nbins, unsigned long long rank,
+// Finds, for one member, the bin holding 0-based rank `*rank` in hist[0..nbins) and sets *below (elements
+// in lower bins), *inbin (elements in that bin), *total.  With first != 0 the rank is the lower-median
+// index (total - 1) / 2 of the whole histogram and is returned through *rank.  Block-cooperative.
+__device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, int nbins, unsigned long long* rank, int first,
                                               unsigned* sh, unsigned long long* part,
                                               unsigned long long* below, unsigned long long* inbin,
-                                              unsigned long long* total, int* next_nonempty) {
-  __shared__ int s_bin, s_next;
-  __shared__ unsigned long long s_below, s_inbin, s_total;
+                                              unsigned long long* total) {
+  __shared__ int s_bin;
+  __shared__ unsigned long long s_below, s_inbin, s_total, s_rank;
   const int t = threadIdx.x;
   for (int k = t; k < nbins; k += QD_SEL_THREADS) sh[k] = __ldcg(hist + k);
   __syncthreads();
@@ -44,98 +46,159 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
     unsigned long long inc = ls;
     for (int o = 1; o < 32; o <<= 1) { unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o); if (t >= o) inc += y; }
     const unsigned long long tot = __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned long long rk = first ? (tot ? (tot - 1) / 2 : 0) : *rank;
     const unsigned long long exc = inc - ls;
-    const unsigned ball = __ballot_sync(0xffffffffu, inc > rank);
+    const unsigned ball = __ballot_sync(0xffffffffu, inc > rk);
     const int lane = ball ? (__ffs(ball) - 1) : 31;
     if (t == lane) {
       unsigned long long cum = exc;
       int c = t * pl;
-      for (; c < t * pl + pl - 1; ++c) { if (cum + part[c] > rank) break; cum += part[c]; }
+      for (; c < t * pl + pl - 1; ++c) { if (cum + part[c] > rk) break; cum += part[c]; }
       int k = c * per;
       const int kend = min(k + per, nbins) - 1;
-      for (; k < kend; ++k) { if (cum + sh[k] > rank) break; cum += sh[k]; }
-      int nx = -1;
-      for (int q = k + 1; q < nbins; ++q) if (sh[q]) { nx = q; break; }
-      s_bin = k; s_below = cum; s_inbin = sh[k]; s_total = tot; s_next = nx;
+      for (; k < kend; ++k) { if (cum + sh[k] > rk) break; cum += sh[k]; }
+      s_bin = k; s_below = cum; s_inbin = sh[k]; s_total = tot; s_rank = rk;
     }
   }
   __syncthreads();
-  *below = s_below; *inbin = s_inbin; *total = s_total; *next_nonempty = s_next;
+  *below = s_below; *inbin = s_inbin; *total = s_total; *rank = s_rank;
   const int r = s_bin;
   __syncthreads();
   return r;
 }
 
+// Radix passes of 13 bits (the first covers the exponent and two mantissa bits) narrow the candidates
+// until at most QD_SEL_CAP share the prefix -- two passes for continuous data of any size here -- then ONE
+// gather pass appends them to a list (and records the smallest key above the prefix bucket); block 0 sorts
+// the list in shared memory and reads both middle elements.  Heavily duplicated data simply keeps taking
+// radix passes down to bit 0.  3 sweeps + 3 grid syncs in the common case instead of 6 + 6.
+// hist / list counter / mingt are left zeroed (resp. all-ones) for the next launch: no memset nodes.
 __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
-                                                               unsigned long long* mingt, QdSelOut out) {
+                                                               unsigned long long* list, unsigned* lcount,
+                                                               unsigned long long* mingt, int* more_flag, QdSelOut out) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ unsigned sh[QD_SEL_MAXBINS];
+  __shared__ __align__(16) unsigned sh[QD_SEL_MAXBINS];
   __shared__ unsigned long long part[QD_SEL_THREADS];
   const int b = blockIdx.y;
   const size_t off = (size_t)b * g.ncell;
   const int stride = gridDim.x * QD_SEL_THREADS;
   const int t0 = blockIdx.x * QD_SEL_THREADS + threadIdx.x;
-  const int shifts[QD_SEL_PASSES] = {52, 39, 26, 13, 0};
-  const int nbits[QD_SEL_PASSES] = {11, 13, 13, 13, 13};
-  unsigned long long prefix = 0, rank = 0, count = 0, le = 0;
-  for (int pass = 0; pass < QD_SEL_PASSES; ++pass) {
+  const int shifts[QD_SEL_PASSES] = {50, 37, 24, 11, 0};
+  const int nbits[QD_SEL_PASSES] = {13, 13, 13, 13, 11};
+  unsigned long long prefix = 0, rank = 0, count = 0, inbin = ~0ull;
+  int npass = 0, lo_shift = 63;
+  // One radix pass.  Every block of the GRID takes part in the sync; members whose candidates already fit
+  // the list (work == false) skip the sweep.
+  auto radix_pass = [&](int pass, bool work) {
     const int shift = shifts[pass], nb = 1 << nbits[pass];
     unsigned* gh = hist + ((size_t)pass * g.batch + b) * QD_SEL_MAXBINS;
-    for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) sh[k] = 0;
-    __syncthreads();
-    const int hi = shift + nbits[pass];
-    for (int idx = t0; idx < g.ncell; idx += stride) {
-      const double v = x[off + idx];
-      if (v > 0.0) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-        if (pass == 0 || (key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
+    if (work) {
+      for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) sh[k] = 0;
+      __syncthreads();
+      const int hi = shift + nbits[pass];
+      for (int idx = t0; idx < g.ncell; idx += stride) {
+        const double v = x[off + idx];
+        if (v > 0.0) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+          if (pass == 0 || (key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
+        }
       }
+      __syncthreads();
+      for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) { const unsigned c = sh[k]; if (c) atomicAdd(gh + k, c); }
+      __threadfence();
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) { const unsigned c = sh[k]; if (c) atomicAdd(gh + k, c); }
-    __threadfence();
     grid.sync();
-    unsigned long long below, inbin, total; int nx;
-    const int bin = qd_sel_locate(gh, nb, rank, sh, part, &below, &inbin, &total, &nx);
-    if (pass == 0) {
-      count = total;
-      rank = count ? (count - 1) / 2 : 0;
-      // rank changed from 0 -> relocate with the real rank (members with no positives keep going:
-      // every block of the grid must reach every grid.sync)
-      const int bin2 = qd_sel_locate(gh, nb, rank, sh, part, &below, &inbin, &total, &nx);
-      prefix |= ((unsigned long long)bin2) << shift;
-    } else {
+    if (work) {
+      unsigned long long below, total;
+      const int bin = qd_sel_locate(gh, nb, &rank, pass == 0, sh, part, &below, &inbin, &total);
+      if (pass == 0) count = total;
       prefix |= ((unsigned long long)bin) << shift;
+      rank -= below;
+      npass = pass + 1; lo_shift = shift;
     }
-    le += below;
-    rank -= below;
-    if (pass == QD_SEL_PASSES - 1) le += inbin;            // all elements of the last bucket equal L
-  }
-  // closing pass: smallest element above L when the upper middle element is not L itself
-  const double L = __longlong_as_double((long long)prefix);
-  const bool need_upper = count > 0 && !(count & 1ull) && !(le > count / 2);
-  if (need_upper) {
-    unsigned long long m = ~0ull;
-    for (int idx = t0; idx < g.ncell; idx += stride) {
-      const double v = x[off + idx];
-      if (v > L) { const unsigned long long key = (unsigned long long)__double_as_longlong(v); if (key < m) m = key; }
+  };
+  // Gather pass: candidates sharing the prefix -> list (when they fit); smallest key above the prefix
+  // bucket -> mingt (needed when the upper middle element of an even count lies outside the bucket).
+  auto gather_pass = [&](bool work) {
+    const bool fits = inbin <= QD_SEL_CAP;
+    const bool need_above = count > 0 && !(count & 1ull) && (rank + 1 >= inbin);
+    if (work && ((fits && inbin > 0) || need_above)) {
+      unsigned long long m = ~0ull;
+      unsigned long long* lst = list + (size_t)b * QD_SEL_CAP;
+      const unsigned long long pk = prefix >> lo_shift;
+      for (int idx = t0; idx < g.ncell; idx += stride) {
+        const double v = x[off + idx];
+        if (v > 0.0) {
+          const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+          const unsigned long long kk = key >> lo_shift;
+          if (kk == pk) { if (fits) lst[atomicAdd(lcount + b, 1u)] = key; }
+          else if (kk > pk && key < m) m = key;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_down_sync(0xffffffffu, m, o); if (y < m) m = y; }
+      if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(mingt + b, m);
+      __threadfence();
     }
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_down_sync(0xffffffffu, m, o); if (y < m) m = y; }
-    if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(mingt + b, m);
-    __threadfence();
+    grid.sync();
+  };
+  radix_pass(0, true);
+  radix_pass(1, inbin > QD_SEL_CAP);
+  const bool more = inbin > QD_SEL_CAP;                    // heavily duplicated data: keep narrowing
+  if (more && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(more_flag, 1);
+  gather_pass(!more);
+  if (__ldcg(more_flag)) {                                 // grid-uniform (set before the sync above)
+    radix_pass(2, more);
+    radix_pass(3, more && inbin > QD_SEL_CAP);
+    radix_pass(4, more && inbin > QD_SEL_CAP);
+    gather_pass(more);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *more_flag = 0;
   }
-  grid.sync();
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  // leave the histograms of the passes that ran zeroed for the next launch (every block is past its reads)
+  for (int p = 0; p < npass; ++p) {
+    unsigned* gh = hist + ((size_t)p * g.batch + b) * QD_SEL_MAXBINS;
+    for (int k = t0; k < (1 << nbits[p]); k += stride) gh[k] = 0u;
+  }
+  if (blockIdx.x != 0) return;
+  const bool fits = inbin <= QD_SEL_CAP;                   // false only when one VALUE fills the last bucket
+  const bool even = count > 0 && !(count & 1ull);
+  const bool need_above = even && (rank + 1 >= inbin);
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // 4096 x u64 = 32 KB
+  unsigned long long Lk = prefix, Uk = prefix;
+  if (count > 0 && fits) {
+    const int m = (int)inbin;
+    int n2 = 1; while (n2 < m) n2 <<= 1;
+    const unsigned long long* lst = list + (size_t)b * QD_SEL_CAP;
+    for (int k = threadIdx.x; k < n2; k += QD_SEL_THREADS) skeys[k] = k < m ? __ldcg(lst + k) : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1)
+      for (int st = size >> 1; st > 0; st >>= 1) {
+        for (int k = threadIdx.x; k < n2; k += QD_SEL_THREADS) {
+          const int q = k ^ st;
+          if (q > k) {
+            const unsigned long long a = skeys[k], c2 = skeys[q];
+            const bool up = (k & size) == 0;
+            if ((a > c2) == up) { skeys[k] = c2; skeys[q] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    Lk = skeys[rank];
+    Uk = (rank + 1 < (unsigned long long)m) ? skeys[rank + 1] : Lk;
+  }
+  if (threadIdx.x == 0) {
     double r = out.empty_value;
     if (count > 0) {
-      if (count & 1ull) r = L;
+      const double L = __longlong_as_double((long long)Lk);
+      if (!even) r = L;
       else {
-        const double U = need_upper ? __longlong_as_double((long long)__ldcg(mingt + b)) : L;
+        const double U = need_above ? __longlong_as_double((long long)__ldcg(mingt + b)) : __longlong_as_double((long long)Uk);
         r = (L + U) / 2.0;                                  // np.mean of the two middle values
       }
     }
     out.value[(size_t)b * out.stride] = r;
     if (out.count) out.count[(size_t)b * out.stride] = (double)count;
+    lcount[b] = 0u;
+    mingt[b] = ~0ull;
   }
 }
 #else

@@ -37,6 +37,10 @@ def test_median_edge_cases(lib):
     qdcheck.check_median_edge_cases(lib)
 
 
+def test_median_large_duplicates_and_batch(lib):
+    qdcheck.check_median_large(lib)
+
+
 def test_ops_random(lib):
     qdcheck.check_ops_random(lib)
 
