@@ -45,7 +45,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk;
+  int nlat, nlon, ncell, batch, device, nblk, red_blk;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -140,6 +140,8 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
     QD_LAUNCH(kern, (grid), (block), (c)->stream, __VA_ARGS__); \
     qd_prof_end((c), pi_); (c)->launches++; } while (0)
 #define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+// grid-stride kernels that end in a grid-wide reduction (QD_CELL_LOOP): at most red_blk blocks per member
+#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3((c)->red_blk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 
 #ifndef QD_HOST_EMU
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
@@ -204,6 +206,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   memset(c->err, 0, sizeof(c->err));
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
+  c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
   c->d_lai = nullptr; c->eco_nl = 0; c->eco_every_nphys = 1; c->eco_steps = 0; c->eco_have_alpha = 0;
@@ -233,6 +236,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select_coop, QD_SEL_THREADS, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int resident = std::max(1, per_sm * sms);
+    c->red_blk = std::max(1, std::min(c->nblk, (8 * sms + batch - 1) / batch));     // one resident wave of 256-thread blocks
     const int want = (c->ncell + QD_SEL_THREADS - 1) / QD_SEL_THREADS;
     c->sel_gx = std::max(1, std::min(want, resident / batch));
     if ((long long)c->sel_gx * batch > resident) { delete c; return QD_E_INVALID; }   // ensemble too large for one cooperative grid
@@ -554,7 +558,7 @@ extern "C" int qd_median_pos(qd_ctx* c, const double* in, double empty_value, do
 }
 extern "C" int qd_wsum(qd_ctx* c, const double* in, double* out_host) {
   if (!c || !in || !out_host) return QD_E_INVALID;
-  QD_K(c, k_wsum, c->geo, in, ROW(c, QD_R_W), c->d_part[0], c->d_ticket + 2 * c->batch, c->d_scal + QD_S_TMP2, QD_S_COUNT);
+  QD_KR(c, k_wsum, c->geo, in, ROW(c, QD_R_W), c->d_part[0], c->d_ticket + 2 * c->batch, c->d_scal + QD_S_TMP2, QD_S_COUNT);
   QD_CHECK_LAUNCH(c);
   std::vector<double> s((size_t)c->batch * QD_S_COUNT);
   int rc = qd_get_scalars(c, s.data());
@@ -644,7 +648,7 @@ static QdEcoArgs eco_args(qd_ctx* c, double dt) {
 static int eco_policy(qd_ctx* c, double dt) {
   if (!c->d_lai) return QD_OK;
   QdEcoArgs E = eco_args(c, dt);
-  QD_K(c, k_eco_stats, c->geo, E);
+  QD_KR(c, k_eco_stats, c->geo, E);
   QD_K(c, k_eco_canopy, c->geo, E);
   return QD_OK;
 }
@@ -807,7 +811,7 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
     T.qnet = F(c, QD_F_QNET); T.ice = M(c, QD_M_ICE); T.land = M(c, QD_M_LAND);
     T.part_max_u = c->d_part[0]; T.part_max_va = c->d_part[1]; T.ticket = c->d_ticket + 3 * c->batch;
     T.dt = dt; T.with_qnet = (mode_loop && cfg->with_ocean) ? 1 : 0; T.has_cloud_eff = c->has_cloud_eff; T.with_max = 0;
-    QD_K(c, k_tail, c->geo, T);
+    QD_KR(c, k_tail, c->geo, T);
   }
   QD_CHECK_LAUNCH(c);
   return QD_OK;
@@ -860,7 +864,7 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
   Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
   Co.ticket = c->d_ticket + 5 * c->batch;
-  QD_K(c, k_ocean_continuity, c->geo, Co, sc);
+  QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
   QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
   Sa.sst = F(c, QD_F_SST); Sa.ub = ub; Sa.vb = vb; Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
   QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
@@ -926,7 +930,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   P0.u = F(c, QD_F_U); P0.v = F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
-  QD_K(c, k_ocean_prep, c->geo, P0);
+  QD_KR(c, k_ocean_prep, c->geo, P0);
   QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
   QD_CHECK_LAUNCH(c);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
@@ -1017,13 +1021,13 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   QdPrecipAArgs Pa; memset(&Pa, 0, sizeof(Pa));
   Pa.u = F(c, QD_F_U); Pa.v = F(c, QD_F_V); Pa.pcond = F(c, QD_F_PCOND); Pa.nx = F(c, QD_F_OROG_NX); Pa.ny = F(c, QD_F_OROG_NY);
   Pa.pos = F(c, QD_F_X0); Pa.orog_raw = F(c, QD_F_X1); Pa.part = c->d_part[0]; Pa.ticket = c->d_ticket + 6 * c->batch;
-  QD_K(c, k_precip_a, c->geo, Pa);
+  QD_KR(c, k_precip_a, c->geo, Pa);
   if (orog) { double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X2)}; if ((rc = op_gauss(c, 1, fl, sx, w1))) return rc; }
   if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT))) return rc;
   QdPrecipBArgs Pb; memset(&Pb, 0, sizeof(Pb));
   Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = F(c, QD_F_X1); Pb.praw = F(c, QD_F_X2);
   Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
-  QD_K(c, k_precip_b, c->geo, Pb);
+  QD_KR(c, k_precip_b, c->geo, Pb);
   QdPrecipCArgs Pc; Pc.praw = F(c, QD_F_X2); Pc.pos = F(c, QD_F_X0); Pc.g0 = F(c, QD_F_X3); Pc.g1 = F(c, QD_F_X4);
   QD_K(c, k_precip_c, c->geo, Pc, w1);
   QdPrecipDArgs Pd; Pd.g0 = F(c, QD_F_X3); Pd.g1 = F(c, QD_F_X4); Pd.precip = F(c, QD_F_PRECIP);

@@ -31,15 +31,14 @@ QD_D double qd_eco_total(const QdEcoArgs& A, const QdGeo& g, int b, int idx) {
 }
 
 __global__ void __launch_bounds__(QD_THREADS) k_eco_stats(QdGeo g, QdEcoArgs A) {
-  QD_CELL_PROLOGUE(g)
   double sd = 0.0, nd = 0.0, sb = 0.0, nb = 0.0;
-  if (active) {
+  QD_CELL_LOOP(g) {
     const double now = qd_eco_total(A, g, b, idx);
     const double s = A.snap[off + idx];
     const double d = fabs(now - s);
-    if (d == d) { sd = d; nd = 1.0; }                       // nanmean skips NaN
+    if (d == d) { sd += d; nd += 1.0; }                     // nanmean skips NaN
     const double m = qd_max(s, 1e-6);
-    if (m == m) { sb = m; nb = 1.0; }
+    if (m == m) { sb += m; nb += 1.0; }
   }
   double t;
   const size_t pb = (size_t)b * gridDim.x;

@@ -24,10 +24,9 @@ struct QdOcPrepArgs {
   unsigned* ticket;
 };
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs A) {
-  QD_CELL_PROLOGUE(g)
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
-  if (active) {
+  QD_CELL_LOOP(g) {
     const size_t c = off + idx;
     const double uo = A.uo[c], vo = A.vo[c];
     const double ur = A.u[c] - uo, vr = A.v[c] - vo;
@@ -35,8 +34,9 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs
     const double Ve = qd_min(Va, P[QD_P_OC_VCAP]);
     A.taux[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * ur);
     A.tauy[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * vr);
-    mu = sqrt(uo * uo + vo * vo);
-    mva = Va;
+    const double sp = sqrt(uo * uo + vo * vo);
+    if (sp > mu) mu = sp;                       // NaN-ignoring running maxima, like qd_block_max
+    if (Va > mva) mva = Va;
   }
   double t;
   double* pu = A.part_u + (size_t)b * gridDim.x;
@@ -145,19 +145,20 @@ struct QdOcContArgs {
   unsigned* ticket;
 };
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcContArgs A, QdSubCtl sc) {
-  QD_CELL_PROLOGUE(g)
-  const bool done = qd_sub_done(g, b, sc);
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const bool done = qd_sub_done(g, blockIdx.y, sc);
+  const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
+  const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
   double contrib = 0.0;
-  if (active && !done) {
+  QD_CELL_LOOP(g) {
+    if (done) break;
+    QD_CELL_JI(g)
     const size_t c = off + idx;
-    const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
     const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);
     double e = A.eta_in[c] + (-sub_dt * P[QD_P_OC_H] * div);
     const bool land = A.land[c] == 1;
     if (land) e = 0.0;
     A.eta[c] = e;
-    contrib = e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
+    contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
   }
   double t;
   double* part = A.part + (size_t)b * gridDim.x;

@@ -45,6 +45,17 @@ struct QdGaussW { int r; int wrap; double w[2 * QD_GAUSS_MAXR + 1]; };
   const size_t off = (size_t)b * (geo).ncell;                         \
   (void)i; (void)j; (void)off;
 
+// Grid-stride form for kernels that end in a grid-wide reduction: the grid is capped at a few blocks per SM
+// (QD_KR in qd_api.cu), so the "last block" ticket -- one atomic round trip on every block's critical path,
+// ~40 us per launch at 1441x2880 with one block per 256 cells (profiles/r01_ncu_hires_step.md) -- is paid
+// by ~1e3 blocks instead of ~1.6e4.  Partials stay per block and are combined in block order: deterministic.
+#define QD_CELL_LOOP(geo)                                             \
+  const int b = blockIdx.y;                                           \
+  const size_t off = (size_t)b * (geo).ncell;                         \
+  (void)off;                                                          \
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (geo).ncell; idx += gridDim.x * blockDim.x)
+#define QD_CELL_JI(geo) const int j = idx / (geo).nlon; const int i = idx - j * (geo).nlon; (void)i; (void)j;
+
 QD_HD const double* qd_row(const QdGeo& g, int id) { return g.rows + (size_t)id * g.nlat; }
 // rows that follow a member's parameters (K4, ocean sponge, polar flag): member b's copy of the table
 QD_HD const double* qd_mrow(const QdGeo& g, int id, int b) { return g.rows + (size_t)b * g.row_bstride + (size_t)id * g.nlat; }
@@ -303,9 +314,8 @@ __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* 
 // partials are combined in a fixed order by the last block to finish.
 __global__ void __launch_bounds__(QD_THREADS) k_wsum(QdGeo g, const double* x, const double* wrow,
                                                     double* partial, unsigned* ticket, double* out, int out_stride) {
-  QD_CELL_PROLOGUE(g)
   double v = 0.0;
-  if (active) v = x[off + idx] * (wrow ? wrow[j] : 1.0);
+  QD_CELL_LOOP(g) { QD_CELL_JI(g) v += x[off + idx] * (wrow ? wrow[j] : 1.0); }
   double tot;
   double* part = partial + (size_t)b * gridDim.x;
   if (qd_block_sum<0>(v, &tot)) part[blockIdx.x] = tot;

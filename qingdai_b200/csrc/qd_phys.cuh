@@ -411,10 +411,9 @@ struct QdTailArgs {
   double dt; int with_qnet, has_cloud_eff, with_max;
 };
 __global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
-  QD_CELL_PROLOGUE(g)
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
-  if (active) {
+  QD_CELL_LOOP(g) {
     const size_t c = off + idx;
     const double df = P[QD_P_DIFF_FACTOR];
     const double rate = A.dt / (2.0 * 24 * 3600);
@@ -436,8 +435,9 @@ __global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
     if (A.with_max) {
       const double uo = A.uo[c], vo = A.vo[c];
       const double ur = u - uo, vr = v - vo;
-      mu = sqrt(uo * uo + vo * vo);
-      mva = sqrt(ur * ur + vr * vr);
+      const double sp = sqrt(uo * uo + vo * vo), va = sqrt(ur * ur + vr * vr);
+      if (sp > mu) mu = sp;                     // NaN-ignoring running maxima, like qd_block_max
+      if (va > mva) mva = va;
     }
   }
   if (A.with_max) {
