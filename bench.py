@@ -47,8 +47,8 @@ ALG_BYTES = {
 
 def alg_bytes_per_cell(name):
     """Algorithmic bytes per cell of one launch; the fused del^4 tile kernel reads and writes each of its
-    n fields once (its profile name carries n: ``k_hyper4_tile<32>[3]``)."""
-    if name.startswith("k_hyper4_tile") and name.endswith("]"):
+    n fields once (its profile name carries n: ``k_hyper4_stream[3]``, ``k_hyper4_tile<8>[3]``)."""
+    if name.startswith("k_hyper4_") and name.endswith("]"):
         return 16 * int(name[name.rindex("[") + 1:-1])
     return ALG_BYTES.get(name, 16)
 

@@ -77,11 +77,13 @@ typedef enum {
   QD_R_COS_ADV_ATM,   /* max(1e-6, cos)          */
   /* a cosine table used by the Laplacian is followed by its 1/c and 1/c^2 rows (the stencil kernels
    * multiply by reciprocals: fp64 division is ~20 instructions on sm_100 and the step is otherwise
-   * fp64-issue bound; differences to true division are <= 1 ulp per operation) */
+   * fp64-issue bound; differences to true division are <= 1 ulp per operation) and by the three
+   * centred-stencil coefficient rows ap, am, bl of the del^4 kernels; the library fills all five
+   * companion rows itself (qd_create, qd_set_rows*, qd_user_row*) */
   QD_R_COS_ADV_HALF,  /* max(cos, 0.5)           */
-  QD_R_ICOS_HALF, QD_R_ICOS2_HALF,
+  QD_R_ICOS_HALF, QD_R_ICOS2_HALF, QD_R_H4AP_HALF, QD_R_H4AM_HALF, QD_R_H4BL_HALF,
   QD_R_COS_LAP_ATM,   /* max(cos, 0.2)           */
-  QD_R_ICOS_LAP_ATM, QD_R_ICOS2_LAP_ATM,
+  QD_R_ICOS_LAP_ATM, QD_R_ICOS2_LAP_ATM, QD_R_H4AP_LAP_ATM, QD_R_H4AM_LAP_ATM, QD_R_H4BL_LAP_ATM,
   QD_R_COS_CAP,       /* max(cos, 1e-6)          */
   QD_R_FSAFE,         /* regularised Coriolis    */
   QD_R_K4_U, QD_R_K4_V, QD_R_K4_H, QD_R_K4_Q, QD_R_K4_C,
@@ -222,8 +224,8 @@ int  qd_wsum(qd_ctx* ctx, const double* in_dev, double* out_host /* [B] sum(x*w)
 /* device row tables for the operator calls above */
 const double* qd_row_dev(qd_ctx* ctx, int row_id);
 /* upload an arbitrary [nlat] row table into one of 6 user row slots (0/1 are used by the *_host operator
- * forms, 2..4 hold the QD_OCEAN_K4_U/V/ETA overrides) (the library appends the 1/x and
- * 1/x^2 rows the Laplacian kernels expect right behind it), returns its device pointer */
+ * forms, 2..4 hold the QD_OCEAN_K4_U/V/ETA overrides) (the library appends the five
+ * companion rows the Laplacian kernels expect right behind it), returns its device pointer */
 const double* qd_user_row(qd_ctx* ctx, int slot, const double* rows_host);   /* every member's copy */
 int  qd_user_row_member(qd_ctx* ctx, int slot, int member, const double* rows_host);
 
@@ -247,6 +249,7 @@ int  qd_use_graphs(qd_ctx* ctx, int enable);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */
+int  qd_set_h4_stream(qd_ctx* ctx, int enable);               /* 0: force the tile kernel for del^4 (tests); default 1 */
 int  qd_launch_count(qd_ctx* ctx, long long* out);            /* kernels launched so far */
 /* per-kernel device time: CUDA events on the launching stream around every launch while enabled */
 int  qd_profile(qd_ctx* ctx, int enable);

@@ -45,7 +45,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk, red_blk;
+  int nlat, nlon, ncell, batch, device, nblk, red_blk, h4_stream;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -67,7 +67,9 @@ struct qd_ctx {
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
-    return 4 + (do_hyper ? std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
+    const long long tiles_i = (nlon + 63) / 64;                  // launch_hyper4: large grids take the stream + pole-tile pair
+    const bool stream = h4_stream && nlat >= 96 && nlon >= 64 && tiles_i * ((nlat + 31) / 32) * batch * 3 >= 2 * 148;
+    return 4 + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
   }
 #endif
   char err[512];
@@ -191,6 +193,31 @@ static inline bool qd_in_row_table(qd_ctx* c, const double* p) {
   return p >= c->d_rows && p < c->d_rows + (size_t)c->batch * c->geo.row_bstride;
 }
 
+// Companion rows of a cosine table t[0..nlat): t[1] = 1/c, t[2] = 1/c^2 and the centred-stencil coefficients of
+// the del^4 kernels t[3] = ap, t[4] = am, t[5] = bl (same expressions as k_hyper4_tile evaluates per block).
+static void qd_cos_companions(const QdGeo& g, int nlat, double* t) {
+  for (int j = 0; j < nlat; ++j) { const double x = t[j]; t[nlat + j] = 1.0 / x; t[2 * (size_t)nlat + j] = 1.0 / (x * x); }
+  for (int j = 0; j < nlat; ++j) {
+    double ap = 0.0, am = 0.0, bl = 0.0;
+    if (j >= 2 && j <= nlat - 3) {
+      const double icj = t[nlat + j] * g.inv_2dlat;
+      ap = (icj * (t[j + 1] * g.inv_2dlat)) * g.inv_a_sq;
+      am = (icj * (t[j - 1] * g.inv_2dlat)) * g.inv_a_sq;
+      bl = (t[2 * (size_t)nlat + j] * g.inv_dlon_sq) * g.inv_a_sq;
+    }
+    t[3 * (size_t)nlat + j] = ap; t[4 * (size_t)nlat + j] = am; t[5 * (size_t)nlat + j] = bl;
+  }
+}
+// one member's built-in row table: host rows -> companions of the two Laplacian cosine tables -> device
+static int qd_upload_rows(qd_ctx* c, int member, const double* rows) {
+  const int nlat = c->nlat;
+  std::vector<double> h(rows, rows + (size_t)QD_R_COUNT * nlat);
+  qd_cos_companions(c->geo, nlat, h.data() + (size_t)QD_R_COS_ADV_HALF * nlat);
+  qd_cos_companions(c->geo, nlat, h.data() + (size_t)QD_R_COS_LAP_ATM * nlat);
+  if (cudaMemcpy(c->d_rows + (size_t)member * c->geo.row_bstride, h.data(), h.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return QD_E_CUDA;
+  return QD_OK;
+}
+
 // ------------------------------------------------------------------------------ lifecycle
 extern "C" int qd_version(void) { return 100; }
 extern "C" const char* qd_last_error(const qd_ctx* c) { return c ? c->err : "null context"; }
@@ -206,6 +233,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   memset(c->err, 0, sizeof(c->err));
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
+  c->h4_stream = 1;
   c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
@@ -215,7 +243,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
 #endif
-  const size_t nrows = (size_t)(QD_R_COUNT + 3 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
+  const size_t nrows = (size_t)(QD_R_COUNT + 6 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
 #define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
   QD_ALLOC(c->d_rows, (size_t)batch * nrows * 8);
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
@@ -252,7 +280,6 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #undef QD_ALLOC
   c->h_prm = (double*)malloc((size_t)batch * QD_P_COUNT * 8);
   memcpy(c->h_prm, params_host, (size_t)batch * QD_P_COUNT * 8);
-  for (int b = 0; b < batch; ++b) cudaMemcpy(c->d_rows + (size_t)b * nrows, rows_host, (size_t)QD_R_COUNT * nlat * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_cols, cols_host, (size_t)QD_C_COUNT * nlon * 8, cudaMemcpyHostToDevice);
   cudaMemcpy(c->d_prm, params_host, (size_t)batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice);
   {
@@ -269,6 +296,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
   g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
+  for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { delete c; return QD_E_CUDA; }
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
   *out = c;
   return QD_OK;
@@ -319,14 +347,13 @@ extern "C" int qd_set_params(qd_ctx* c, const double* p) {
 extern "C" int qd_set_rows(qd_ctx* c, const double* rows) {
   if (!c || !rows) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  for (int b = 0; b < c->batch; ++b)
-    QD_CUDA(c, cudaMemcpy(c->d_rows + (size_t)b * c->geo.row_bstride, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
+  for (int b = 0; b < c->batch; ++b) { int rc = qd_upload_rows(c, b, rows); if (rc) return qd_fail(c, rc, "qd_set_rows", cudaSuccess); }
   return QD_OK;
 }
 extern "C" int qd_set_rows_member(qd_ctx* c, int member, const double* rows) {
   if (!c || !rows || member < 0 || member >= c->batch) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  QD_CUDA(c, cudaMemcpy(c->d_rows + (size_t)member * c->geo.row_bstride, rows, (size_t)QD_R_COUNT * c->nlat * 8, cudaMemcpyHostToDevice));
+  { int rc = qd_upload_rows(c, member, rows); if (rc) return qd_fail(c, rc, "qd_set_rows_member", cudaSuccess); }
   return QD_OK;
 }
 extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
@@ -335,16 +362,14 @@ extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
   QD_CUDA(c, cudaMemcpy(out, c->d_scal, (size_t)c->batch * QD_S_COUNT * 8, cudaMemcpyDeviceToHost));
   return QD_OK;
 }
-extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + 3 * QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
-#define QD_USER_ROW(c, slot) ((c)->d_rows + (size_t)(QD_R_COUNT + 3 * (slot)) * (c)->nlat)
+extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + 6 * QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
+#define QD_USER_ROW(c, slot) ((c)->d_rows + (size_t)(QD_R_COUNT + 6 * (slot)) * (c)->nlat)
 extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_host) {
   if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host) return nullptr;
   cudaStreamSynchronize(c->stream);
-  std::vector<double> tmp(3 * (size_t)c->nlat);
-  for (int j = 0; j < c->nlat; ++j) {
-    const double x = rows_host[j];
-    tmp[j] = x; tmp[c->nlat + j] = 1.0 / x; tmp[2 * (size_t)c->nlat + j] = 1.0 / (x * x);
-  }
+  std::vector<double> tmp(6 * (size_t)c->nlat);
+  for (int j = 0; j < c->nlat; ++j) tmp[j] = rows_host[j];
+  qd_cos_companions(c->geo, c->nlat, tmp.data());
   double* dst = QD_USER_ROW(c, slot);
   for (int b = 0; b < c->batch; ++b)
     if (cudaMemcpy(dst + (size_t)b * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
@@ -353,14 +378,14 @@ extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_hos
 extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double* rows_host) {
   if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host || member < 0 || member >= c->batch) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<double> tmp(3 * (size_t)c->nlat);
-  for (int j = 0; j < c->nlat; ++j) {
-    const double x = rows_host[j];
-    tmp[j] = x; tmp[c->nlat + j] = 1.0 / x; tmp[2 * (size_t)c->nlat + j] = 1.0 / (x * x);
-  }
+  std::vector<double> tmp(6 * (size_t)c->nlat);
+  for (int j = 0; j < c->nlat; ++j) tmp[j] = rows_host[j];
+  qd_cos_companions(c->geo, c->nlat, tmp.data());
   QD_CUDA(c, cudaMemcpy(QD_USER_ROW(c, slot) + (size_t)member * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
   return QD_OK;
 }
+// test / tuning switch: 0 forces the shared-memory tile kernel for del^4 at every size (default 1: large grids stream)
+extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->h4_stream = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
 extern "C" int qd_get_counters(qd_ctx* c, int* a, int* o, int* ce) {
@@ -403,7 +428,24 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   // profile names carry the number of fields in the launch (bench.py: 16 B per cell and field)
   static const char* const nm32[] = {"", "k_hyper4_tile<32>[1]", "k_hyper4_tile<32>[2]", "k_hyper4_tile<32>[3]", "k_hyper4_tile<32>[4]", "k_hyper4_tile<32>[5]"};
   static const char* const nm8[] = {"", "k_hyper4_tile<8>[1]", "k_hyper4_tile<8>[2]", "k_hyper4_tile<8>[3]", "k_hyper4_tile<8>[4]", "k_hyper4_tile<8>[5]"};
+  static const char* const nms[] = {"", "k_hyper4_stream[1]", "k_hyper4_stream[2]", "k_hyper4_stream[3]", "k_hyper4_stream[4]", "k_hyper4_stream[5]"};
   const int nn = H.n < 1 ? 1 : (H.n > 5 ? 5 : H.n);
+  H.tj_lo = 1 << 30; H.tj_skip = 0; H.ja = 0; H.jb = 0;
+#ifndef QD_HOST_EMU
+  const int ntj8 = (c->nlat + 7) / 8;
+  if (blocks32 >= 2 * 148 && c->nlat >= 96 && c->nlon >= 64 && c->h4_stream) {
+    // large grid: warp-streaming kernel on the rows with a centred dependency cone, tile kernel on the
+    // tile rows that touch a pole (tile row 0 and the last two)
+    constexpr int R = 64;
+    H.ja = 8; H.jb = (ntj8 - 2) * 8;
+    const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+    const int nwarps = nstrips * ((H.jb - H.ja + R - 1) / R);
+    QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+    H.tj_lo = 1; H.tj_skip = ntj8 - 3;
+    QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * 3, c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    return QD_OK;
+  }
+#endif
   if (blocks32 >= 2 * 148) {
     QD_KGN(c, nm32[nn], k_hyper4_tile<32>, dim3(tiles_i * ((c->nlat + 31) / 32), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
   } else {

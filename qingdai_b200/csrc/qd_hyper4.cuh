@@ -27,6 +27,8 @@ struct QdHyper4Args {
   int nsub;                                // inner sub-division (QD_K4_NSUB / QD_OCEAN_K4_NSUB): sub = dt / nsub
   int ocean;                               // 1: per-member sub_dt and early exit through the device sub-step counter
   QdSubCtl sc;
+  int tj_lo, tj_skip;                      // tile kernel: tile rows >= tj_lo are shifted by tj_skip (pole tiles only, see launch_hyper4)
+  int ja, jb;                              // streaming kernel: output rows [ja, jb), all with a centred dependency cone
 };
 
 // Laplacian at (global row j, tile column c) from a tile accessor A(jglobal, tile_col).
@@ -64,6 +66,16 @@ QD_HD double qd_lap_rel(const Acc& A, int j, int c, const QdGeo& g, const double
 #define QD_H4_NY 4
 
 QD_HD double qd_clean_fast(double x) { return (fabs(x) <= DBL_MAX) ? x : qd_nan_to_num(x); }
+#if !QD_EMU
+// np.nan_to_num without branches (selects only): keeps the streaming kernel's loads and arithmetic of
+// neighbouring rows free to overlap; identical results to qd_nan_to_num.
+__device__ __forceinline__ double qd_clean_sel(double x) {
+  const int hi = __double2hiint(x);
+  const double big = __hiloint2double((hi & 0x80000000) | 0x7fefffff, 0xffffffff);     // copysign(DBL_MAX, x)
+  const double alt = (x != x) ? 0.0 : big;
+  return (fabs(x) <= DBL_MAX) ? x : alt;
+}
+#endif
 
 // Interior rows (2 <= j <= n_lat-3, every np.gradient centred) use three per-row coefficients staged in
 // shared memory:  lap F = ap*(F[j+2]-F[j]) - am*(F[j]-F[j-2]) + bl*((F[i+1]-2F)+F[i-1])  with
@@ -86,7 +98,8 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;
   const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * NX + tx;
   const int tiles_i = (g.nlon + TI - 1) / TI;
-  const int tj = blockIdx.x / tiles_i, ti = blockIdx.x - tj * tiles_i;
+  const int tj0 = blockIdx.x / tiles_i, ti = blockIdx.x - tj0 * tiles_i;
+  const int tj = tj0 >= A.tj_lo ? tj0 + A.tj_skip : tj0;
   const int j0 = tj * TJ, i0 = ti * TI;
   const int jF0 = j0 - 4, jL0 = j0 - 2, iF0 = i0 - 2;
   const int nlat = g.nlat, nlon = g.nlon;
@@ -208,6 +221,109 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
     }
   }
 }
+
+// ---- streaming form for large grids -------------------------------------------------------------------
+// One WARP marches down a strip of 28 longitudes (lanes 2..29; lanes 0,1,30,31 carry the +-2 column halo),
+// keeping F[j..j+4] and lap(F)[j-2..j+2] in registers; east / west neighbours come from warp shuffles.  No
+// shared memory, no barriers, one coalesced load and one store per cell and row: ~50 thread instructions
+// per cell instead of ~340 for the tile kernel (profiles/r01_ncu_hires_step.md), which was issue-bound at
+// 15 % of HBM peak.  Only rows whose whole dependency cone uses centred differences (4 <= j <= n_lat-5) are
+// produced here; the tile kernel does the few rows next to the poles.  Same operand order as the tile
+// kernel, so both produce identical bits.
+#define QD_H4S_COLS 28
+#define QD_H4S_WARPS 4
+// `cr` tables carry, behind the cosine row and its 1/c, 1/c^2 rows, the three centred-stencil coefficient
+// rows ap, am, bl of the tile kernel (filled on the host by qd_cos_companions with the same expressions).
+template <int R>
+__global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
+  static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
+  const int b = blockIdx.y;
+  if (A.ocean && qd_sub_done(g, b, A.sc)) return;
+  const int lane = threadIdx.x & 31;
+  const int nlat = g.nlat, nlon = g.nlon;
+  const int nstrips = (nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+  const int w = blockIdx.x * QD_H4S_WARPS + (threadIdx.x >> 5);
+  const int chunk = w / nstrips, strip = w - chunk * nstrips;
+  const int j0 = A.ja + chunk * R;
+  if (j0 >= A.jb) return;
+  const int j1 = min(j0 + R, A.jb);
+  const int k = blockIdx.z;
+  const size_t off = (size_t)b * g.ncell;
+  const double* __restrict__ cap = A.cosr + 3 * (size_t)nlat;
+  const double* __restrict__ cam = A.cosr + 4 * (size_t)nlat;
+  const double* __restrict__ cbl = A.cosr + 5 * (size_t)nlat;
+  double sub_dt = A.dt;
+  if (A.ocean) sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
+  const double inner = sub_dt / (double)(A.nsub > 1 ? A.nsub : 1);
+  // k4 of this chunk's rows: lane l holds rows j0+l (and j0+32+l); one division per lane instead of one per row
+  double kq0, kq1 = 0.0;
+  {
+    const double* __restrict__ k4r = A.k4rows[k] + (size_t)b * A.k4_bstride[k];
+    const double k4div = fmax(1e-12, sub_dt), k4scale = A.scale[k];
+    const bool raw = A.raw_k4[k] != 0;
+    auto k4row = [&](int j) {
+      double v = (j < nlat) ? k4r[j] : 0.0;
+      if (!raw) v = v / k4div;                              // ocean.py:347
+      return k4scale * v;
+    };
+    kq0 = k4row(j0 + lane);
+    if (R > 32) kq1 = k4row(j0 + 32 + lane);
+  }
+  int gi = strip * QD_H4S_COLS - 2 + lane;
+  if (gi < 0) gi += nlon;
+  if (gi >= nlon) gi -= nlon;
+  if (gi >= nlon) gi -= nlon;
+  const bool writer = lane >= 2 && lane < 2 + QD_H4S_COLS && (strip * QD_H4S_COLS + lane - 2) < nlon;
+  const double* __restrict__ p = A.src[k] + off + (size_t)(j0 - 4) * nlon + gi;
+  double* __restrict__ d = A.dst[k] + off + (size_t)j0 * nlon + gi;
+  auto lap_row = [&](double fm2, double fc, double fp2, double ap, double am, double bl) {
+    const double fe = __shfl_down_sync(0xffffffffu, fc, 1), fw = __shfl_up_sync(0xffffffffu, fc, 1);
+    return qd_clean_sel((ap * (fp2 - fc) - am * (fc - fm2)) + bl * ((fe - 2.0 * fc) + fw));
+  };
+  // F window f0..f3 = F[j..j+3]; lap window l0..l3 = lap(F)[j-2..j+1]; c?m / c?0 = coefficients of rows j, j+1
+  double f0 = qd_clean_sel(p[0]), f1 = qd_clean_sel(p[nlon]), f2 = qd_clean_sel(p[2 * (size_t)nlon]), f3 = qd_clean_sel(p[3 * (size_t)nlon]);
+  p += 4 * (size_t)nlon;
+  double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+  double apm = 0.0, amm = 0.0, blm = 0.0, ap0 = 0.0, am0 = 0.0, bl0 = 0.0;
+  // One group = 4 rows: the four loads of new F rows and the twelve coefficient loads are issued together
+  // so that their latency overlaps; unrolling by the window length turns the register shifts into renames.
+  // jr = row of the first new Laplacian value of the group; emit = false for the warm-up group.
+#define QD_H4S_GROUP(jr, emit)                                                                       \
+  {                                                                                                  \
+    const double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];        \
+    p += 4 * (size_t)nlon;                                                                           \
+    const double a0 = cap[(jr)], a1 = cap[(jr) + 1], a2 = cap[(jr) + 2], a3 = cap[(jr) + 3];         \
+    const double m0 = cam[(jr)], m1 = cam[(jr) + 1], m2 = cam[(jr) + 2], m3 = cam[(jr) + 3];         \
+    const double b0 = cbl[(jr)], b1 = cbl[(jr) + 1], b2 = cbl[(jr) + 2], b3 = cbl[(jr) + 3];         \
+    QD_H4S_STEP(n0, a0, m0, b0, 0, emit) QD_H4S_STEP(n1, a1, m1, b1, 1, emit)                        \
+    QD_H4S_STEP(n2, a2, m2, b2, 2, emit) QD_H4S_STEP(n3, a3, m3, b3, 3, emit)                        \
+  }
+#define QD_H4S_STEP(nv, ap, am, bl, s, emit)                                                         \
+  {                                                                                                  \
+    const double f4 = qd_clean_sel(nv);                                                             \
+    const double l4 = lap_row(f0, f2, f4, ap, am, bl);                                               \
+    if (emit) {                                                                                      \
+      const int r = j - j0 + (s);                                                                    \
+      const double le = __shfl_down_sync(0xffffffffu, l2, 1), lw = __shfl_up_sync(0xffffffffu, l2, 1); \
+      const double L2 = (apm * (l4 - l2) - amm * (l2 - l0)) + blm * ((le - 2.0 * l2) + lw);          \
+      const double k4 = __shfl_sync(0xffffffffu, (R > 32 && r >= 32) ? kq1 : kq0, r & 31);           \
+      if (writer && j + (s) < j1) d[(size_t)(s) * nlon] = qd_clean_sel(f0 - k4 * L2 * inner);       \
+    }                                                                                                \
+    l0 = l1; l1 = l2; l2 = l3; l3 = l4;                                                              \
+    apm = ap0; amm = am0; blm = bl0; ap0 = ap; am0 = am; bl0 = bl;                                   \
+    f0 = f1; f1 = f2; f2 = f3; f3 = f4;                                                              \
+  }
+  {
+    const int j = j0;
+    QD_H4S_GROUP(j0 - 2, false)                            // warm-up: lap(F) at rows j0-2 .. j0+1
+  }
+  for (int j = j0; j < j1; j += 4) {
+    QD_H4S_GROUP(j + 2, true)
+    d += 4 * (size_t)nlon;
+  }
+#undef QD_H4S_GROUP
+#undef QD_H4S_STEP
+}
 #else
 // Host check build: the same tile algorithm with cooperative loops written so that one sequential
 // "thread" can run a whole phase (see qd_rt.h); the GPU kernel above is exercised by tests/test_gpu.py.
@@ -221,7 +337,8 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
   const int b = blockIdx.y;
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;
   const int tiles_i = (g.nlon + TI - 1) / TI;
-  const int tj = blockIdx.x / tiles_i, ti = blockIdx.x - tj * tiles_i;
+  const int tj0 = blockIdx.x / tiles_i, ti = blockIdx.x - tj0 * tiles_i;
+  const int tj = tj0 >= A.tj_lo ? tj0 + A.tj_skip : tj0;
   const int j0 = tj * TJ, i0 = ti * TI;
   const int jF0 = j0 - 4, jL0 = j0 - 2, iF0 = i0 - 2;
   const int nlat = g.nlat, nlon = g.nlon;

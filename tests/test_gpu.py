@@ -110,3 +110,7 @@ def test_ecology_adapter(lib, golden, tag):
 
 def test_loop_with_ecology(lib, golden):
     qdcheck.check_eco_loop(lib, golden("eco_golden.npz"))
+
+
+def test_hyper4_streaming_kernel(lib):
+    qdcheck.check_hyper4_stream(lib)
