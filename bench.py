@@ -12,7 +12,8 @@ Workloads (BASELINE.json configs):
               cloud coupling, dynamic ocean, hydrology), dt=300 s, one member per GPU.  DEFAULT.
   ensemble64  configs[3]: 64 independent 181x360 members (topography seeds 42..105) split across GPUs.
   hires       configs[4] at one GPU: 1441x2880 full physics, dt=37 s.
-Multi-GPU: members / replicas are independent -> no data-path collective.
+Multi-GPU: ensemble members are independent -> no data-path collective; `--workload hires` at N>1 splits ONE
+domain into latitude bands with peer-to-peer halo exchange.
 """
 from __future__ import annotations
 
@@ -130,6 +131,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=0, help="oracle steps for cpu_baseline (0 = auto, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="hires at N>1: independent replicas instead of latitude bands")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -172,16 +174,20 @@ def main():
     from qingdai_b200.synthetic import make_topography
     from qingdai_b200.engine import S as SC
 
+    band = None
     if spec["members_total"]:
         assert spec["members_total"] % world == 0
         members = spec["members_total"] // world
         scaling, seeds = "strong", [42 + rank * members + m for m in range(members)]
+    elif args.workload == "hires" and world > 1 and not args.replicas:
+        # configs[4]: ONE 1441x2880 domain split into latitude bands over the GPUs (halo rows over NVLink)
+        members, scaling, seeds, band = 1, "strong", [42], (rank, world, 16)
     else:
         members = spec["members_per_gpu"]
         scaling, seeds = "weak", [42 + rank * members + m for m in range(members)]
     topos = [make_topography(nlat, nlon, seed=s, land_frac=0.40) for s in seeds]
     sim = Simulation(nlat, nlon, topos, spec["params"], dt=dt, batch=members, with_ocean=True, with_hydrology=True,
-                     loop_with_albedo=True, device=f"cuda:{local}")
+                     loop_with_albedo=True, device=f"cuda:{local}", band=band)
     eng = sim.engine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     state_bytes = members * ncell * 8 * 45
@@ -216,7 +222,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     ms_per_step = dev_ms / args.steps
-    total_members = members * world
+    total_members = 1 if band else members * world
     steps_per_s = 1e3 / ms_per_step
     value = total_members * steps_per_s * dt / DAY
 
@@ -238,7 +244,7 @@ def main():
 
     # -------- per-kernel device time (CUDA events around every launch) -> roofline of the dominant kernel
     roof = None
-    if not args.no_profile and rank == 0:
+    if not args.no_profile and rank == 0 and not band:
         import ctypes
         eng.lib.qd_profile(eng.ctx, 1)
         nprof = min(args.steps, 20)
@@ -288,7 +294,7 @@ def main():
                 "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "cell_steps_per_s": total_members * ncell * steps_per_s,
                 "config": {"workload": spec["label"], "grid": [nlat, nlon], "dt_s": dt, "members_per_gpu": members,
-                           "members_total": total_members, "parallelism": f"independent members x{world}" if world > 1 else "single GPU",
+                           "members_total": total_members, "parallelism": (f"latitude bands x{world}, halo 16 rows over NVLink peer stores" if band else f"independent members x{world}") if world > 1 else "single GPU",
                            "l2": f"256 MiB L2 flush before every timed step (state ~{state_bytes / 1e6:.0f} MB per GPU)",
                            "loop_with_albedo": True},
                 "clocks": clocks,

@@ -256,6 +256,19 @@ int  qd_profile(qd_ctx* ctx, int enable);
 int  qd_profile_report(qd_ctx* ctx, char* buf, int buflen);   /* "name count total_ms" lines; sync */
 
 /* ------------------------------------------------------------------ routing (routing.py:211-335) */
+/* ------------------------------------------------------------------ latitude bands (one domain over the GPUs of a node)
+ * BASELINE configs[4] / SURVEY 8e: rank r of `world` computes a contiguous block of latitude rows (full longitude
+ * circles); halos, partial sums and median histograms travel through per-rank exchange buffers that the peers map
+ * (CUDA IPC) and write directly over NVLink.  Call order on every rank: qd_create, qd_bind, qd_band_init,
+ * qd_band_export -> exchange the 64-byte handles out of band (the host side uses torch.distributed) ->
+ * qd_band_connect.  Afterwards qd_loop_step runs the partitioned step; fields keep their full-size layout and a
+ * rank's own rows [own0, own1) are authoritative.  batch must be 1; routing and the ecology coupling are not
+ * partitioned. */
+int  qd_band_init(qd_ctx* ctx, int rank, int world, int halo_rows);
+int  qd_band_export(qd_ctx* ctx, void* handle64);
+int  qd_band_connect(qd_ctx* ctx, const void* handles /* [world][64] in rank order */);
+int  qd_band_info(qd_ctx* ctx, int* own0, int* own1, int* halo_rows, int* error_word /* != 0: a bounded wait expired */);
+
 /* ------------------------------------------------------------------ ecology sub-daily
  * Replaces EcologyAdapter.step_subdaily (adapter.py:140-186) + PopulationManager.step_subdaily /
  * _should_recompute_canopy / _recompute_canopy_cache / canopy_reflectance_factor

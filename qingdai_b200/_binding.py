@@ -105,6 +105,10 @@ PROTOTYPES = {
     "qd_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "qd_profile": (_I, [_P, _I]),
     "qd_profile_report": (_I, [_P, C.c_char_p, _I]),
+    "qd_band_init": (_I, [_P, _I, _I, _I]),
+    "qd_band_export": (_I, [_P, _P]),
+    "qd_band_connect": (_I, [_P, _P]),
+    "qd_band_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "qd_eco_bind": (_I, [_P, _P, _I, _D, _D, _D, _I]),
     "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
     "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),

@@ -45,7 +45,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk, red_blk, h4_stream;
+  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -75,6 +75,9 @@ struct qd_ctx {
   char err[512];
   qd_route route;
   void* prof;
+  // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
+  QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
+  int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
   // ecology sub-daily (qd_eco.cuh)
   const double* d_lai; int eco_nl, eco_every_nphys, eco_steps, eco_have_alpha;
   double eco_k, eco_every_hours, eco_delta;
@@ -141,10 +144,12 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
     const int pi_ = qd_prof_begin((c), #kern); \
     QD_LAUNCH(kern, (grid), (block), (c)->stream, __VA_ARGS__); \
     qd_prof_end((c), pi_); (c)->launches++; } while (0)
-#define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->cur_nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 // grid-stride kernels that end in a grid-wide reduction (QD_CELL_LOOP): at most red_blk blocks per member
-#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3((c)->red_blk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min((c)->red_blk, (c)->cur_nblk), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 
+struct BIn;
+static void band_release(qd_ctx* c);
 #ifndef QD_HOST_EMU
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
 static bool qd_prof_on(qd_ctx* c) { return c->prof && qd_prof_of(c)->on; }
@@ -233,10 +238,14 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   memset(c->err, 0, sizeof(c->err));
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
+  c->cur_nblk = c->nblk;
   c->h4_stream = 1;
   c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
+  memset(&c->band, 0, sizeof(c->band)); c->band.world = 1; c->band_on = 0; c->band_bytes = 0; c->band_base = nullptr;
+  memset(c->band_peer_map, 0, sizeof(c->band_peer_map)); memset(c->band_shm, 0, sizeof(c->band_shm)); c->band_maxext = 0;
+  for (int k = 0; k < QD_F_COUNT + QD_M_COUNT; ++k) c->band_valid[k] = 1 << 28;
   c->d_lai = nullptr; c->eco_nl = 0; c->eco_every_nphys = 1; c->eco_steps = 0; c->eco_have_alpha = 0;
   c->eco_k = 0.5; c->eco_every_hours = 6.0; c->eco_delta = 0.05;
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
@@ -295,6 +304,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
+  g.own0 = 0; g.own1 = nlat; g.sa0 = 0; g.sa1 = nlat; g.sb0 = 0; g.sb1 = 0; g.ncomp = c->ncell;
   g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
   for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { delete c; return QD_E_CUDA; }
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
@@ -318,6 +328,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
+  band_release(c);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
@@ -410,12 +421,242 @@ extern "C" int qd_download_field(qd_ctx* c, int f, int m, double* h) { if (!c ||
 extern "C" int qd_upload_mask(qd_ctx* c, int f, int m, const uint8_t* h) { if (!c || f < 0 || f >= QD_M_COUNT) return QD_E_INVALID; return qd_xfer(c, M(c, f), 1, m, (void*)h, true); }
 extern "C" int qd_download_mask(qd_ctx* c, int f, int m, uint8_t* h) { if (!c || f < 0 || f >= QD_M_COUNT) return QD_E_INVALID; return qd_xfer(c, M(c, f), 1, m, h, false); }
 
+// ------------------------------------------------------------------------------ latitude bands (host side)
+#ifdef QD_HOST_EMU
+#include <sys/mman.h>
+#include <fcntl.h>
+#include <unistd.h>
+#endif
+#define QD_VALID_ALL (1 << 28)
+static const int QD_BAND_STATIC_F[] = {QD_F_FRICTION, QD_F_BASE_ALBEDO, QD_F_ELEVATION, QD_F_CS_MAP, QD_F_OROG_NX, QD_F_OROG_NY};
+static inline bool band_is_static(int id) {
+  if (id == QD_F_COUNT + QD_M_LAND) return true;
+  for (int s : QD_BAND_STATIC_F) if (s == id) return true;
+  return false;
+}
+static void band_rows_of(int nlat, int world, int rank, int* r0, int* r1) {
+  const int base = nlat / world, rem = nlat % world;
+  *r0 = rank * base + std::min(rank, rem);
+  *r1 = *r0 + base + (rank < rem ? 1 : 0);
+}
+// compute region = own rows widened by `ext` rows on both sides (mod n_lat) -> c->geo segments, launch size
+static void band_set_ext(qd_ctx* c, int ext) {
+  QdGeo& g = c->geo;
+  if (!c->band_on) { g.sa0 = 0; g.sa1 = c->nlat; g.sb0 = g.sb1 = 0; }
+  else {
+    const int lo = g.own0 - ext, hi = g.own1 + ext, n = c->nlat;
+    if (hi - lo >= n) { g.sa0 = 0; g.sa1 = n; g.sb0 = g.sb1 = 0; }
+    else if (lo < 0) { g.sa0 = 0; g.sa1 = hi; g.sb0 = n + lo; g.sb1 = n; }
+    else if (hi > n) { g.sa0 = lo; g.sa1 = n; g.sb0 = 0; g.sb1 = hi - n; }
+    else { g.sa0 = lo; g.sa1 = hi; g.sb0 = g.sb1 = 0; }
+  }
+  g.ncomp = ((g.sa1 - g.sa0) + (g.sb1 - g.sb0)) * c->nlon;
+  c->cur_nblk = std::max(1, (g.ncomp + QD_THREADS - 1) / QD_THREADS);
+}
+static int band_fid(qd_ctx* c, const void* p) {             // field / mask slot of a pointer into the bound blocks, -1 otherwise
+  const size_t fsz = (size_t)c->batch * c->ncell;
+  const double* d = (const double*)p;
+  if (c->fields && d >= c->fields && d < c->fields + (size_t)QD_F_COUNT * fsz) return (int)((d - c->fields) / fsz);
+  const uint8_t* m = (const uint8_t*)p;
+  if (c->masks && m >= c->masks && m < c->masks + (size_t)QD_M_COUNT * fsz) return QD_F_COUNT + (int)((m - c->masks) / fsz);
+  return -1;
+}
+static int band_exchange(qd_ctx* c, const int* ids, int n) {
+  for (int k0 = 0; k0 < n; k0 += QD_BAND_MAXX) {
+    QdBandList L; memset(&L, 0, sizeof(L));
+    L.n = std::min(QD_BAND_MAXX, n - k0);
+    for (int k = 0; k < L.n; ++k) { L.f[k] = F(c, ids[k0 + k]); c->band_valid[ids[k0 + k]] = c->band.H; }
+    const int gx = std::max(1, std::min(32, (c->band.H * c->nlon + QD_THREADS - 1) / QD_THREADS));
+    QD_KG(c, k_band_push, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
+    QD_KG(c, k_band_unpack, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
+  }
+  return QD_OK;
+}
+// rows a semi-Lagrangian gather may reach: winds are clipped to +-200 m/s (dynamics.py:522-527), the second
+// bilinear tap adds one row, one more for safety
+static int band_radv(qd_ctx* c, double dt) { return (int)floor(200.0 * fabs(dt) / (c->geo.a * c->geo.dlat)) + 2; }
+
+struct BIn { const void* p; int r; };
+#define BP(c, ins, outs) do { int rc_ = band_prep((c), ins, outs); if (rc_) return rc_; } while (0)
+#define BL(...) {__VA_ARGS__}
+#define BPV(c, ins, outs) do { int rc_ = band_prep_v((c), ins, outs); if (rc_) return rc_; } while (0)
+// Called before every field kernel of the step.  ins: (pointer, stencil / gather radius in rows); outs: fields the
+// kernel writes on its whole compute region.  Chooses the widest compute region the inputs allow, exchanging
+// halos first when an input is not even valid for the kernel's own rows; records the outputs' valid width.
+static int band_prep_v(qd_ctx* c, const std::vector<BIn>& ins, const std::vector<const void*>& outs);
+static int band_prep(qd_ctx* c, std::initializer_list<BIn> ins, std::initializer_list<const void*> outs) {
+  if (!c->band_on) return QD_OK;
+  return band_prep_v(c, std::vector<BIn>(ins), std::vector<const void*>(outs));
+}
+static int band_prep_v(qd_ctx* c, const std::vector<BIn>& ins, const std::vector<const void*>& outs) {
+  if (!c->band_on) return QD_OK;
+  const int H = c->band.H, T = H / 2;
+  bool need = false;
+  for (const BIn& in : ins) {
+    const int id = band_fid(c, in.p);
+    if (id < 0) continue;
+    if (c->band_valid[id] < in.r) {
+      if (id >= QD_F_COUNT) return qd_fail(c, QD_E_STATE, "latitude bands: a mask would need a halo exchange", cudaSuccess);
+      need = true;
+    }
+  }
+  if (need) {
+    int ids[32]; int n = 0;
+    for (const BIn& in : ins) {
+      const int id = band_fid(c, in.p);
+      if (id < 0 || id >= QD_F_COUNT || band_is_static(id)) continue;
+      if (c->band_valid[id] - in.r >= T) continue;
+      bool dup = false;
+      for (int k = 0; k < n; ++k) dup = dup || ids[k] == id;
+      if (!dup && n < 32) ids[n++] = id;
+    }
+    int rc = band_exchange(c, ids, n); if (rc) return rc;
+  }
+  int ext = std::min(H, c->band_maxext);
+  for (const BIn& in : ins) {
+    const int id = band_fid(c, in.p);
+    if (id < 0) continue;
+    if (in.r > H) return qd_fail(c, QD_E_STATE, "latitude bands: halo width smaller than a stencil radius", cudaSuccess);
+    ext = std::min(ext, c->band_valid[id] - in.r);
+  }
+  if (ext < 0) return qd_fail(c, QD_E_STATE, "latitude bands: negative compute extent", cudaSuccess);
+  band_set_ext(c, ext);
+  for (const void* o : outs) { const int id = band_fid(c, o); if (id >= 0) c->band_valid[id] = ext; }
+  return QD_OK;
+}
+static void band_invalidate_dynamic(qd_ctx* c) {            // start of a step / of a sub-step body: fixed point for graph replay
+  if (!c->band_on) return;
+  for (int id = 0; id < QD_F_COUNT + QD_M_COUNT; ++id) c->band_valid[id] = band_is_static(id) ? QD_VALID_ALL : 0;
+}
+static int band_allreduce(qd_ctx* c, std::initializer_list<int> ids, bool is_max) {
+  if (!c->band_on) return QD_OK;
+  QdBandRed R; memset(&R, 0, sizeof(R));
+  for (int id : ids) { R.id[R.n] = id; R.is_max[R.n] = is_max ? 1 : 0; R.n++; }
+  QD_KG(c, k_band_allreduce, dim3(1), dim3(32), c->band, R, c->d_scal);
+  return QD_OK;
+}
+
+extern "C" int qd_band_init(qd_ctx* c, int rank, int world, int halo_rows) {
+  if (!c || world < 1 || world > QD_BAND_MAXW || rank < 0 || rank >= world) return QD_E_INVALID;
+  if (world == 1) { c->band_on = 0; return QD_OK; }
+  if (c->batch != 1) return qd_fail(c, QD_E_INVALID, "latitude bands drive one member per context", cudaSuccess);
+  const int min_rows = c->nlat / world;
+  int H = std::min(halo_rows, min_rows / 2);
+  if (H < 4) return qd_fail(c, QD_E_INVALID, "latitude bands need >= 8 rows per rank (del^4 halo of 4)", cudaSuccess);
+  QdBandCtl& B = c->band;
+  memset(&B, 0, sizeof(B));
+  B.rank = rank; B.world = world; B.H = H; B.nlon = c->nlon; B.nlat = c->nlat;
+  size_t off = QD_BF_WORDS * 8;
+  auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+  B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * 8);
+  B.off_red = take((size_t)2 * QD_BAND_MAXW * QD_BAND_MAXR * 8);
+  B.off_hist = take((size_t)2 * QD_BAND_MAXW * QD_SEL_MAXBINS * 4);
+  B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * 8);
+#ifdef QD_HOST_EMU
+  B.off_emu = take((size_t)QD_BAND_MAXW * ((size_t)c->ncell + 1) * 8);
+#else
+  B.off_emu = off;
+#endif
+  c->band_bytes = off;
+#ifdef QD_HOST_EMU
+  snprintf(c->band_shm, sizeof(c->band_shm), "/qd_band_%d_%d_%p", (int)getpid(), rank, (void*)c);
+  int fd = shm_open(c->band_shm, O_CREAT | O_RDWR | O_TRUNC, 0600);
+  if (fd < 0 || ftruncate(fd, (off_t)c->band_bytes) != 0) return qd_fail(c, QD_E_CUDA, "shm_open", cudaSuccess);
+  c->band_base = (char*)mmap(nullptr, c->band_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (c->band_base == (char*)MAP_FAILED) return qd_fail(c, QD_E_CUDA, "mmap", cudaSuccess);
+  memset(c->band_base, 0, c->band_bytes);
+#else
+  QD_CUDA(c, cudaMalloc((void**)&c->band_base, c->band_bytes));
+  QD_CUDA(c, cudaMemset(c->band_base, 0, c->band_bytes));
+  QD_CUDA(c, cudaDeviceSynchronize());
+#endif
+  B.peer[rank] = c->band_base;
+  band_rows_of(c->nlat, world, rank, &c->geo.own0, &c->geo.own1);
+  c->band_maxext = H;
+  return QD_OK;
+}
+// 64 opaque bytes that let the other ranks map this rank's exchange buffer (cudaIpcMemHandle_t / shm name)
+extern "C" int qd_band_export(qd_ctx* c, void* handle64) {
+  if (!c || !handle64 || !c->band_base) return QD_E_INVALID;
+  memset(handle64, 0, 64);
+#ifdef QD_HOST_EMU
+  memcpy(handle64, c->band_shm, std::min(sizeof(c->band_shm), (size_t)64));
+#else
+  static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  QD_CUDA(c, cudaIpcGetMemHandle(&h, c->band_base));
+  memcpy(handle64, &h, sizeof(h));
+#endif
+  return QD_OK;
+}
+extern "C" int qd_band_connect(qd_ctx* c, const void* handles /* [world][64], rank order */) {
+  if (!c || !handles || !c->band_base) return QD_E_INVALID;
+  QdBandCtl& B = c->band;
+  for (int r = 0; r < B.world; ++r) {
+    if (r == B.rank) continue;
+    const char* h = (const char*)handles + (size_t)r * 64;
+#ifdef QD_HOST_EMU
+    char name[65]; memcpy(name, h, 64); name[64] = 0;
+    int fd = shm_open(name, O_RDWR, 0600);
+    if (fd < 0) return qd_fail(c, QD_E_CUDA, "shm_open(peer)", cudaSuccess);
+    void* m = mmap(nullptr, c->band_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return qd_fail(c, QD_E_CUDA, "mmap(peer)", cudaSuccess);
+    c->band_peer_map[r] = m; B.peer[r] = (char*)m;
+#else
+    cudaIpcMemHandle_t ih; memcpy(&ih, h, sizeof(ih));
+    void* m = nullptr;
+    QD_CUDA(c, cudaIpcOpenMemHandle(&m, ih, cudaIpcMemLazyEnablePeerAccess));
+    c->band_peer_map[r] = m; B.peer[r] = (char*)m;
+#endif
+  }
+  c->band_on = 1;
+  band_invalidate_dynamic(c);
+  band_set_ext(c, 0);
+  return QD_OK;
+}
+extern "C" int qd_band_info(qd_ctx* c, int* own0, int* own1, int* halo, int* error_word) {
+  if (!c) return QD_E_INVALID;
+  if (own0) *own0 = c->geo.own0;
+  if (own1) *own1 = c->geo.own1;
+  if (halo) *halo = c->band_on ? c->band.H : 0;
+  if (error_word) {
+    *error_word = 0;
+    if (c->band_on) {
+      unsigned long long e = 0;
+#ifdef QD_HOST_EMU
+      e = ((unsigned long long*)c->band_base)[QD_BF_ERR];
+#else
+      QD_CUDA(c, cudaStreamSynchronize(c->stream));
+      QD_CUDA(c, cudaMemcpy(&e, c->band_base + QD_BF_ERR * 8, 8, cudaMemcpyDeviceToHost));
+#endif
+      *error_word = (int)e;
+    }
+  }
+  return QD_OK;
+}
+static void band_release(qd_ctx* c) {
+  if (!c->band_base) return;
+#ifdef QD_HOST_EMU
+  for (int r = 0; r < QD_BAND_MAXW; ++r) if (c->band_peer_map[r]) munmap(c->band_peer_map[r], c->band_bytes);
+  munmap(c->band_base, c->band_bytes);
+  shm_unlink(c->band_shm);
+#else
+  for (int r = 0; r < QD_BAND_MAXW; ++r) if (c->band_peer_map[r]) cudaIpcCloseMemHandle(c->band_peer_map[r]);
+  cudaFree(c->band_base);
+#endif
+  c->band_base = nullptr; c->band_on = 0;
+}
+
 // ------------------------------------------------------------------------------ operator building blocks
 static QdFields mk_fields(int n) { QdFields f; memset(&f, 0, sizeof(f)); f.n = n; for (int k = 0; k < QD_MAX_FIELDS; ++k) f.scale[k] = 1.0; return f; }
 
 static int op_laplacian(qd_ctx* c, int n, const double* const* src, double* const* dst, const double* cosr) {
   QdFields f = mk_fields(n);
-  for (int k = 0; k < n; ++k) { f.src[k] = src[k]; f.dst[k] = dst[k]; }
+  std::vector<BIn> bi; std::vector<const void*> bo;
+  for (int k = 0; k < n; ++k) { f.src[k] = src[k]; f.dst[k] = dst[k]; bi.push_back({src[k], 2}); bo.push_back(dst[k]); }
+  BPV(c, bi, bo);
   QD_K(c, k_laplacian, c->geo, f, cosr);
   QD_CHECK_LAUNCH(c);
   return QD_OK;
@@ -430,7 +671,37 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   static const char* const nm8[] = {"", "k_hyper4_tile<8>[1]", "k_hyper4_tile<8>[2]", "k_hyper4_tile<8>[3]", "k_hyper4_tile<8>[4]", "k_hyper4_tile<8>[5]"};
   static const char* const nms[] = {"", "k_hyper4_stream[1]", "k_hyper4_stream[2]", "k_hyper4_stream[3]", "k_hyper4_stream[4]", "k_hyper4_stream[5]"};
   const int nn = H.n < 1 ? 1 : (H.n > 5 ? 5 : H.n);
-  H.tj_lo = 1 << 30; H.tj_skip = 0; H.ja = 0; H.jb = 0;
+  H.tj_lo = 1 << 30; H.tj_skip = 0; H.ja = 0; H.jb = 0; H.row0 = 0; H.row1 = c->nlat;
+  {
+    std::vector<BIn> bi; std::vector<const void*> bo;
+    for (int k = 0; k < H.n; ++k) { bi.push_back({H.src[k], 4}); bo.push_back(H.dst[k]); }
+    BPV(c, bi, bo);
+  }
+  if (c->band_on) {
+    // latitude bands: the tile kernel over each segment of the compute region (large segments stream their
+    // centred rows); pole handling inside the kernels works on global row indices
+    const int seg[2][2] = {{c->geo.sa0, c->geo.sa1}, {c->geo.sb0, c->geo.sb1}};
+    for (int q = 0; q < 2; ++q) {
+      int s0 = seg[q][0], s1 = seg[q][1];
+      if (s1 <= s0) continue;
+#ifndef QD_HOST_EMU
+      const int ja = std::max(s0, 8), jb = std::min(s1, ((c->nlat + 7) / 8 - 2) * 8);
+      if (c->h4_stream && c->nlon >= 64 && jb - ja >= 32 && (long long)(jb - ja) * c->nlon * H.n >= (1 << 20)) {
+        constexpr int R = 64;
+        H.ja = ja; H.jb = jb;
+        const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+        const int nwarps = nstrips * ((jb - ja + R - 1) / R);
+        QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        if (s0 < ja) { H.row0 = s0; H.row1 = ja; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((ja - s0 + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
+        if (jb < s1) { H.row0 = jb; H.row1 = s1; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((s1 - jb + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
+        continue;
+      }
+#endif
+      H.row0 = s0; H.row1 = s1;
+      QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((s1 - s0 + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    }
+    return QD_OK;
+  }
 #ifndef QD_HOST_EMU
   const int ntj8 = (c->nlat + 7) / 8;
   if (blocks32 >= 2 * 148 && c->nlat >= 96 && c->nlon >= 64 && c->h4_stream) {
@@ -479,8 +750,14 @@ static int op_shapiro(qd_ctx* c, int n, double* const* fld, double* const* scrat
   const int np = passes > 1 ? passes : 1;
   for (int p = 0; p < np; ++p) {
     QdFields a = mk_fields(n), b2 = mk_fields(n);
-    for (int k = 0; k < n; ++k) { a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k]; }
+    std::vector<BIn> i1, i2; std::vector<const void*> o1, o2;
+    for (int k = 0; k < n; ++k) {
+      a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k];
+      i1.push_back({fld[k], 0}); o1.push_back(scratch[k]); i2.push_back({scratch[k], 1}); o2.push_back(fld[k]);
+    }
+    BPV(c, i1, o1);
     QD_K(c, k_shapiro_lon, c->geo, a, p == 0 ? 1 : 0);
+    BPV(c, i2, o2);
     QD_K(c, k_shapiro_lat, c->geo, b2);
   }
   QD_CHECK_LAUNCH(c);
@@ -502,8 +779,14 @@ extern "C" int qd_set_gauss(qd_ctx* c, int which, int radius, int wrap, const do
 static int op_gauss(qd_ctx* c, int n, double* const* fld, double* const* scratch, const QdGaussW& w) {
   if (w.r == 0) return QD_OK;
   QdFields a = mk_fields(n), b2 = mk_fields(n);
-  for (int k = 0; k < n; ++k) { a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k]; }
+  std::vector<BIn> i1, i2; std::vector<const void*> o1, o2;
+  for (int k = 0; k < n; ++k) {
+    a.src[k] = fld[k]; a.dst[k] = scratch[k]; b2.src[k] = scratch[k]; b2.dst[k] = fld[k];
+    i1.push_back({fld[k], w.r}); o1.push_back(scratch[k]); i2.push_back({scratch[k], 0}); o2.push_back(fld[k]);
+  }
+  BPV(c, i1, o1);
   QD_K(c, k_gauss_lat, c->geo, a, w);
+  BPV(c, i2, o2);
   QD_K(c, k_gauss_lon, c->geo, b2, w);
   QD_CHECK_LAUNCH(c);
   return QD_OK;
@@ -516,7 +799,8 @@ static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
   int kcut = (int)(cutoff * kN);
   kcut = std::max(1, std::min(kN, kcut));
   const double fac = std::max(0.0, 1.0 - std::min(1.0, damp));
-  QD_KG(c, k_zonal_bandstop, dim3(c->nlat, c->batch), dim3(QD_THREADS), c->geo, fld, c->d_twid, kcut, 1.0 - fac,
+  BP(c, BL({fld, 0}), BL(fld));
+  QD_KG(c, k_zonal_bandstop, dim3((c->geo.sa1 - c->geo.sa0) + (c->geo.sb1 - c->geo.sb0), c->batch), dim3(QD_THREADS), c->geo, fld, c->d_twid, kcut, 1.0 - fac,
         c->d_spec_coef, c->d_spec_out);
   QD_CHECK_LAUNCH(c);
   return QD_OK;
@@ -525,12 +809,12 @@ static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
 static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst, double* cnt, int stride) {
   QdSelOut out; out.value = dst; out.count = cnt; out.stride = stride; out.empty_value = empty_value;
 #ifdef QD_HOST_EMU
-  qd_select_host(c->geo, x, out);
+  qd_select_host(c->geo, x, out, c->band);
   c->launches++;
 #else
   // the kernel leaves hist / list counter / mingt reset for the next launch (no memset nodes in the step graph)
   QdGeo geo = c->geo;
-  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_sel_list, (void*)&c->d_sel_cnt, (void*)&c->d_mingt, (void*)&c->d_sel_more, (void*)&out};
+  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_sel_list, (void*)&c->d_sel_cnt, (void*)&c->d_mingt, (void*)&c->d_sel_more, (void*)&out, (void*)&c->band};
   const int pi = qd_prof_begin(c, "k_select_coop");
   QD_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_select_coop, dim3(c->sel_gx, c->batch), dim3(QD_SEL_THREADS), args, 0, c->stream));
   qd_prof_end(c, pi);
@@ -769,6 +1053,12 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
     if (c->eco_steps % std::max(1, c->eco_every_nphys) == 0) { A.with_eco = 1; c->eco_have_alpha = 1; }
     else A.with_eco = c->eco_have_alpha ? 2 : 3;
   }
+  if (cfg->with_eco && c->band_on) return qd_fail(c, QD_E_STATE, "latitude bands: the ecology coupling is not partitioned yet", cudaSuccess);
+  BP(c, BL({A.u, 0}, {A.v, 0}, {A.h, 0}, {A.ts, 0}, {A.q, 0}, {A.cloud, 0}, {A.hice, 0}, {A.wland, 0}, {A.ssnow, 0}, {A.eday, 0},
+           {A.precip, 0}, {A.cloud_eff, 0}, {A.base_albedo, 0}, {A.elevation, 0}, {A.fcanopy, 0}, {A.land, 0}, {A.pcond, 0},
+           {A.isr_a, 0}, {A.isr_b, 0}, {A.alpha_eco, 0}, {A.eflux, 0}, {A.lh, 0}, {A.lhrel, 0}),
+     BL(A.h, A.ts, A.q, A.hice, A.wland, A.ssnow, A.eday, A.ts_pre, A.q_pre, A.isr, A.isr_a, A.isr_b, A.olr, A.eflux, A.pcond, A.lh,
+        A.lhrel, A.albedo, A.teq, A.csnow, A.rland, A.alpha_eco, A.glacier));
   QD_K(c, k_column, c->geo, A);
 
   if (has_alb) {
@@ -783,6 +1073,9 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
     E.ts = F(c, QD_F_TS); E.q_pre = F(c, QD_F_X3); E.cloud = F(c, QD_F_CLOUD); E.pcond = F(c, QD_F_PCOND); E.isr = F(c, QD_F_ISR);
     E.albedo = F(c, QD_F_ALBEDO); E.teq = F(c, QD_F_TEQ); E.u = F(c, QD_F_U); E.v = F(c, QD_F_V); E.lh = F(c, QD_F_LH); E.lhrel = F(c, QD_F_LHREL);
     E.cs_map = F(c, QD_F_CS_MAP); E.land = M(c, QD_M_LAND); E.dt = dt;
+    BP(c, BL({E.h, 0}, {E.hice, 0}, {E.ts_pre, 0}, {E.olr, 0}, {E.cloud_eff, 0}, {E.ts, 0}, {E.q_pre, 0}, {E.cloud, 0}, {E.pcond, 0},
+             {E.isr, 0}, {E.albedo, 0}, {E.teq, 0}, {E.u, 0}, {E.v, 0}, {E.lh, 0}, {E.lhrel, 0}, {E.cs_map, 0}, {E.land, 0}),
+       BL(E.h, E.hice, E.ts_pre, E.olr, E.cloud_eff));
     QD_K(c, k_energy, c->geo, E);
     c->has_cloud_eff = 1;
   }
@@ -792,6 +1085,8 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   QdAdvMomArgs AM; memset(&AM, 0, sizeof(AM));
   AM.ts_pre = F(c, QD_F_X2); AM.q_pre = F(c, QD_F_X3); AM.h = F(c, QD_F_H); AM.friction = F(c, QD_F_FRICTION);
   AM.ts = F(c, QD_F_TS); AM.q = F(c, QD_F_Q); AM.u = F(c, QD_F_U); AM.v = F(c, QD_F_V); AM.dt = dt;
+  BP(c, BL({AM.ts_pre, band_radv(c, dt)}, {AM.q_pre, band_radv(c, dt)}, {AM.h, 1}, {AM.friction, 0}, {AM.u, 0}, {AM.v, 0}, {AM.ts, 0}, {AM.q, 0}),
+     BL(AM.ts, AM.q, AM.u, AM.v));
   QD_K(c, k_advect_momentum, c->geo, AM);
 
   // From here on u, v, h, q, cloud may live in scratch slots (the fused del^4 kernel is out of place);
@@ -844,6 +1139,7 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   // cloud tail: advect with the NEW winds, then dissipation / damping / hygiene (+ Q_net in loop mode)
   {
     QdFields f = mk_fields(1); f.src[0] = cur[iC]; f.dst[0] = F(c, QD_F_X9);
+    BP(c, BL({f.src[0], band_radv(c, dt)}, {cur[iU], 0}, {cur[iV], 0}), BL(f.dst[0]));
     QD_K(c, k_advect, c->geo, f, cur[iU], cur[iV], dt, ROW(c, QD_R_COS_ADV_ATM));
     QdTailArgs T; memset(&T, 0, sizeof(T));
     T.u_in = cur[iU]; T.v_in = cur[iV]; T.h_in = cur[iH]; T.q_in = cur[iQ];
@@ -853,6 +1149,9 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
     T.qnet = F(c, QD_F_QNET); T.ice = M(c, QD_M_ICE); T.land = M(c, QD_M_LAND);
     T.part_max_u = c->d_part[0]; T.part_max_va = c->d_part[1]; T.ticket = c->d_ticket + 3 * c->batch;
     T.dt = dt; T.with_qnet = (mode_loop && cfg->with_ocean) ? 1 : 0; T.has_cloud_eff = c->has_cloud_eff; T.with_max = 0;
+    BP(c, BL({T.u_in, 0}, {T.v_in, 0}, {T.h_in, 0}, {T.q_in, 0}, {T.ts, 0}, {T.cloud_adv, 0}, {T.hice, 0}, {T.isr, 0}, {T.albedo, 0},
+             {T.cloud_eff, 0}, {T.lh, 0}, {T.uo, 0}, {T.vo, 0}, {T.land, 0}, {T.qnet, 0}, {T.ice, 0}),
+       BL(T.u, T.v, T.h, T.ts, T.q, T.cloud, T.qnet, T.ice));
     QD_KR(c, k_tail, c->geo, T);
   }
   QD_CHECK_LAUNCH(c);
@@ -875,6 +1174,10 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
   Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
   Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
+  if (c->band_on)   // loop-carried fields start every sub-step from "own rows only": the body replays unchanged (WHILE node)
+    for (int id : {(int)QD_F_UO, (int)QD_F_VO, (int)QD_F_ETA, (int)QD_F_SST, (int)QD_F_TS, (int)QD_F_X2, (int)QD_F_X3, (int)QD_F_X4,
+                   (int)QD_F_X5, (int)QD_F_X6, (int)QD_F_X7, (int)QD_F_X8, (int)QD_F_X9}) c->band_valid[id] = 0;
+  BP(c, BL({Mo.eta, 1}, {Mo.uo, 0}, {Mo.vo, 0}, {Mo.taux, 0}, {Mo.tauy, 0}, {Mo.land, 0}), BL(Mo.ub, Mo.vb));
   QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
   double* ub = F(c, QD_F_X2); double* vb = F(c, QD_F_X3); double* eta_cur = F(c, QD_F_ETA);
   if (do_hyper) {
@@ -906,15 +1209,19 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
   Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
   Co.ticket = c->d_ticket + 5 * c->batch;
+  BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}), BL(Co.eta));
   QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
+  { int rcb = band_allreduce(c, {QD_S_ETA_NUM}, false); if (rcb) return rcb; }
   QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
   Sa.sst = F(c, QD_F_SST); Sa.ub = ub; Sa.vb = vb; Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
+  BP(c, BL({Sa.sst, 2}, {Sa.ub, 0}, {Sa.vb, 0}, {Sa.eta, 0}), BL(Sa.eta, Sa.tb));
   QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
   Sb.tb = F(c, QD_F_X7); Sb.ub = ub; Sb.vb = vb; Sb.qnet = F(c, QD_F_QNET);
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
+  BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}), BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm));
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
   return QD_OK;
 }
@@ -972,7 +1279,9 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   P0.u = F(c, QD_F_U); P0.v = F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
+  BP(c, BL({P0.u, 0}, {P0.v, 0}, {P0.uo, 0}, {P0.vo, 0}), BL(P0.taux, P0.tauy));
   QD_KR(c, k_ocean_prep, c->geo, P0);
+  { int rcb = band_allreduce(c, {QD_S_MAX_UOCEAN, QD_S_MAX_VA}, true); if (rcb) return rcb; }
   QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
   QD_CHECK_LAUNCH(c);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
@@ -1032,6 +1341,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   Po.sst = F(c, QD_F_SST); Po.uo = F(c, QD_F_UO); Po.vo = F(c, QD_F_VO); Po.ts_atm = F(c, QD_F_TS);
   Po.land = M(c, QD_M_LAND); Po.ice = M(c, QD_M_ICE); Po.has_ice = cfg->oc_has_ice; Po.inject = inject;
   QD_KG(c, k_ocean_polar, dim3(2, c->batch), dim3(QD_THREADS), c->geo, Po);
+  if (c->band_on) for (int id : {(int)QD_F_SST, (int)QD_F_UO, (int)QD_F_VO, (int)QD_F_TS}) c->band_valid[id] = 0;   // pole rows changed on their owners only
   QD_CHECK_LAUNCH(c);
   return QD_OK;
 }
@@ -1063,30 +1373,40 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   QdPrecipAArgs Pa; memset(&Pa, 0, sizeof(Pa));
   Pa.u = F(c, QD_F_U); Pa.v = F(c, QD_F_V); Pa.pcond = F(c, QD_F_PCOND); Pa.nx = F(c, QD_F_OROG_NX); Pa.ny = F(c, QD_F_OROG_NY);
   Pa.pos = F(c, QD_F_X0); Pa.orog_raw = F(c, QD_F_X1); Pa.part = c->d_part[0]; Pa.ticket = c->d_ticket + 6 * c->batch;
+  BP(c, BL({Pa.u, 1}, {Pa.v, 1}, {Pa.pcond, 0}, {Pa.nx, 0}, {Pa.ny, 0}), BL(Pa.pos, Pa.orog_raw));
   QD_KR(c, k_precip_a, c->geo, Pa);
+  if ((rc = band_allreduce(c, {QD_S_SUM_PQW}, false))) return rc;
   if (orog) { double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X2)}; if ((rc = op_gauss(c, 1, fl, sx, w1))) return rc; }
   if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT))) return rc;
   QdPrecipBArgs Pb; memset(&Pb, 0, sizeof(Pb));
   Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = F(c, QD_F_X1); Pb.praw = F(c, QD_F_X2);
   Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
+  BP(c, BL({Pb.pos, 0}, {Pb.pcond, 0}, {Pb.orog, 0}), BL(Pb.praw));
   QD_KR(c, k_precip_b, c->geo, Pb);
+  if ((rc = band_allreduce(c, {QD_S_SUM_PRAWW}, false))) return rc;
   QdPrecipCArgs Pc; Pc.praw = F(c, QD_F_X2); Pc.pos = F(c, QD_F_X0); Pc.g0 = F(c, QD_F_X3); Pc.g1 = F(c, QD_F_X4);
+  BP(c, BL({Pc.praw, w1.r}, {Pc.pos, w1.r}, {Pc.g1, 0}), BL(Pc.g0, Pc.g1));
   QD_K(c, k_precip_c, c->geo, Pc, w1);
   QdPrecipDArgs Pd; Pd.g0 = F(c, QD_F_X3); Pd.g1 = F(c, QD_F_X4); Pd.precip = F(c, QD_F_PRECIP);
+  BP(c, BL({Pd.g0, 0}, {Pd.g1, 0}), BL(Pd.precip));
   QD_K(c, k_precip_d, c->geo, Pd, w1);
   // clouds (run_simulation.py:1866-1934)
   if ((rc = op_median(c, F(c, QD_F_PRECIP), 1e-6, c->d_scal + QD_S_PREF, c->d_scal + QD_S_CNT_PRECIP, QD_S_COUNT))) return rc;
   QdCloudAArgs Ca; Ca.precip = F(c, QD_F_PRECIP); Ca.ts = F(c, QD_F_TS); Ca.u = F(c, QD_F_U); Ca.v = F(c, QD_F_V);
   Ca.craw = F(c, QD_F_X0); Ca.sraw = F(c, QD_F_X1);
+  BP(c, BL({Ca.precip, 0}, {Ca.ts, 1}, {Ca.u, 1}, {Ca.v, 1}), BL(Ca.craw, Ca.sraw));
   QD_K(c, k_cloud_a, c->geo, Ca);
   {
     QdFields f = mk_fields(2); f.src[0] = F(c, QD_F_X0); f.src[1] = F(c, QD_F_X1); f.dst[0] = F(c, QD_F_X2); f.dst[1] = F(c, QD_F_X3);
+    BP(c, BL({f.src[0], w1.r}, {f.src[1], w1.r}), BL(f.dst[0], f.dst[1]));
     QD_K(c, k_gauss_lat, c->geo, f, w1);
   }
   QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt;
+  BP(c, BL({Cb.g0, 0}, {Cb.g1, 0}, {Cb.cloud, 0}), BL(Cb.cloud));
   QD_K(c, k_cloud_b, c->geo, Cb, w1);
   if (P[QD_P_CLOUD_ADVECT] != 0.0) {
     QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X0);
+    BP(c, BL({f.src[0], band_radv(c, dt)}, {F(c, QD_F_U), 0}, {F(c, QD_F_V), 0}), BL(f.dst[0]));
     QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_HALF));
     const double sig = P[QD_P_CLOUD_SMOOTH_SIGMA];
     QdGaussW wc = c->w_cloud;
@@ -1094,10 +1414,12 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
     const double* src = F(c, QD_F_X0);
     if (wc.r > 0) {
       QdFields g1 = mk_fields(1); g1.src[0] = F(c, QD_F_X0); g1.dst[0] = F(c, QD_F_X1);
+      BP(c, BL({g1.src[0], wc.r}), BL(g1.dst[0]));
       QD_K(c, k_gauss_lat, c->geo, g1, wc);
       src = F(c, QD_F_X1);
     }
     QdCloudCArgs Cc; Cc.g0 = src; Cc.cloud = F(c, QD_F_CLOUD);
+    BP(c, BL({Cc.g0, 0}, {Cc.cloud, 0}), BL(Cc.cloud));
     QD_K(c, k_cloud_c, c->geo, Cc, wc);
   }
   QD_CHECK_LAUNCH(c);
@@ -1106,6 +1428,9 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
 
 static int loop_step_enqueue(qd_ctx* c, const qd_step_cfg_t* cfg) {
   int rc;
+  band_invalidate_dynamic(c);               // every step starts from "own rows only": one graph serves every step
+  if (c->band_on && cfg->with_routing && c->route.ready)
+    return qd_fail(c, QD_E_STATE, "latitude bands: river routing is a global DAG and is not partitioned (SURVEY 8e)", cudaSuccess);
   if ((rc = loop_physics(c, cfg))) return rc;
   if ((rc = atmos_core(c, cfg, 1))) return rc;
   if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
@@ -1113,6 +1438,7 @@ static int loop_step_enqueue(qd_ctx* c, const qd_step_cfg_t* cfg) {
     QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, cfg->dt);
   }
   QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
+  if (c->band_on) band_set_ext(c, 0);
   return QD_OK;
 }
 

@@ -33,6 +33,8 @@ QD_D double qd_eco_total(const QdEcoArgs& A, const QdGeo& g, int b, int idx) {
 __global__ void __launch_bounds__(QD_THREADS) k_eco_stats(QdGeo g, QdEcoArgs A) {
   double sd = 0.0, nd = 0.0, sb = 0.0, nb = 0.0;
   QD_CELL_LOOP(g) {
+    QD_CELL_JI(g)
+    if (!qd_owned(g, j)) continue;
     const double now = qd_eco_total(A, g, b, idx);
     const double s = A.snap[off + idx];
     const double d = fabs(now - s);

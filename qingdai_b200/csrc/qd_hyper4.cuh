@@ -29,6 +29,7 @@ struct QdHyper4Args {
   QdSubCtl sc;
   int tj_lo, tj_skip;                      // tile kernel: tile rows >= tj_lo are shifted by tj_skip (pole tiles only, see launch_hyper4)
   int ja, jb;                              // streaming kernel: output rows [ja, jb), all with a centred dependency cone
+  int row0, row1;                          // tile kernel: output rows [row0, row1) (tile rows count from row0)
 };
 
 // Laplacian at (global row j, tile column c) from a tile accessor A(jglobal, tile_col).
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
   const int tiles_i = (g.nlon + TI - 1) / TI;
   const int tj0 = blockIdx.x / tiles_i, ti = blockIdx.x - tj0 * tiles_i;
   const int tj = tj0 >= A.tj_lo ? tj0 + A.tj_skip : tj0;
-  const int j0 = tj * TJ, i0 = ti * TI;
+  const int j0 = A.row0 + tj * TJ, i0 = ti * TI;
   const int jF0 = j0 - 4, jL0 = j0 - 2, iF0 = i0 - 2;
   const int nlat = g.nlat, nlon = g.nlon;
   const size_t off = (size_t)b * g.ncell;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
 #pragma unroll
     for (int m = 0; m < TJ / NY; ++m) {
       const int r = ty + m * NY, gj = j0 + r;
-      if (gj < nlat) {
+      if (gj < A.row1) {
         const int e = (r + 2) * CL + tx + 1, fr = r + 4;
         double L2;
         if (gj >= 2 && gj <= nlat - 3) {
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
   const int tiles_i = (g.nlon + TI - 1) / TI;
   const int tj0 = blockIdx.x / tiles_i, ti = blockIdx.x - tj0 * tiles_i;
   const int tj = tj0 >= A.tj_lo ? tj0 + A.tj_skip : tj0;
-  const int j0 = tj * TJ, i0 = ti * TI;
+  const int j0 = A.row0 + tj * TJ, i0 = ti * TI;
   const int jF0 = j0 - 4, jL0 = j0 - 2, iF0 = i0 - 2;
   const int nlat = g.nlat, nlon = g.nlon;
   const size_t off = (size_t)b * g.ncell;
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
 #pragma unroll 4
     for (int r = threadIdx.y; r < TJ; r += QD_H4_NY) {
       const int gj = j0 + r;
-      if (gj < nlat) {
+      if (gj < A.row1) {
         const int lr = r + 2, e = lr * CL + cc + 1, fr = r + 4;
         double L2;
         if (gj >= 2 && gj <= nlat - 3) {

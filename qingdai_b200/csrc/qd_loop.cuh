@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_precip_a(QdGeo g, QdPrecipAArgs 
     const size_t c = off + idx;
     const double div = qd_div_cell(A.u + off, A.v + off, j, i, g);
     A.pos[c] = qd_max(0.0, -(div - P[QD_P_D_CRIT]));
-    contrib += qd_max(0.0, A.pcond[c]) * qd_row(g, QD_R_W)[j];
+    if (qd_owned(g, j)) contrib += qd_max(0.0, A.pcond[c]) * qd_row(g, QD_R_W)[j];
     if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) {           // physics.py:154-156
       const double up = qd_max(0.0, A.u[c] * A.nx[c] + A.v[c] * A.ny[c]);
       A.orog_raw[c] = qd_clip(1.0 + P[QD_P_K_OROG] * up, 1.0, 2.0);
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_precip_b(QdGeo g, QdPrecipBArgs 
     const double F = (1.0 + P[QD_P_BETA_DIV] * F_div) * F_or;
     const double praw = qd_max(0.0, A.pcond[c]) * F;
     A.praw[c] = praw;
-    contrib += praw * qd_row(g, QD_R_W)[j];
+    if (qd_owned(g, j)) contrib += praw * qd_row(g, QD_R_W)[j];
   }
   double t;
   double* part = A.part + (size_t)b * gridDim.x;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
   QD_CELL_LOOP(g) {
+    QD_CELL_JI(g)
     const size_t c = off + idx;
     const double uo = A.uo[c], vo = A.vo[c];
     const double ur = A.u[c] - uo, vr = A.v[c] - vo;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
     const bool land = A.land[c] == 1;
     if (land) e = 0.0;
     A.eta[c] = e;
-    contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
+    if (qd_owned(g, j)) contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
   }
   double t;
   double* part = A.part + (size_t)b * gridDim.x;
@@ -279,6 +280,7 @@ struct QdOcPolarArgs {
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarArgs A) {
   const int b = blockIdx.y, north = blockIdx.x;
   const int j = north ? g.nlat - 1 : 0, n = g.nlon;
+  if (!qd_owned(g, j)) return;               // latitude bands: the rank that owns the pole row (full longitude circle)
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const size_t base = (size_t)b * g.ncell + (size_t)j * n;
   double* T = A.sst + base;

@@ -24,6 +24,10 @@ struct QdGeo {
   const double* cols;    // [QD_C_COUNT][nlon]
   const double* prm;     // [B][QD_P_COUNT]
   double* scal;          // [B][QD_S_COUNT]
+  // Latitude-band decomposition (qd_band.cuh).  Every rank stores full-size fields but computes only the
+  // rows of up to two segments [sa0,sa1) u [sb0,sb1) (its own rows [own0,own1) widened by the halo the
+  // inputs allow; the second segment is the part that wraps over a pole).  One rank: sa = own = [0, nlat).
+  int own0, own1, sa0, sa1, sb0, sb1, ncomp;
 };
 
 struct QdFields {          // up to QD_MAX_FIELDS field pointers passed by value
@@ -36,14 +40,20 @@ struct QdFields {          // up to QD_MAX_FIELDS field pointers passed by value
 
 struct QdGaussW { int r; int wrap; double w[2 * QD_GAUSS_MAXR + 1]; };
 
+// row r of the compute region -> global row
+QD_HD int qd_seg_row(const QdGeo& g, int r) { const int na = g.sa1 - g.sa0; return r < na ? g.sa0 + r : g.sb0 + (r - na); }
+QD_HD bool qd_owned(const QdGeo& g, int j) { return j >= g.own0 && j < g.own1; }
+
 #define QD_CELL_PROLOGUE(geo)                                         \
   const int b = blockIdx.y;                                           \
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;              \
-  const bool active = idx < (geo).ncell;                              \
-  const int j = active ? idx / (geo).nlon : 0;                        \
-  const int i = active ? idx - j * (geo).nlon : 0;                    \
+  const int t_ = blockIdx.x * blockDim.x + threadIdx.x;               \
+  const bool active = t_ < (geo).ncomp;                               \
+  const int r_ = active ? t_ / (geo).nlon : 0;                        \
+  const int i = active ? t_ - r_ * (geo).nlon : 0;                    \
+  const int j = active ? qd_seg_row((geo), r_) : 0;                   \
+  const int idx = j * (geo).nlon + i;                                 \
   const size_t off = (size_t)b * (geo).ncell;                         \
-  (void)i; (void)j; (void)off;
+  (void)i; (void)j; (void)off; (void)idx;
 
 // Grid-stride form for kernels that end in a grid-wide reduction: the grid is capped at a few blocks per SM
 // (QD_KR in qd_api.cu), so the "last block" ticket -- one atomic round trip on every block's critical path,
@@ -53,8 +63,10 @@ struct QdGaussW { int r; int wrap; double w[2 * QD_GAUSS_MAXR + 1]; };
   const int b = blockIdx.y;                                           \
   const size_t off = (size_t)b * (geo).ncell;                         \
   (void)off;                                                          \
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < (geo).ncell; idx += gridDim.x * blockDim.x)
-#define QD_CELL_JI(geo) const int j = idx / (geo).nlon; const int i = idx - j * (geo).nlon; (void)i; (void)j;
+  for (int t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < (geo).ncomp; t_ += gridDim.x * blockDim.x)
+#define QD_CELL_JI(geo)                                               \
+  const int r_ = t_ / (geo).nlon; const int i = t_ - r_ * (geo).nlon; \
+  const int j = qd_seg_row((geo), r_); const int idx = j * (geo).nlon + i; (void)i; (void)j; (void)idx;
 
 QD_HD const double* qd_row(const QdGeo& g, int id) { return g.rows + (size_t)id * g.nlat; }
 // rows that follow a member's parameters (K4, ocean sponge, polar flag): member b's copy of the table
@@ -271,7 +283,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_divvort(QdGeo g, const double* u
 // One block per (row, member).  twid = cos|sin(2 pi m / n) [2][nlon] from the host.
 __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* f, const double* twid,
                                                               int kcut, double d, double* coef, double* outbuf) {
-  const int b = blockIdx.y, j = blockIdx.x, n = g.nlon;
+  const int b = blockIdx.y, j = qd_seg_row(g, blockIdx.x), n = g.nlon;      // one block per row of the compute region
   double* row = f + (size_t)b * g.ncell + (size_t)j * n;
   const int kN = n / 2;                                   // rfft bins = n/2 + 1
   const int nstop = kN - kcut + 1;
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* 
 __global__ void __launch_bounds__(QD_THREADS) k_wsum(QdGeo g, const double* x, const double* wrow,
                                                     double* partial, unsigned* ticket, double* out, int out_stride) {
   double v = 0.0;
-  QD_CELL_LOOP(g) { QD_CELL_JI(g) v += x[off + idx] * (wrow ? wrow[j] : 1.0); }
+  QD_CELL_LOOP(g) { QD_CELL_JI(g) if (qd_owned(g, j)) v += x[off + idx] * (wrow ? wrow[j] : 1.0); }
   double tot;
   double* part = partial + (size_t)b * gridDim.x;
   if (qd_block_sum<0>(v, &tot)) part[blockIdx.x] = tot;

@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
   QD_CELL_LOOP(g) {
+    QD_CELL_JI(g)
     const size_t c = off + idx;
     const double df = P[QD_P_DIFF_FACTOR];
     const double rate = A.dt / (2.0 * 24 * 3600);

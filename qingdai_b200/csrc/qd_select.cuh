@@ -9,12 +9,7 @@
 // which also yields the upper middle element for even counts (np.median = mean of the two middle values).
 // The whole selection is ONE persistent cooperative launch.
 #pragma once
-#include "qd_ops.cuh"
-
-#define QD_SEL_PASSES 5
-#define QD_SEL_MAXBINS 8192
-#define QD_SEL_THREADS 512
-#define QD_SEL_CAP 2048          // candidates finished by an in-block sort instead of further radix passes
+#include "qd_band.cuh"           // QD_SEL_* sizes, QdBandCtl and the cross-rank pieces used when the field is split over ranks
 
 struct QdSelOut { double* value; double* count; int stride; double empty_value; };
 
@@ -75,7 +70,7 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
 // hist / list counter / mingt are left zeroed (resp. all-ones) for the next launch: no memset nodes.
 __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
                                                                unsigned long long* list, unsigned* lcount,
-                                                               unsigned long long* mingt, int* more_flag, QdSelOut out) {
+                                                               unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) unsigned sh[QD_SEL_MAXBINS];
   __shared__ unsigned long long part[QD_SEL_THREADS];
@@ -83,6 +78,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
   const size_t off = (size_t)b * g.ncell;
   const int stride = gridDim.x * QD_SEL_THREADS;
   const int t0 = blockIdx.x * QD_SEL_THREADS + threadIdx.x;
+  const int c0 = g.own0 * g.nlon, c1 = g.own1 * g.nlon;        // this rank's own rows (all rows without latitude bands)
   const int shifts[QD_SEL_PASSES] = {50, 37, 24, 11, 0};
   const int nbits[QD_SEL_PASSES] = {13, 13, 13, 13, 11};
   unsigned long long prefix = 0, rank = 0, count = 0, inbin = ~0ull;
@@ -96,7 +92,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) sh[k] = 0;
       __syncthreads();
       const int hi = shift + nbits[pass];
-      for (int idx = t0; idx < g.ncell; idx += stride) {
+      for (int idx = c0 + t0; idx < c1; idx += stride) {
         const double v = x[off + idx];
         if (v > 0.0) {
           const unsigned long long key = (unsigned long long)__double_as_longlong(v);
@@ -108,6 +104,10 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       __threadfence();
     }
     grid.sync();
+    if (B.world > 1 && work) {                             // latitude bands (one member): histogram of the whole domain
+      if (blockIdx.x == 0) qd_band_hist_allreduce(B, gh, nb);
+      grid.sync();
+    }
     if (work) {
       unsigned long long below, total;
       const int bin = qd_sel_locate(gh, nb, &rank, pass == 0, sh, part, &below, &inbin, &total);
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       unsigned long long m = ~0ull;
       unsigned long long* lst = list + (size_t)b * QD_SEL_CAP;
       const unsigned long long pk = prefix >> lo_shift;
-      for (int idx = t0; idx < g.ncell; idx += stride) {
+      for (int idx = c0 + t0; idx < c1; idx += stride) {
         const double v = x[off + idx];
         if (v > 0.0) {
           const unsigned long long key = (unsigned long long)__double_as_longlong(v);
@@ -164,11 +164,22 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
   const bool need_above = even && (rank + 1 >= inbin);
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // 4096 x u64 = 32 KB
   unsigned long long Lk = prefix, Uk = prefix;
+  __shared__ unsigned long long s_mingt;
+  if (threadIdx.x == 0) s_mingt = __ldcg(mingt + b);
+  __syncthreads();
+  int mband = 0;
+  if (B.world > 1 && count > 0) {                          // merge every rank's candidates and "next above" key
+    unsigned long long mg;
+    mband = qd_band_list_allgather(B, list + (size_t)b * QD_SEL_CAP, fits ? __ldcg(lcount + b) : 0u, s_mingt, skeys, &mg);
+    if (threadIdx.x == 0) s_mingt = mg;
+    __syncthreads();
+  }
   if (count > 0 && fits) {
     const int m = (int)inbin;
     int n2 = 1; while (n2 < m) n2 <<= 1;
     const unsigned long long* lst = list + (size_t)b * QD_SEL_CAP;
-    for (int k = threadIdx.x; k < n2; k += QD_SEL_THREADS) skeys[k] = k < m ? __ldcg(lst + k) : ~0ull;
+    if (B.world > 1) { for (int k = mband + threadIdx.x; k < n2; k += QD_SEL_THREADS) skeys[k] = ~0ull; }
+    else for (int k = threadIdx.x; k < n2; k += QD_SEL_THREADS) skeys[k] = k < m ? __ldcg(lst + k) : ~0ull;
     __syncthreads();
     for (int size = 2; size <= n2; size <<= 1)
       for (int st = size >> 1; st > 0; st >>= 1) {
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       const double L = __longlong_as_double((long long)Lk);
       if (!even) r = L;
       else {
-        const double U = need_above ? __longlong_as_double((long long)__ldcg(mingt + b)) : __longlong_as_double((long long)Uk);
+        const double U = need_above ? __longlong_as_double((long long)s_mingt) : __longlong_as_double((long long)Uk);
         r = (L + U) / 2.0;                                  // np.mean of the two middle values
       }
     }
@@ -206,10 +217,36 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
 // what the GPU tests exercise, including tests/qdcheck.py:check_median_edge_cases).
 #include <algorithm>
 #include <vector>
-static void qd_select_host(const QdGeo& g, const double* x, QdSelOut out) {
+static void qd_select_host(const QdGeo& g, const double* x, QdSelOut out, const QdBandCtl& B) {
   for (int b = 0; b < g.batch; ++b) {
     std::vector<double> p;
-    for (int k = 0; k < g.ncell; ++k) { const double v = x[(size_t)b * g.ncell + k]; if (v > 0.0) p.push_back(v); }
+    for (int k = g.own0 * g.nlon; k < g.own1 * g.nlon; ++k) { const double v = x[(size_t)b * g.ncell + k]; if (v > 0.0) p.push_back(v); }
+    if (B.world > 1) {             // every rank's positives -> every rank (host check build only: unbounded lists)
+      unsigned long long* mine = qd_bflags(B, B.rank);
+      const unsigned long long epoch = mine[QD_BF_EPOCH_SEL] + 1ull;
+      const size_t cap = (size_t)g.ncell + 1;
+      for (int r = 0; r < B.world; ++r) {
+        double* dst = (double*)(B.peer[r] + B.off_emu) + (size_t)B.rank * cap;
+        dst[0] = (double)p.size();
+        for (size_t k = 0; k < p.size(); ++k) dst[1 + k] = p[k];
+      }
+      qd_fence_sys();
+      mine[QD_BF_EPOCH_SEL] = epoch;
+      for (int r = 0; r < B.world; ++r) qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, epoch);
+      for (int r = 0; r < B.world; ++r) qd_band_wait(B, mine + QD_BF_SEL + r, epoch);
+      p.clear();
+      for (int r = 0; r < B.world; ++r) {
+        const double* src = (const double*)(B.peer[B.rank] + B.off_emu) + (size_t)r * cap;
+        const size_t n = (size_t)src[0];
+        p.insert(p.end(), src + 1, src + 1 + n);
+      }
+      // a rank may only reuse the boxes after every rank has read them: second round trip
+      const unsigned long long e2 = epoch + 1ull;
+      qd_fence_sys();
+      mine[QD_BF_EPOCH_SEL] = e2;
+      for (int r = 0; r < B.world; ++r) qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, e2);
+      for (int r = 0; r < B.world; ++r) qd_band_wait(B, mine + QD_BF_SEL + r, e2);
+    }
     double r = out.empty_value;
     if (!p.empty()) {
       std::sort(p.begin(), p.end());

@@ -187,7 +187,7 @@ def engine_for_grid(grid, **kw):
 
 class Engine:
     def __init__(self, nlat, nlon, batch=1, params: Optional[Sequence[QDParams] | QDParams] = None,
-                 dt=300.0, device=None, lib: Optional[Library] = None):
+                 dt=300.0, device=None, lib: Optional[Library] = None, band=None):
         self.lib = lib or default_library()
         self.nlat, self.nlon, self.batch = int(nlat), int(nlon), int(batch)
         self.shape = (self.nlat, self.nlon)
@@ -227,12 +227,54 @@ class Engine:
                 self._chk(self.lib.qd_set_rows_member(self.ctx, b, _ptr(rb)), "qd_set_rows_member")
         if self.device.type == "cuda":
             self._chk(self.lib.qd_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "qd_set_stream")
+        self.band = None
+        if band is not None and int(band[1]) > 1:
+            self._connect_band(*band)
         r1, w1 = gaussian_taps(1.0)
         self._chk(self.lib.qd_set_gauss(self.ctx, 0, r1, 0, _ptr(w1)), "qd_set_gauss")
         sig = self.params[0].cloud_smooth_sigma
         rc_, wc = gaussian_taps(sig if sig > 0 else 0.2)
         self._chk(self.lib.qd_set_gauss(self.ctx, 1, rc_, 1, _ptr(wc)), "qd_set_gauss")
         self._finalizer = weakref.finalize(self, self.lib.qd_destroy, self.ctx)
+
+    # ---------------------------------------------------------------- latitude bands (SURVEY 8e, configs[4])
+    def _connect_band(self, rank, world, halo_rows=16):
+        """One domain over `world` GPUs: rank r computes a block of latitude rows.  The library allocates its
+        exchange buffer; the 64-byte IPC handles are swapped here through torch.distributed (setup only --
+        the data path is peer-to-peer stores issued by the step's own kernels)."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("latitude bands need an initialised torch.distributed process group")
+        rank, world = int(rank), int(world)
+        self._chk(self.lib.qd_band_init(self.ctx, rank, world, int(halo_rows)), "qd_band_init")
+        mine = np.zeros(64, dtype=np.uint8)
+        self._chk(self.lib.qd_band_export(self.ctx, _ptr(mine)), "qd_band_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, mine.tobytes())
+        blob = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        self._chk(self.lib.qd_band_connect(self.ctx, _ptr(blob)), "qd_band_connect")
+        dist.barrier()
+        self.band = (rank, world)
+
+    def band_info(self):
+        """(own0, own1, halo_rows, error_word) of this rank; the whole grid without bands."""
+        a, b, h, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self._chk(self.lib.qd_band_info(self.ctx, C.byref(a), C.byref(b), C.byref(h), C.byref(e)), "qd_band_info")
+        return a.value, b.value, h.value, e.value
+
+    def gather_rows(self, name, member=0):
+        """Full field assembled from every rank's own rows (diagnostics / tests; off the hot path)."""
+        x = self.get(name, member)
+        if self.band is None:
+            return x
+        import torch.distributed as dist
+        r0, r1, _, _ = self.band_info()
+        parts = [None] * self.band[1]
+        dist.all_gather_object(parts, (r0, r1, x[r0:r1].copy()))
+        out = np.empty_like(x)
+        for a, b, rows in parts:
+            out[a:b] = rows
+        return out
 
     # launch structure (which kernels run, cadences) is shared by the members of one batch; every
     # continuous parameter (P vector, K4 / sponge / polar rows) is per member

@@ -31,10 +31,10 @@ def q_sat_host(T, p0):
 class Simulation:
     def __init__(self, nlat, nlon, topo: dict | Sequence[dict], params: Optional[QDParams | Sequence[QDParams]] = None,
                  dt=300, batch=1, with_ocean=True, with_hydrology=True, with_eco=False, loop_with_albedo=False,
-                 device=None, lib=None, t0=0.0, eco_env=None):
+                 device=None, lib=None, t0=0.0, eco_env=None, band=None):
         self.grid = SphericalGrid(nlat, nlon)
         plist = list(params) if isinstance(params, (list, tuple)) else [params or QDParams.from_env()] * batch
-        self.engine = Engine(nlat, nlon, batch=batch, params=plist, dt=dt, device=device, lib=lib)
+        self.engine = Engine(nlat, nlon, batch=batch, params=plist, dt=dt, device=device, lib=lib, band=band)
         self.dt = dt
         self.t = float(t0)
         self.step_index = 0
