@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=0, help="oracle steps for cpu_baseline (0 = auto, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--halo", type=int, default=16, help="latitude bands: halo rows per exchange")
     ap.add_argument("--replicas", action="store_true", help="hires at N>1: independent replicas instead of latitude bands")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -181,7 +182,8 @@ def main():
         scaling, seeds = "strong", [42 + rank * members + m for m in range(members)]
     elif args.workload == "hires" and world > 1 and not args.replicas:
         # configs[4]: ONE 1441x2880 domain split into latitude bands over the GPUs (halo rows over NVLink)
-        members, scaling, seeds, band = 1, "strong", [42], (rank, world, 16)
+        members, scaling, seeds, band = 1, "strong", [42], (rank, world, args.halo)
+        spec["label"] = "configs[4] 1441x2880 full physics, dt=37 s, ONE domain in latitude bands over the GPUs"
     else:
         members = spec["members_per_gpu"]
         scaling, seeds = "weak", [42 + rank * members + m for m in range(members)]
@@ -244,7 +246,7 @@ def main():
 
     # -------- per-kernel device time (CUDA events around every launch) -> roofline of the dominant kernel
     roof = None
-    if not args.no_profile and rank == 0 and not band:
+    if not args.no_profile and (rank == 0 or band):       # band mode: every rank must run the same (stream-mode) steps
         import ctypes
         eng.lib.qd_profile(eng.ctx, 1)
         nprof = min(args.steps, 20)
@@ -253,6 +255,7 @@ def main():
         buf = ctypes.create_string_buffer(1 << 16)
         eng.lib.qd_profile_report(eng.ctx, buf, len(buf))
         eng.lib.qd_profile(eng.ctx, 0)
+    if roof is None and rank == 0 and not args.no_profile:
         rows = [ln.split() for ln in buf.value.decode().strip().splitlines()]
         rows = [(r[0], int(r[1]), float(r[2])) for r in rows if len(r) == 3]
         tot = sum(r[2] for r in rows) or 1.0
@@ -277,7 +280,7 @@ def main():
                 "share_of_step": ms / tot,
                 "whole_step": {"alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "note": "233 B/cell-step (SURVEY 8d) over the whole fused step"},
-                "top_kernels": [{"kernel": r[0], "launches_per_step": r[1] / nprof, "us_per_launch": r[2] / r[1] * 1e3, "share": r[2] / tot} for r in rows[:8]]}
+                "top_kernels": [{"kernel": r[0], "launches_per_step": r[1] / nprof, "us_per_launch": r[2] / r[1] * 1e3, "share": r[2] / tot} for r in rows[:(40 if band else 8)]]}
 
     # -------- CPU baseline (oracle port, rank 0, N=1 only)
     cpu = None
@@ -294,7 +297,7 @@ def main():
                 "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "cell_steps_per_s": total_members * ncell * steps_per_s,
                 "config": {"workload": spec["label"], "grid": [nlat, nlon], "dt_s": dt, "members_per_gpu": members,
-                           "members_total": total_members, "parallelism": (f"latitude bands x{world}, halo 16 rows over NVLink peer stores" if band else f"independent members x{world}") if world > 1 else "single GPU",
+                           "members_total": total_members, "parallelism": (f"latitude bands x{world}, halo {args.halo} rows over NVLink peer stores" if band else f"independent members x{world}") if world > 1 else "single GPU",
                            "l2": f"256 MiB L2 flush before every timed step (state ~{state_bytes / 1e6:.0f} MB per GPU)",
                            "loop_with_albedo": True},
                 "clocks": clocks,

@@ -462,11 +462,12 @@ static int band_fid(qd_ctx* c, const void* p) {             // field / mask slot
   return -1;
 }
 static int band_exchange(qd_ctx* c, const int* ids, int n) {
+  if (getenv("QD_BAND_TRACE") && c->band.rank == 0) { fprintf(stderr, "[band] exchange"); for (int k = 0; k < n; ++k) fprintf(stderr, " %d", ids[k]); fprintf(stderr, "\n"); }
   for (int k0 = 0; k0 < n; k0 += QD_BAND_MAXX) {
     QdBandList L; memset(&L, 0, sizeof(L));
     L.n = std::min(QD_BAND_MAXX, n - k0);
     for (int k = 0; k < L.n; ++k) { L.f[k] = F(c, ids[k0 + k]); c->band_valid[ids[k0 + k]] = c->band.H; }
-    const int gx = std::max(1, std::min(32, (c->band.H * c->nlon + QD_THREADS - 1) / QD_THREADS));
+    const int gx = std::max(1, std::min(96, (c->band.H * c->nlon / 2 + QD_THREADS - 1) / QD_THREADS));   // one double2 per thread
     QD_KG(c, k_band_push, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
     QD_KG(c, k_band_unpack, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
   }

@@ -31,7 +31,7 @@
 #define QD_BAND_MAXW 8            // ranks (GPUs of one node)
 #define QD_BAND_MAXX 10           // fields per halo exchange
 #define QD_BAND_MAXR 8            // scalars per all-reduce
-#define QD_BAND_SPIN (1u << 27)   // bounded spin (~ seconds) before the error word is raised
+#define QD_BAND_SPIN (1u << 23)   // bounded spin (~ seconds) before the error word is raised
 
 // flag words inside a rank's buffer (unsigned long long each)
 enum { QD_BF_HALO_S = 0, QD_BF_HALO_N = 1, QD_BF_RED = 8, QD_BF_SEL = 16, QD_BF_ERR = 24, QD_BF_EPOCH_HALO = 32,
@@ -73,6 +73,7 @@ __device__ __forceinline__ void qd_st_sys(unsigned long long* p, unsigned long l
 #endif
 // spin until *flag >= epoch; returns false (and raises the error word) when the bound is hit
 QD_D bool qd_band_wait(const QdBandCtl& B, const unsigned long long* flag, unsigned long long epoch) {
+  if (qd_bflags(B, B.rank)[QD_BF_ERR] != 0ull) return false;             // already failed: do not stack timeouts
   for (unsigned n = 0; n < QD_BAND_SPIN; ++n) {
     if (qd_ld_sys(flag) >= epoch) return true;
 #if QD_EMU
@@ -98,8 +99,16 @@ __global__ void __launch_bounds__(QD_THREADS) k_band_push(QdBandCtl B, QdBandLis
   const double* src = L.f[k] + (size_t)row0 * B.nlon;
   double* dst = qd_binbox(B, nbr, parity, dir == 0 ? 1 : 0, k);
   const int n = B.H * B.nlon;
+#if !QD_EMU
+  if ((((size_t)src | (size_t)dst) & 15) == 0 && (n & 1) == 0) {        // 16-byte peer stores
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += gridDim.x * blockDim.x) d2[e] = s2[e];
+  } else
+#endif
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e];
-  qd_fence_sys();                                                      // my peer stores before my ticket
+  // qd_block_is_last: barrier, then ONE thread fences (system scope below covers the block's peer stores, which
+  // it observed through the barrier) and takes the ticket
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
   if (qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks)) {
     QD_BLOCK_LAST_ONE {
@@ -125,19 +134,22 @@ __global__ void __launch_bounds__(QD_THREADS) k_band_unpack(QdBandCtl B, QdBandL
 #endif
   const int parity = (int)(epoch & 1ull);
   const double* src = qd_binbox(B, B.rank, parity, dir, k);
-  const int first = dir == 0 ? own0 - B.H : own1;
+  int first = dir == 0 ? own0 - B.H : own1;                 // H <= rows of any rank: the block never straddles the wrap
+  if (first < 0) first += B.nlat;
+  if (first >= B.nlat) first -= B.nlat;
+  double* dst = L.f[k] + (size_t)first * B.nlon;
   const int n = B.H * B.nlon;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int r = e / B.nlon, i = e - r * B.nlon;
-    int j = first + r;
-    if (j < 0) j += B.nlat;
-    if (j >= B.nlat) j -= B.nlat;
-#if QD_EMU
-    L.f[k][(size_t)j * B.nlon + i] = src[e];
-#else
-    L.f[k][(size_t)j * B.nlon + i] = __ldcg(src + e);
-#endif
+#if !QD_EMU
+  if ((((size_t)src | (size_t)dst) & 15) == 0 && (n & 1) == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += gridDim.x * blockDim.x) d2[e] = __ldcg(s2 + e);
+    return;
   }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = __ldcg(src + e);
+#else
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e];
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- scalars
@@ -184,19 +196,23 @@ __device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsig
   unsigned long long* mine = qd_bflags(B, B.rank);
   const unsigned long long epoch = mine[QD_BF_EPOCH_SEL] + 1ull;
   const int parity = (int)(epoch & 1ull);
-  for (int r = 0; r < B.world; ++r) {
-    unsigned* dst = qd_bhist(B, r, parity, B.rank);
-    for (int k = threadIdx.x; k < nb; k += blockDim.x) dst[k] = __ldcg(gh + k);
+  for (int r = 0; r < B.world; ++r) {                                   // nb is a multiple of 4, boxes are 256-byte aligned
+    uint4* dst = reinterpret_cast<uint4*>(qd_bhist(B, r, parity, B.rank));
+    const uint4* src = reinterpret_cast<const uint4*>(gh);
+    for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) dst[k] = __ldcg(src + k);
   }
   qd_fence_sys();
   __syncthreads();
   if (threadIdx.x == 0) mine[QD_BF_EPOCH_SEL] = epoch;
   if (threadIdx.x < B.world) { qd_st_sys(qd_bflags(B, threadIdx.x) + QD_BF_SEL + B.rank, epoch); qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch); }
   __syncthreads();
-  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-    unsigned s = 0;
-    for (int r = 0; r < B.world; ++r) s += __ldcg(qd_bhist(B, B.rank, parity, r) + k);
-    gh[k] = s;
+  for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) {
+    uint4 s = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = 0; r < B.world; ++r) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(qd_bhist(B, B.rank, parity, r)) + k);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<uint4*>(gh)[k] = s;
   }
   __threadfence();
 }

@@ -183,7 +183,7 @@ QD_D bool qd_block_is_last(unsigned* ticket, unsigned nblocks) {
   __shared__ int last;
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
-    __threadfence();
+    __threadfence_system();            // system scope: the latitude-band kernels publish stores to peer GPUs this way
     unsigned t = atomicAdd(ticket, 1u);
     last = (t == nblocks - 1);
     if (last) *ticket = 0;
