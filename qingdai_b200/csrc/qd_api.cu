@@ -305,6 +305,8 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
   g.own0 = 0; g.own1 = nlat; g.sa0 = 0; g.sa1 = nlat; g.sb0 = 0; g.sb1 = 0; g.ncomp = c->ncell;
+  g.div_nlon = (1ull << 40) / (unsigned long long)nlon + 1ull;
+  if ((unsigned long long)c->ncell * (unsigned long long)nlon >= (1ull << 40)) { delete c; return QD_E_INVALID; }
   g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
   for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { delete c; return QD_E_CUDA; }
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }

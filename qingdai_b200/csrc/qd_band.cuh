@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_band_push(QdBandCtl B, QdBandLis
   // qd_block_is_last: barrier, then ONE thread fences (system scope below covers the block's peer stores, which
   // it observed through the barrier) and takes the ticket
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
-  if (qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks)) {
+  if (qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks, true)) {
     QD_BLOCK_LAST_ONE {
       qd_fence_sys();
       mine[QD_BF_EPOCH_HALO] = epoch;

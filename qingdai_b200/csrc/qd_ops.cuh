@@ -28,7 +28,9 @@ struct QdGeo {
   // rows of up to two segments [sa0,sa1) u [sb0,sb1) (its own rows [own0,own1) widened by the halo the
   // inputs allow; the second segment is the part that wraps over a pole).  One rank: sa = own = [0, nlat).
   int own0, own1, sa0, sa1, sb0, sb1, ncomp;
+  unsigned long long div_nlon;   // floor(2^40 / nlon) + 1: t / nlon == (t * div_nlon) >> 40 for t * nlon < 2^40
 };
+QD_HD int qd_div_nlon(const QdGeo& g, int t) { return (int)(((unsigned long long)(unsigned)t * g.div_nlon) >> 40); }
 
 struct QdFields {          // up to QD_MAX_FIELDS field pointers passed by value
   int n;
@@ -48,7 +50,7 @@ QD_HD bool qd_owned(const QdGeo& g, int j) { return j >= g.own0 && j < g.own1; }
   const int b = blockIdx.y;                                           \
   const int t_ = blockIdx.x * blockDim.x + threadIdx.x;               \
   const bool active = t_ < (geo).ncomp;                               \
-  const int r_ = active ? t_ / (geo).nlon : 0;                        \
+  const int r_ = active ? qd_div_nlon((geo), t_) : 0;                 \
   const int i = active ? t_ - r_ * (geo).nlon : 0;                    \
   const int j = active ? qd_seg_row((geo), r_) : 0;                   \
   const int idx = j * (geo).nlon + i;                                 \
@@ -65,7 +67,7 @@ QD_HD bool qd_owned(const QdGeo& g, int j) { return j >= g.own0 && j < g.own1; }
   (void)off;                                                          \
   for (int t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < (geo).ncomp; t_ += gridDim.x * blockDim.x)
 #define QD_CELL_JI(geo)                                               \
-  const int r_ = t_ / (geo).nlon; const int i = t_ - r_ * (geo).nlon; \
+  const int r_ = qd_div_nlon((geo), t_); const int i = t_ - r_ * (geo).nlon; \
   const int j = qd_seg_row((geo), r_); const int idx = j * (geo).nlon + i; (void)i; (void)j; (void)idx;
 
 QD_HD const double* qd_row(const QdGeo& g, int id) { return g.rows + (size_t)id * g.nlat; }
@@ -87,6 +89,17 @@ QD_HD double qd_lap_cell(const Acc& F, int j, int i, const QdGeo& g, const doubl
   const int nlat = g.nlat, nlon = g.nlon;
   const double* ic = c + nlat;
   const double* ic2 = c + 2 * nlat;
+  if (j >= 2 && j <= nlat - 3) {
+    // every np.gradient involved is centred: the same operations as the general form below, without its
+    // per-row case analysis (bit-identical)
+    const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+    const double f0 = F(j, i);
+    const double gp = (F(j + 2, i) - f0) * g.inv_2dlat, gm = (f0 - F(j - 2, i)) * g.inv_2dlat;
+    const double gphi = (c[j + 1] * gp - c[j - 1] * gm) * g.inv_2dlat;
+    const double term_phi = ic[j] * gphi;
+    const double d2 = ((F(j, ip) - 2.0 * f0) + F(j, im)) * g.inv_dlon_sq;
+    return (term_phi + d2 * ic2[j]) * g.inv_a_sq;
+  }
   const int jm = j > 0 ? j - 1 : 0, jp = j < nlat - 1 ? j + 1 : nlat - 1;
   // G(jj): np.gradient(F, dphi, axis=0) at row jj (edge_order=1)
   auto G = [&](int jj) -> double {
@@ -223,6 +236,10 @@ QD_HD int qd_extend(int k, int n, int wrap) {
 template <class Load>
 QD_HD double qd_gauss_tap(const Load& E, int c, int n, const QdGaussW& w) {
   double out = E(c) * w.w[w.r];
+  if (c - w.r >= 0 && c + w.r < n) {           // no boundary extension: skip the modulo arithmetic (same sums, same order)
+    for (int jj = -w.r; jj < 0; ++jj) out = out + (E(c + jj) + E(c - jj)) * w.w[w.r + jj];
+    return out;
+  }
   for (int jj = -w.r; jj < 0; ++jj)
     out = out + (E(qd_extend(c + jj, n, w.wrap)) + E(qd_extend(c - jj, n, w.wrap))) * w.w[w.r + jj];
   return out;

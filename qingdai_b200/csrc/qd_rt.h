@@ -87,12 +87,20 @@ void qd_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body);
 #define QD_BLOCK_LAST_FOR(k, n) for (int k = threadIdx.x; k < (int)(n); k += blockDim.x)
 #endif
 
-// np.nan_to_num for one value (NaN -> 0, +-inf -> +-DBL_MAX).
+// np.nan_to_num for one value (NaN -> 0, +-inf -> +-DBL_MAX).  Device form: selects only, no branches (the
+// branchy form cost 6-10 issue slots and a reconvergence point per value in every stencil load).
 QD_HD double qd_nan_to_num(double x) {
+#if !QD_EMU && defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(x);
+  const double big = __hiloint2double((hi & 0x80000000) | 0x7fefffff, 0xffffffff);     // copysign(DBL_MAX, x)
+  const double alt = (x != x) ? 0.0 : big;
+  return (fabs(x) <= DBL_MAX) ? x : alt;
+#else
   if (x != x) return 0.0;
   if (x > DBL_MAX) return DBL_MAX;
   if (x < -DBL_MAX) return -DBL_MAX;
   return x;
+#endif
 }
 QD_HD double qd_clip(double x, double lo, double hi) {   // np.clip = minimum(maximum(x, lo), hi), NaN propagates
   if (x != x) return x;
@@ -170,7 +178,7 @@ QD_D bool qd_block_max(double v, double* total) {   // NaN-ignoring max of non-n
 // writes / atomics.  GPU: returns true in all threads of the last of `nblocks` blocks to arrive
 // (so they can run a cooperative epilogue); host build: true only in the last thread of that
 // block, which then runs the QD_BLOCK_LAST_* loops serially.  Resets the ticket for the next use.
-QD_D bool qd_block_is_last(unsigned* ticket, unsigned nblocks) {
+QD_D bool qd_block_is_last(unsigned* ticket, unsigned nblocks, bool system_scope = false) {
 #if QD_EMU
   static thread_local unsigned cnt = 0;
   if (++cnt == blockDim.x * blockDim.y) {
@@ -183,7 +191,8 @@ QD_D bool qd_block_is_last(unsigned* ticket, unsigned nblocks) {
   __shared__ int last;
   __syncthreads();
   if (threadIdx.x == 0 && threadIdx.y == 0) {
-    __threadfence_system();            // system scope: the latitude-band kernels publish stores to peer GPUs this way
+    if (system_scope) __threadfence_system();     // the latitude-band kernels publish stores to peer GPUs this way
+    else __threadfence();
     unsigned t = atomicAdd(ticket, 1u);
     last = (t == nblocks - 1);
     if (last) *ticket = 0;
