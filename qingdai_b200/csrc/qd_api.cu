@@ -469,9 +469,14 @@ static int band_exchange(qd_ctx* c, const int* ids, int n) {
     QdBandList L; memset(&L, 0, sizeof(L));
     L.n = std::min(QD_BAND_MAXX, n - k0);
     for (int k = 0; k < L.n; ++k) { L.f[k] = F(c, ids[k0 + k]); c->band_valid[ids[k0 + k]] = c->band.H; }
-    const int gx = std::max(1, std::min(96, (c->band.H * c->nlon / 2 + QD_THREADS - 1) / QD_THREADS));   // one double2 per thread
-    QD_KG(c, k_band_push, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
-    QD_KG(c, k_band_unpack, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1);
+    // every block waits on a peer: the whole grid must be resident (gx * fields * 2 <= 480 blocks of 256 threads)
+    const int gx = std::max(1, std::min(QD_BAND_GX, (c->band.H * c->nlon / 2 + 4 * QD_THREADS - 1) / (4 * QD_THREADS)));
+#ifdef QD_HOST_EMU
+    QD_KG(c, k_band_exchange, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1, 1);
+    QD_KG(c, k_band_exchange, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1, 2);
+#else
+    QD_KG(c, k_band_exchange, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1, 3);
+#endif
   }
   return QD_OK;
 }
@@ -552,6 +557,7 @@ extern "C" int qd_band_init(qd_ctx* c, int rank, int world, int halo_rows) {
   size_t off = QD_BF_WORDS * 8;
   auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
   B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * 8);
+  B.off_sflag = take((size_t)2 * QD_BAND_MAXX * QD_BAND_GX * 8);
   B.off_red = take((size_t)2 * QD_BAND_MAXW * QD_BAND_MAXR * 8);
   B.off_hist = take((size_t)2 * QD_BAND_MAXW * QD_SEL_MAXBINS * 4);
   B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * 8);

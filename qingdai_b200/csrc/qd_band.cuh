@@ -40,7 +40,7 @@ enum { QD_BF_HALO_S = 0, QD_BF_HALO_N = 1, QD_BF_RED = 8, QD_BF_SEL = 16, QD_BF_
 struct QdBandCtl {
   int rank, world, H, nlon, nlat;
   char* peer[QD_BAND_MAXW];                 // base of every rank's buffer as mapped here (peer[rank] = own)
-  unsigned long long off_inbox, off_red, off_hist, off_list, off_emu;   // byte offsets, identical on every rank
+  unsigned long long off_inbox, off_red, off_hist, off_list, off_emu, off_sflag;   // byte offsets, identical on every rank
 };
 QD_HD unsigned long long* qd_bflags(const QdBandCtl& B, int r) { return (unsigned long long*)B.peer[r]; }
 QD_HD double* qd_binbox(const QdBandCtl& B, int r, int parity, int dir, int slot) {
@@ -87,69 +87,69 @@ QD_D bool qd_band_wait(const QdBandCtl& B, const unsigned long long* flag, unsig
 // ---------------------------------------------------------------------------------------------- halo rows
 struct QdBandList { int n; double* f[QD_BAND_MAXX]; };     // member-0 base pointers of the fields to exchange
 
-// grid (blocks, n fields, 2 directions).  dir 0: my lowest H rows go to my SOUTH neighbour (its "from north"
-// inbox), dir 1: my top H rows go to my NORTH neighbour (its "from south" inbox).
-__global__ void __launch_bounds__(QD_THREADS) k_band_push(QdBandCtl B, QdBandList L, int own0, int own1) {
-  const int k = blockIdx.y, dir = blockIdx.z;
-  unsigned long long* mine = qd_bflags(B, B.rank);
-  const unsigned long long epoch = mine[QD_BF_EPOCH_HALO] + 1ull;      // every block reads it before the last block bumps it
-  const int parity = (int)(epoch & 1ull);
-  const int nbr = dir == 0 ? (B.rank + B.world - 1) % B.world : (B.rank + 1) % B.world;
-  const int row0 = dir == 0 ? own0 : own1 - B.H;
-  const double* src = L.f[k] + (size_t)row0 * B.nlon;
-  double* dst = qd_binbox(B, nbr, parity, dir == 0 ? 1 : 0, k);
-  const int n = B.H * B.nlon;
-#if !QD_EMU
-  if ((((size_t)src | (size_t)dst) & 15) == 0 && (n & 1) == 0) {        // 16-byte peer stores
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += gridDim.x * blockDim.x) d2[e] = s2[e];
-  } else
-#endif
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e];
-  // qd_block_is_last: barrier, then ONE thread fences (system scope below covers the block's peer stores, which
-  // it observed through the barrier) and takes the ticket
-  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
-  if (qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks, true)) {
-    QD_BLOCK_LAST_ONE {
-      qd_fence_sys();
-      mine[QD_BF_EPOCH_HALO] = epoch;
-      const int south = (B.rank + B.world - 1) % B.world, north = (B.rank + 1) % B.world;
-      qd_st_sys(qd_bflags(B, south) + QD_BF_HALO_N, epoch);            // I am my south neighbour's north side
-      qd_st_sys(qd_bflags(B, north) + QD_BF_HALO_S, epoch);
-    }
-  }
+// ONE kernel per exchange, grid (gx slices, n fields, 2 directions), every block resident (gx * n * 2 <= one wave).
+// Block (x, k, dir) stores slice x of field k's boundary rows into the neighbour on side `dir` (dir 0: my lowest H
+// rows to my SOUTH neighbour, dir 1: my top H rows to my NORTH neighbour), publishes the slice's own epoch flag
+// there, then waits for the matching slice from the opposite neighbour and copies it next to my own rows (mod
+// n_lat: the ring is closed over the poles).  No grid-wide dependency: a slice is unpacked as soon as it arrived.
+#define QD_BAND_GX 24
+QD_HD unsigned long long* qd_bslice_flag(const QdBandCtl& B, int r, int dir, int k, int x) {
+  return (unsigned long long*)(B.peer[r] + B.off_sflag) + ((size_t)dir * QD_BAND_MAXX + k) * QD_BAND_GX + x;
 }
-// dir 0: rows arriving from the south neighbour land below my own rows, dir 1: above them (mod n_lat: the
-// ring is closed over the poles).
-__global__ void __launch_bounds__(QD_THREADS) k_band_unpack(QdBandCtl B, QdBandList L, int own0, int own1) {
-  const int k = blockIdx.y, dir = blockIdx.z;
+// phase: 1 = push, 2 = receive, 3 = both (GPU; the sequential host check build launches 1 then 2: its blocks do not overlap)
+__global__ void __launch_bounds__(QD_THREADS) k_band_exchange(QdBandCtl B, QdBandList L, int own0, int own1, int phase) {
+  const int x = blockIdx.x, k = blockIdx.y, dir = blockIdx.z;
   unsigned long long* mine = qd_bflags(B, B.rank);
-  const unsigned long long epoch = mine[QD_BF_EPOCH_HALO];            // bumped by my own push, earlier on this stream
-#if QD_EMU
-  if (threadIdx.x == 0) qd_band_wait(B, mine + (dir == 0 ? QD_BF_HALO_S : QD_BF_HALO_N), epoch);
-#else
-  if (threadIdx.x == 0) qd_band_wait(B, mine + (dir == 0 ? QD_BF_HALO_S : QD_BF_HALO_N), epoch);
-  __syncthreads();
-#endif
+  const unsigned long long epoch = mine[QD_BF_EPOCH_HALO] + 1ull;      // bumped by the last block to FINISH: all are resident, all read it first
   const int parity = (int)(epoch & 1ull);
-  const double* src = qd_binbox(B, B.rank, parity, dir, k);
-  int first = dir == 0 ? own0 - B.H : own1;                 // H <= rows of any rank: the block never straddles the wrap
-  if (first < 0) first += B.nlat;
-  if (first >= B.nlat) first -= B.nlat;
-  double* dst = L.f[k] + (size_t)first * B.nlon;
+  const int south = (B.rank + B.world - 1) % B.world, north = (B.rank + 1) % B.world;
   const int n = B.H * B.nlon;
+  const int per = ((n + gridDim.x - 1) / gridDim.x + 1) & ~1;           // slice length, even (16-byte stores)
+  const int e0 = x * per, e1 = (e0 + per < n) ? e0 + per : n;
+  // ---- push: (dir 0) rows [own0, own0+H) -> south neighbour's "from north" inbox; (dir 1) rows [own1-H, own1) -> north's "from south"
+  if (phase & 1) {
+    const int nbr = dir == 0 ? south : north, rdir = dir == 0 ? 1 : 0;
+    const double* src = L.f[k] + (size_t)(dir == 0 ? own0 : own1 - B.H) * B.nlon;
+    double* dst = qd_binbox(B, nbr, parity, rdir, k);
 #if !QD_EMU
-  if ((((size_t)src | (size_t)dst) & 15) == 0 && (n & 1) == 0) {
-    const double2* s2 = reinterpret_cast<const double2*>(src);
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n / 2; e += gridDim.x * blockDim.x) d2[e] = __ldcg(s2 + e);
-    return;
-  }
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = __ldcg(src + e);
-#else
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) dst[e] = src[e];
+    if ((((size_t)src | (size_t)dst) & 15) == 0 && (e1 & 1) == 0) {
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      double2* d2 = reinterpret_cast<double2*>(dst);
+      for (int e = e0 / 2 + threadIdx.x; e < e1 / 2; e += blockDim.x) d2[e] = s2[e];
+    } else
 #endif
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = src[e];
+#if !QD_EMU
+    __syncthreads();
+#endif
+    QD_BLOCK_LAST_ONE { qd_fence_sys(); qd_st_sys(qd_bslice_flag(B, nbr, rdir, k, x), epoch); }
+  }
+  // ---- receive: slice x of field k arriving on side `dir` (dir 0: from the south neighbour -> rows below mine)
+  if (phase & 2) {
+#if QD_EMU
+    if (threadIdx.x == 0) qd_band_wait(B, qd_bslice_flag(B, B.rank, dir, k, x), epoch);
+#else
+    if (threadIdx.x == 0) qd_band_wait(B, qd_bslice_flag(B, B.rank, dir, k, x), epoch);
+    __syncthreads();
+#endif
+    int first = dir == 0 ? own0 - B.H : own1;               // H <= rows of any rank: the block never straddles the wrap
+    if (first < 0) first += B.nlat;
+    if (first >= B.nlat) first -= B.nlat;
+    const double* src = qd_binbox(B, B.rank, parity, dir, k);
+    double* dst = L.f[k] + (size_t)first * B.nlon;
+#if !QD_EMU
+    if ((((size_t)src | (size_t)dst) & 15) == 0 && (e1 & 1) == 0) {
+      const double2* s2 = reinterpret_cast<const double2*>(src);
+      double2* d2 = reinterpret_cast<double2*>(dst);
+      for (int e = e0 / 2 + threadIdx.x; e < e1 / 2; e += blockDim.x) d2[e] = __ldcg(s2 + e);
+    } else
+      for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = __ldcg(src + e);
+#else
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = src[e];
+#endif
+  }
+  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+  if ((phase & 2) && qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks)) { QD_BLOCK_LAST_ONE { mine[QD_BF_EPOCH_HALO] = epoch; } }
 }
 
 // ---------------------------------------------------------------------------------------------- scalars
@@ -191,20 +191,24 @@ __global__ void k_band_allreduce(QdBandCtl B, QdBandRed R, double* scal) {
 // ---------------------------------------------------------------------------------------------- selection
 // Block-cooperative pieces used by block 0 of k_select_coop when the field is split over ranks.
 #if !QD_EMU
-// gh[0..nb) <- sum over ranks of their gh (element-wise, exact integers)
-__device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsigned* gh, int nb) {
+// Collectives of the selection kernel.  `epoch` = (value of the rank's selection epoch word at kernel start) +
+// (index of the collective inside this launch); every block computes it the same way, block 0 stores the last one
+// back when the kernel ends.  Blocks 0..world-1 each serve one peer, block 0 combines.
+//
+// gh[0..nb) <- sum over ranks of their gh (element-wise, exact integers).  Call after a grid.sync (gh complete);
+// the caller grid.syncs afterwards.
+__device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsigned* gh, int nb, unsigned long long epoch) {
   unsigned long long* mine = qd_bflags(B, B.rank);
-  const unsigned long long epoch = mine[QD_BF_EPOCH_SEL] + 1ull;
   const int parity = (int)(epoch & 1ull);
-  for (int r = 0; r < B.world; ++r) {                                   // nb is a multiple of 4, boxes are 256-byte aligned
+  for (int r = blockIdx.x; r < B.world; r += gridDim.x) {               // nb is a multiple of 4, boxes are 256-byte aligned
     uint4* dst = reinterpret_cast<uint4*>(qd_bhist(B, r, parity, B.rank));
     const uint4* src = reinterpret_cast<const uint4*>(gh);
     for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) dst[k] = __ldcg(src + k);
+    __syncthreads();
+    if (threadIdx.x == 0) { qd_fence_sys(); qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, epoch); }
   }
-  qd_fence_sys();
-  __syncthreads();
-  if (threadIdx.x == 0) mine[QD_BF_EPOCH_SEL] = epoch;
-  if (threadIdx.x < B.world) { qd_st_sys(qd_bflags(B, threadIdx.x) + QD_BF_SEL + B.rank, epoch); qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch); }
+  if (blockIdx.x != 0) return;
+  if (threadIdx.x < B.world) qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch);
   __syncthreads();
   for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) {
     uint4 s = make_uint4(0u, 0u, 0u, 0u);
@@ -216,23 +220,23 @@ __device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsig
   }
   __threadfence();
 }
-// every rank's candidate list + "smallest key above the bucket" -> all ranks; returns the merged count in
-// skeys[0..m) (shared memory, unsorted) and the global mingt
+// every rank's candidate list + "smallest key above the bucket" -> all ranks.  Blocks 0..world-1 push (call from
+// every block after the grid.sync that completes the local list); block 0 returns the merged count with the keys in
+// skeys[0..m) (shared memory, unsorted) and the global mingt; other blocks return -1.
 __device__ __forceinline__ int qd_band_list_allgather(const QdBandCtl& B, const unsigned long long* lst, unsigned cnt, unsigned long long mingt_local,
-                                                      unsigned long long* skeys, unsigned long long* mingt_out) {
+                                                      unsigned long long* skeys, unsigned long long* mingt_out, unsigned long long epoch) {
   unsigned long long* mine = qd_bflags(B, B.rank);
-  const unsigned long long epoch = mine[QD_BF_EPOCH_SEL] + 1ull;
   const int parity = (int)(epoch & 1ull);
   if (cnt > QD_SEL_CAP) cnt = QD_SEL_CAP;
-  for (int r = 0; r < B.world; ++r) {
+  for (int r = blockIdx.x; r < B.world; r += gridDim.x) {
     unsigned long long* dst = qd_blist(B, r, parity, B.rank);
     if (threadIdx.x == 0) { dst[0] = cnt; dst[1] = mingt_local; }
     for (int k = threadIdx.x; k < (int)cnt; k += blockDim.x) dst[2 + k] = __ldcg(lst + k);
+    __syncthreads();
+    if (threadIdx.x == 0) { qd_fence_sys(); qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, epoch); }
   }
-  qd_fence_sys();
-  __syncthreads();
-  if (threadIdx.x == 0) mine[QD_BF_EPOCH_SEL] = epoch;
-  if (threadIdx.x < B.world) { qd_st_sys(qd_bflags(B, threadIdx.x) + QD_BF_SEL + B.rank, epoch); qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch); }
+  if (blockIdx.x != 0) return -1;
+  if (threadIdx.x < B.world) qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch);
   __syncthreads();
   int m = 0;
   unsigned long long mg = ~0ull;

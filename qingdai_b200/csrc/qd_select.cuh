@@ -67,7 +67,8 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
 // gather pass appends them to a list (and records the smallest key above the prefix bucket); block 0 sorts
 // the list in shared memory and reads both middle elements.  Heavily duplicated data simply keeps taking
 // radix passes down to bit 0.  3 sweeps + 3 grid syncs in the common case instead of 6 + 6.
-// hist / list counter / mingt are left zeroed (resp. all-ones) for the next launch: no memset nodes.
+// The histograms are left zeroed for the next launch and the list counter / mingt are reset at the start: no
+// memset nodes in the step graph.
 __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
                                                                unsigned long long* list, unsigned* lcount,
                                                                unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B) {
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
   const int nbits[QD_SEL_PASSES] = {13, 13, 13, 13, 11};
   unsigned long long prefix = 0, rank = 0, count = 0, inbin = ~0ull;
   int npass = 0, lo_shift = 63;
+  // latitude bands: epoch of the k-th cross-rank collective of this launch = word at launch + k (same in every block)
+  unsigned long long sel_epoch = B.world > 1 ? qd_bflags(B, B.rank)[QD_BF_EPOCH_SEL] : 0ull;
   // One radix pass.  Every block of the GRID takes part in the sync; members whose candidates already fit
   // the list (work == false) skip the sweep.
   auto radix_pass = [&](int pass, bool work) {
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     }
     grid.sync();
     if (B.world > 1 && work) {                             // latitude bands (one member): histogram of the whole domain
-      if (blockIdx.x == 0) qd_band_hist_allreduce(B, gh, nb);
+      qd_band_hist_allreduce(B, gh, nb, ++sel_epoch);
       grid.sync();
     }
     if (work) {
@@ -141,6 +144,8 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     }
     grid.sync();
   };
+  // list counter / "next above" key: reset here (they are first touched in the gather pass, two grid syncs later)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { lcount[b] = 0u; mingt[b] = ~0ull; }
   radix_pass(0, true);
   radix_pass(1, inbin > QD_SEL_CAP);
   const bool more = inbin > QD_SEL_CAP;                    // heavily duplicated data: keep narrowing
@@ -158,22 +163,20 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     unsigned* gh = hist + ((size_t)p * g.batch + b) * QD_SEL_MAXBINS;
     for (int k = t0; k < (1 << nbits[p]); k += stride) gh[k] = 0u;
   }
-  if (blockIdx.x != 0) return;
   const bool fits = inbin <= QD_SEL_CAP;                   // false only when one VALUE fills the last bucket
-  const bool even = count > 0 && !(count & 1ull);
-  const bool need_above = even && (rank + 1 >= inbin);
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // 4096 x u64 = 32 KB
-  unsigned long long Lk = prefix, Uk = prefix;
   __shared__ unsigned long long s_mingt;
-  if (threadIdx.x == 0) s_mingt = __ldcg(mingt + b);
-  __syncthreads();
   int mband = 0;
   if (B.world > 1 && count > 0) {                          // merge every rank's candidates and "next above" key
-    unsigned long long mg;
-    mband = qd_band_list_allgather(B, list + (size_t)b * QD_SEL_CAP, fits ? __ldcg(lcount + b) : 0u, s_mingt, skeys, &mg);
-    if (threadIdx.x == 0) s_mingt = mg;
-    __syncthreads();
-  }
+    unsigned long long mg = ~0ull;
+    mband = qd_band_list_allgather(B, list + (size_t)b * QD_SEL_CAP, fits ? __ldcg(lcount + b) : 0u, __ldcg(mingt + b), skeys, &mg, ++sel_epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) s_mingt = mg;
+  } else if (threadIdx.x == 0) s_mingt = __ldcg(mingt + b);
+  if (blockIdx.x != 0) return;
+  __syncthreads();
+  const bool even = count > 0 && !(count & 1ull);
+  const bool need_above = even && (rank + 1 >= inbin);
+  unsigned long long Lk = prefix, Uk = prefix;
   if (count > 0 && fits) {
     const int m = (int)inbin;
     int n2 = 1; while (n2 < m) n2 <<= 1;
@@ -208,8 +211,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     }
     out.value[(size_t)b * out.stride] = r;
     if (out.count) out.count[(size_t)b * out.stride] = (double)count;
-    lcount[b] = 0u;
-    mingt[b] = ~0ull;
+    if (B.world > 1) qd_bflags(B, B.rank)[QD_BF_EPOCH_SEL] = sel_epoch;
   }
 }
 #else
