@@ -287,6 +287,13 @@ int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alph
 /* A_b^surface [B][nb][nlat][nlon] (NaN on ocean) from the cached canopy factor */
 int  qd_eco_bands(qd_ctx* ctx, int nb, const double* r_eff_host, double soil_ref, double* out_dev);
 
+/* ------------------------------------------------------------------ phytoplankton tracer transport
+ * PhytoManager.advect_diffuse (pygcm/ecology/phyto.py:496-547, called every physics step at
+ * scripts/run_simulation.py:2256-2258): conc_dev [S][nlat][nlon] f64 in place; uo_dev / vo_dev [nlat][nlon] or NULL
+ * for the context's own ocean currents. */
+int  qd_phyto_advect_diffuse(qd_ctx* ctx, double* conc_dev, int n_species, const double* uo_dev, const double* vo_dev,
+                             double dt, double adv_alpha, double k_h);
+
 int  qd_route_setup(qd_ctx* ctx, int n_order, const int64_t* flow_order_host,
                     const int64_t* flow_to_host /* [ncell] */, const uint8_t* land_host,
                     const uint8_t* lake_host, const int32_t* lake_id_host,

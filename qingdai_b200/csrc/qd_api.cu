@@ -6,6 +6,7 @@
 #include "qd_loop.cuh"
 #include "qd_hyper4.cuh"
 #include "qd_eco.cuh"
+#include "qd_phyto.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -78,6 +79,7 @@ struct qd_ctx {
   // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
   QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
+  double* d_phyto_tmp; size_t phyto_cap;                  // scratch of qd_phyto_advect_diffuse
   // ecology sub-daily (qd_eco.cuh)
   const double* d_lai; int eco_nl, eco_every_nphys, eco_steps, eco_have_alpha;
   double eco_k, eco_every_hours, eco_delta;
@@ -246,6 +248,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   memset(&c->band, 0, sizeof(c->band)); c->band.world = 1; c->band_on = 0; c->band_bytes = 0; c->band_base = nullptr;
   memset(c->band_peer_map, 0, sizeof(c->band_peer_map)); memset(c->band_shm, 0, sizeof(c->band_shm)); c->band_maxext = 0;
   for (int k = 0; k < QD_F_COUNT + QD_M_COUNT; ++k) c->band_valid[k] = 1 << 28;
+  c->d_phyto_tmp = nullptr; c->phyto_cap = 0;
   c->d_lai = nullptr; c->eco_nl = 0; c->eco_every_nphys = 1; c->eco_steps = 0; c->eco_have_alpha = 0;
   c->eco_k = 0.5; c->eco_every_hours = 6.0; c->eco_delta = 0.05;
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
@@ -331,6 +334,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
   band_release(c);
+  cudaFree(c->d_phyto_tmp);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
@@ -1023,6 +1027,30 @@ extern "C" int qd_eco_subdaily(qd_ctx* c, const double* isr, double dt, double* 
   QD_K(c, k_eco_cell, c->geo, A);
   QD_CHECK_LAUNCH(c);
   if (produced) *produced = want;
+  return QD_OK;
+}
+// PhytoManager.advect_diffuse on S tracers [S][nlat][nlon] (in place).  uo / vo: device currents [nlat][nlon], or
+// NULL for the context's own ocean state (member 0).
+extern "C" int qd_phyto_advect_diffuse(qd_ctx* c, double* conc, int S, const double* uo, const double* vo, double dt,
+                                       double adv_alpha, double k_h) {
+  if (!c || !conc || S < 1) return QD_E_INVALID;
+  QD_BOUND(c);
+  if (c->band_on) return qd_fail(c, QD_E_STATE, "latitude bands: tracer transport is not partitioned", cudaSuccess);
+  if (dt <= 0.0) return QD_OK;                                         // phyto.py:507-508
+  const size_t need = (size_t)S * c->ncell;
+  if (need > c->phyto_cap) {
+    QD_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_phyto_tmp); c->d_phyto_tmp = nullptr; c->phyto_cap = 0;
+    QD_CUDA(c, cudaMalloc((void**)&c->d_phyto_tmp, need * 8));
+    c->phyto_cap = need;
+  }
+  QdPhytoArgs A; memset(&A, 0, sizeof(A));
+  A.uo = uo ? uo : F(c, QD_F_UO); A.vo = vo ? vo : F(c, QD_F_VO); A.C = conc; A.tmp = c->d_phyto_tmp; A.land = M(c, QD_M_LAND);
+  A.dt = dt; A.alpha = adv_alpha; A.dtkh = k_h > 0.0 ? dt * k_h : 0.0;
+  QD_KG(c, k_phyto_advect, dim3(c->nblk, S), dim3(QD_THREADS), c->geo, A);
+  QD_KG(c, k_phyto_finish, dim3(c->nblk, S), dim3(QD_THREADS), c->geo, A);
+  QD_KG(c, k_phyto_polar, dim3(2, S), dim3(QD_THREADS), c->geo, A);
+  QD_CHECK_LAUNCH(c);
   return QD_OK;
 }
 extern "C" int qd_eco_bands(qd_ctx* c, int nb, const double* r_eff, double soil, double* out) {

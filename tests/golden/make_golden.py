@@ -524,6 +524,46 @@ def gen_eco():
     print("eco_golden.npz:", len(out), "arrays")
 
 
+# ------------------------------------------------------------------------------------ phytoplankton transport
+def gen_phyto():
+    """PhytoManager.advect_diffuse (pygcm/ecology/phyto.py:496-547): per-species semi-Lagrangian advection by the
+    ocean currents + explicit lateral diffusion + polar ring means, called every physics step by the script
+    (run_simulation.py:2256-2258).  SURVEY 8f row 1."""
+    from pygcm.grid import SphericalGrid
+    from pygcm.ecology.phyto import PhytoManager
+    out = {}
+    for tag, (nlat, nlon, dt, env) in {"p1": (25, 48, 300.0, {}),
+                                       "p2": (19, 36, 1800.0, {"QD_PHYTO_ADV_ALPHA": "0.45", "QD_PHYTO_KH": "2.0e4"})}.items():
+        set_env(env)
+        rng = np.random.default_rng(500 + nlat)
+        grid = SphericalGrid(nlat, nlon)
+        land = (rng.uniform(size=(nlat, nlon)) < 0.3).astype(np.uint8)
+        if tag == "p2":
+            land[0, :] = 1                                           # no ocean on the south pole row
+        with quiet():
+            ph = PhytoManager(grid, land, H_mld_m=50.0, diag=False)
+        S = int(ph.S)
+        C = np.abs(rng.standard_normal((S, nlat, nlon))) * 0.3 * (land == 0)
+        C[0, 3, 4] = np.nan
+        ph.C_phyto_s = C.copy()
+        out[f"{tag}_land"], out[f"{tag}_dt"], out[f"{tag}_C0"] = land, np.array(dt), C
+        out[f"{tag}_kh"] = np.array(ph.K_h)
+        out[f"{tag}_alpha"] = np.array(float(env.get("QD_PHYTO_ADV_ALPHA", "0.7")))
+        ncalls = 4
+        out[f"{tag}_ncalls"] = np.array(ncalls)
+        for n in range(ncalls):
+            uo = rng.standard_normal((nlat, nlon)) * 0.8 * (land == 0)
+            vo = rng.standard_normal((nlat, nlon)) * 0.5 * (land == 0)
+            if n == 2:
+                uo[5, 6], vo[7, 8] = 40.0, -25.0                     # departure points several cells away
+            with quiet(), np.errstate(all="ignore"):
+                ph.advect_diffuse(uo, vo, dt)
+            out[f"{tag}_c{n}_uo"], out[f"{tag}_c{n}_vo"] = uo, vo
+            out[f"{tag}_c{n}_C"] = np.array(ph.C_phyto_s, copy=True)
+    np.savez_compressed(os.path.join(OUT, "phyto_golden.npz"), **out)
+    print("phyto_golden.npz:", len(out), "arrays")
+
+
 def gen_routing():
     """Network from the reference's own builder (scripts/generate_hydrology_maps.py:85-273) on a small
     procedural elevation, then pygcm.routing.RiverRouting (unmodified, fed through an in-memory stand-in
@@ -594,6 +634,8 @@ def main():
         gen_routing()
     if "eco" in which:
         gen_eco()
+    if "phyto" in which:
+        gen_phyto()
 
 
 if __name__ == "__main__":

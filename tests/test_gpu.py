@@ -114,3 +114,8 @@ def test_loop_with_ecology(lib, golden):
 
 def test_hyper4_streaming_kernel(lib):
     qdcheck.check_hyper4_stream(lib)
+
+
+@pytest.mark.parametrize("tag", ["p1", "p2"])
+def test_phyto_transport(lib, golden, tag):
+    qdcheck.check_phyto(lib, golden("phyto_golden.npz"), tag)
