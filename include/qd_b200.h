@@ -287,6 +287,15 @@ int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alph
 /* A_b^surface [B][nb][nlat][nlon] (NaN on ocean) from the cached canopy factor */
 int  qd_eco_bands(qd_ctx* ctx, int nb, const double* r_eff_host, double soil_ref, double* out_dev);
 
+/* ------------------------------------------------------------------ global diagnostics (one launch, warp-shuffle reductions)
+ * energy.compute_energy_diagnostics (energy.py:494-538), hydrology.diagnose_water_closure (hydrology.py:270-340),
+ * WindDrivenSlabOcean.diagnostics (ocean.py:535-561).  out_host: [B][qd_diag_count()] doubles: slot 0 = sum of the
+ * area weights, then weighted SUMS (divide by slot 0 + 1e-15 for the reference's means) of T_s, h, q, cloud, h_ice,
+ * W_land, S_snow, E, precip, R_land, albedo, SST, I, R, OLR, SW_sfc, LW_sfc, SH, LH, ocean KE, then eta min / max,
+ * max |U_ocean|, max |u|, T_s min / max (qd_diag.cuh: QD_D_*). */
+int  qd_diag_count(void);
+int  qd_diag(qd_ctx* ctx, double* out_host);
+
 /* ------------------------------------------------------------------ phytoplankton tracer transport
  * PhytoManager.advect_diffuse (pygcm/ecology/phyto.py:496-547, called every physics step at
  * scripts/run_simulation.py:2256-2258): conc_dev [S][nlat][nlon] f64 in place; uo_dev / vo_dev [nlat][nlon] or NULL

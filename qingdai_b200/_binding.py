@@ -113,6 +113,8 @@ PROTOTYPES = {
     "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
     "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),
     "qd_eco_bands": (_I, [_P, _I, _P, _D, _P]),
+    "qd_diag_count": (_I, []),
+    "qd_diag": (_I, [_P, _P]),
     "qd_phyto_advect_diffuse": (_I, [_P, _P, _I, _P, _P, _D, _D, _D]),
     "qd_route_setup": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "qd_route_levels": (_I, [_P]),

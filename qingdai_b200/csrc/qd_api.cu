@@ -7,6 +7,7 @@
 #include "qd_hyper4.cuh"
 #include "qd_eco.cuh"
 #include "qd_phyto.cuh"
+#include "qd_diag.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <vector>
@@ -79,6 +80,7 @@ struct qd_ctx {
   // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
   QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
+  double *d_diag_part, *d_diag_out;                       // qd_diag scratch
   double* d_phyto_tmp; size_t phyto_cap;                  // scratch of qd_phyto_advect_diffuse
   // ecology sub-daily (qd_eco.cuh)
   const double* d_lai; int eco_nl, eco_every_nphys, eco_steps, eco_have_alpha;
@@ -282,6 +284,8 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
     if ((long long)c->sel_gx * batch > resident) { delete c; return QD_E_INVALID; }   // ensemble too large for one cooperative grid
   }
 #endif
+  QD_ALLOC(c->d_diag_part, (size_t)batch * QD_DIAG_COUNT * c->nblk * 8);
+  QD_ALLOC(c->d_diag_out, (size_t)batch * QD_DIAG_COUNT * 8);
   QD_ALLOC(c->d_step_idx, sizeof(int));
   QD_ALLOC(c->d_sub_ctr, sizeof(int));
   QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
@@ -334,7 +338,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
   band_release(c);
-  cudaFree(c->d_phyto_tmp);
+  cudaFree(c->d_phyto_tmp); cudaFree(c->d_diag_part); cudaFree(c->d_diag_out);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
@@ -1027,6 +1031,25 @@ extern "C" int qd_eco_subdaily(qd_ctx* c, const double* isr, double dt, double* 
   QD_K(c, k_eco_cell, c->geo, A);
   QD_CHECK_LAUNCH(c);
   if (produced) *produced = want;
+  return QD_OK;
+}
+// Global diagnostics of every member in one launch (qd_diag.cuh); out_host [B][QD_DIAG_COUNT].  Sync.
+extern "C" int qd_diag_count(void) { return QD_DIAG_COUNT; }
+extern "C" int qd_diag(qd_ctx* c, double* out_host) {
+  if (!c || !out_host) return QD_E_INVALID;
+  QD_BOUND(c);
+  if (c->band_on) return qd_fail(c, QD_E_STATE, "latitude bands: use Engine.gather_rows for diagnostics", cudaSuccess);
+  QdDiagArgs A; memset(&A, 0, sizeof(A));
+  A.ts = F(c, QD_F_TS); A.h = F(c, QD_F_H); A.q = F(c, QD_F_Q); A.cloud = F(c, QD_F_CLOUD); A.hice = F(c, QD_F_HICE);
+  A.wland = F(c, QD_F_WLAND); A.ssnow = F(c, QD_F_SSNOW); A.eflux = F(c, QD_F_EFLUX); A.precip = F(c, QD_F_PRECIP);
+  A.rland = F(c, QD_F_RLAND); A.albedo = F(c, QD_F_ALBEDO); A.sst = F(c, QD_F_SST); A.isr = F(c, QD_F_ISR);
+  A.cloud_eff = F(c, QD_F_CLOUD_EFF); A.lh = F(c, QD_F_LH); A.u = F(c, QD_F_U); A.v = F(c, QD_F_V);
+  A.uo = F(c, QD_F_UO); A.vo = F(c, QD_F_VO); A.eta = F(c, QD_F_ETA); A.land = M(c, QD_M_LAND);
+  A.has_cloud_eff = c->has_cloud_eff; A.part = c->d_diag_part; A.ticket = c->d_ticket + 2 * c->batch; A.out = c->d_diag_out;
+  QD_KR(c, k_diag, c->geo, A);
+  QD_CHECK_LAUNCH(c);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QD_CUDA(c, cudaMemcpy(out_host, c->d_diag_out, (size_t)c->batch * QD_DIAG_COUNT * 8, cudaMemcpyDeviceToHost));
   return QD_OK;
 }
 // PhytoManager.advect_diffuse on S tracers [S][nlat][nlon] (in place).  uo / vo: device currents [nlat][nlon], or

@@ -405,6 +405,25 @@ class Engine:
         self._eco_on, self._eco_leaf = bool(enabled), float(alpha_leaf_scalar)
         self.refresh_params()
 
+    DIAG = ("wsum", "ts", "h", "q", "cloud", "hice", "wland", "ssnow", "eflux", "precip", "rland", "albedo", "sst", "I", "R", "OLR",
+            "SW_sfc", "LW_sfc", "SH", "LH", "KE_ocean", "eta_min", "eta_max", "uocean_max", "uabs_max", "ts_min", "ts_max")
+
+    def diag(self):
+        """One launch of the device diagnostics kernel (csrc/qd_diag.cuh): list of dicts, one per member.  Weighted
+        sums come back as the reference's area-weighted MEANS, sum(x w) / (sum(w) + 1e-15) (energy.py:522-527)."""
+        n = int(self.lib.qd_diag_count())
+        assert n == len(self.DIAG)
+        raw = np.empty((self.batch, n), dtype=np.float64)
+        self._chk(self.lib.qd_diag(self.ctx, _ptr(raw)), "qd_diag")
+        out = []
+        for b in range(self.batch):
+            d = dict(zip(self.DIAG, raw[b]))
+            den = d["wsum"] + 1e-15
+            for k in self.DIAG[1:21]:
+                d[k] = d[k] / den
+            out.append(d)
+        return out
+
     def scalars(self):
         out = np.empty((self.batch, NS), dtype=np.float64)
         self._chk(self.lib.qd_get_scalars(self.ctx, _ptr(out)), "qd_get_scalars")

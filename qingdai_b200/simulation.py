@@ -90,13 +90,39 @@ class Simulation:
         self.step_index += nsteps
 
     def diagnostics(self, member=0):
-        """Area-weighted means used by the reference's periodic prints (energy.py:494-538 style)."""
-        e = self.engine
-        w = np.maximum(np.cos(np.deg2rad(self.grid.lat_mesh)), 0.0)
-        ws = float(np.sum(w) + 1e-15)
-        out = {}
-        for name in ("ts", "h", "q", "cloud", "precip", "albedo", "sst"):
-            x = e.get(name, member)
-            out[name + "_mean"] = float(np.sum(x * w) / ws)
-        out["u_absmax"] = float(np.max(np.abs(e.get("u", member))))
+        """Area-weighted means used by the reference's periodic prints, from one device reduction kernel."""
+        d = self.engine.diag()[member]
+        out = {name + "_mean": d[name] for name in ("ts", "h", "q", "cloud", "precip", "albedo", "sst")}
+        out["u_absmax"] = d["uabs_max"]
         return out
+
+    def energy_diagnostics(self, member=0):
+        """energy.compute_energy_diagnostics (energy.py:494-538) of the current state."""
+        d = self.engine.diag()[member]
+        toa = d["I"] - d["R"] - d["OLR"]
+        sfc = d["SW_sfc"] - d["LW_sfc"] - d["SH"] - d["LH"]
+        return {"TOA_net": toa, "SFC_net": sfc, "ATM_net": toa - sfc, "I_mean": d["I"], "R_mean": d["R"], "OLR_mean": d["OLR"],
+                "SW_sfc_mean": d["SW_sfc"], "LW_sfc_mean": d["LW_sfc"], "SH_mean": d["SH"], "LH_mean": d["LH"]}
+
+    def water_closure(self, member=0, dt_since_prev=None, prev_total=None):
+        """hydrology.diagnose_water_closure (hydrology.py:270-340) of the current state."""
+        d = self.engine.diag()[member]
+        p = self.engine.params[member]
+        res = {"CWV_mean": float(p.rho_a) * float(p.h_mbl) * d["q"], "ICE_mean": float(p.rho_i) * d["hice"], "W_land_mean": d["wland"],
+               "S_snow_mean": d["ssnow"], "E_mean": d["eflux"], "P_mean": d["precip"], "R_mean": d["rland"]}
+        res["total_reservoir_mean"] = res["CWV_mean"] + res["ICE_mean"] + res["W_land_mean"] + res["S_snow_mean"]
+        if dt_since_prev is not None and prev_total is not None and dt_since_prev > 0:
+            res["d/dt_total_mean"] = (res["total_reservoir_mean"] - prev_total) / float(dt_since_prev)
+            res["closure_residual"] = res["d/dt_total_mean"] - (res["E_mean"] - res["P_mean"] - res["R_mean"])
+        return res
+
+    def ocean_diagnostics(self, member=0):
+        """WindDrivenSlabOcean.diagnostics (ocean.py:535-561)."""
+        d = self.engine.diag()[member]
+        p = self.engine.params[member]
+        a = const.PLANET_RADIUS
+        dlat, dlon = self.engine.dlat, self.engine.dlon
+        min_cos = float(np.min(np.maximum(np.cos(np.deg2rad(self.grid.lat)), 0.5)))
+        dx_min = min(a * dlat, a * dlon * max(1e-3, min_cos))
+        return {"KE_mean": d["KE_ocean"], "U_max": d["uocean_max"], "eta_min": d["eta_min"], "eta_max": d["eta_max"],
+                "cfl_per_s": float(np.sqrt(p.oc_g * p.oc_H) / max(1e-12, dx_min))}

@@ -106,3 +106,7 @@ def test_hyper4_streaming_kernel(lib):
 @pytest.mark.parametrize("tag", ["p1", "p2"])
 def test_phyto_transport(lib, golden, tag):
     qdcheck.check_phyto(lib, golden("phyto_golden.npz"), tag)
+
+
+def test_global_diagnostics(lib):
+    qdcheck.check_diag(lib)
