@@ -66,6 +66,7 @@ struct qd_ctx {
 #ifndef QD_HOST_EMU
   cudaStream_t cap_stream, cap_stream2;
   cudaGraph_t capture_graph;                        // non-null while a whole loop step is being captured
+  std::map<const void*, int> red_cache;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
@@ -138,6 +139,24 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
 #define QD_REQUIRE(c, cond) do { if (!(cond)) return qd_fail((c), QD_E_INVALID, #cond, cudaSuccess); } while (0)
 #define QD_BOUND(c) do { if (!(c)->fields || !(c)->masks) return qd_fail((c), QD_E_UNBOUND, "qd_bind was not called", cudaSuccess); } while (0)
 
+// Blocks per member of a grid-stride reduction kernel: exactly ONE resident wave of that kernel (a partial second
+// wave ran k_ocean_continuity at 55 % occupancy and doubled its time, profiles/r01_ncu_full_hires_step_v2.csv).
+static int qd_red_blocks(qd_ctx* c, const void* kern) {
+#ifdef QD_HOST_EMU
+  (void)kern;
+  return c->red_blk;
+#else
+  auto it = c->red_cache.find(kern);
+  if (it != c->red_cache.end()) return it->second;
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QD_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const int n = std::max(1, (per_sm * std::max(1, sms)) / c->batch);
+  c->red_cache[kern] = n;
+  return n;
+#endif
+}
+
 // Every launch goes through QD_KG so that launches are counted and, in profiling mode, bracketed by
 // CUDA events on the launching stream (per-kernel device time for bench.py's roofline object).
 #define QD_KGN(c, name, kern, grid, block, ...) do { \
@@ -150,7 +169,7 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
     qd_prof_end((c), pi_); (c)->launches++; } while (0)
 #define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->cur_nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 // grid-stride kernels that end in a grid-wide reduction (QD_CELL_LOOP): at most red_blk blocks per member
-#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min((c)->red_blk, (c)->cur_nblk), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min(qd_red_blocks((c), (const void*)kern), (c)->cur_nblk), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 
 struct BIn;
 static void band_release(qd_ctx* c);

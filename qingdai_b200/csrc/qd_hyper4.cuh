@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
 // `cr` tables carry, behind the cosine row and its 1/c, 1/c^2 rows, the three centred-stencil coefficient
 // rows ap, am, bl of the tile kernel (filled on the host by qd_cos_companions with the same expressions).
 template <int R>
-__global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
+__global__ void __launch_bounds__(32 * QD_H4S_WARPS, 6) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
   static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
   const int b = blockIdx.y;
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;

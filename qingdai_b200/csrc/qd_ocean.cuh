@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
   double contrib = 0.0;
-  QD_CELL_LOOP(g) {
-    if (done) break;
+  QD_CELL_LOOP_N(g, done ? 0 : g.ncomp) {
     QD_CELL_JI(g)
     const size_t c = off + idx;
     const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);

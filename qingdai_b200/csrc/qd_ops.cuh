@@ -65,7 +65,15 @@ QD_HD bool qd_owned(const QdGeo& g, int j) { return j >= g.own0 && j < g.own1; }
   const int b = blockIdx.y;                                           \
   const size_t off = (size_t)b * (geo).ncell;                         \
   (void)off;                                                          \
+  _Pragma("unroll 2")                                                 \
   for (int t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < (geo).ncomp; t_ += gridDim.x * blockDim.x)
+// same loop over the first `limit` cells of the compute region, unrolled twice so that the loads of two cells overlap
+#define QD_CELL_LOOP_N(geo, limit)                                    \
+  const int b = blockIdx.y;                                           \
+  const size_t off = (size_t)b * (geo).ncell;                         \
+  (void)off;                                                          \
+  _Pragma("unroll 2")                                                 \
+  for (int t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < (limit); t_ += gridDim.x * blockDim.x)
 #define QD_CELL_JI(geo)                                               \
   const int r_ = qd_div_nlon((geo), t_); const int i = t_ - r_ * (geo).nlon; \
   const int j = qd_seg_row((geo), r_); const int idx = j * (geo).nlon + i; (void)i; (void)j; (void)idx;
