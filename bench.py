@@ -216,7 +216,6 @@ def main():
         e1.record()
         evs.append((e0, e1))
     barrier()
-    clocks = sampler.stop()
     launches = eng.launches() - l0
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -231,18 +230,53 @@ def main():
     # -------- end-to-end through the public API: per step H2D forcing + D2H of a step metric (mean Ts)
     barrier()
     w0 = time.perf_counter()
+    metric_bytes = 0
     for _ in range(args.steps):
         sim.step(1)
-        eng.sync()
-        _ = eng.scalars()                       # D2H read of the per-member step scalars (n_sub, sums)
+        if band:
+            eng.sync()
+            _ = eng.scalars()                   # latitude bands: per-rank step scalars (n_sub, global sums)
+            metric_bytes = eng.scalars().size * 8
+        else:
+            d = eng.diag()                      # the step's metrics: one reduction launch + D2H of the global means
+            metric_bytes = len(d) * len(d[0]) * 8
     barrier()
     e2e_s = time.perf_counter() - w0
+    clocks = sampler.stop()                     # sampled over the device-timed and the end-to-end region
     t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_val = total_members * (args.steps / e2e_s) * dt / DAY
-    nscal = eng.scalars().size * 8
+    # -------- the reference's object-level operator interface with HOST arrays every step (rank 0, small grids):
+    # SpectralModel.time_step(Teq, dt, albedo) + WindDrivenSlabOcean.step(dt, u, v, Q_net, ice_mask) + reads of T_s
+    dropin = None
+    if rank == 0 and world == 1 and members == 1 and ncell <= 200000:
+        from qingdai_b200.dynamics import SpectralModel
+        from qingdai_b200.grid import SphericalGrid
+        from qingdai_b200.ocean import WindDrivenSlabOcean
+        grid = SphericalGrid(nlat, nlon)
+        tp = topos[0]
+        gcm = SpectralModel(grid, tp["friction"], land_mask=tp["land_mask"], greenhouse_factor=0.40, tau_rad=864000.0)
+        oc = WindDrivenSlabOcean(grid, tp["land_mask"], 50.0)
+        rng = np.random.default_rng(0)
+        Teq = 250.0 + 40.0 * np.cos(np.deg2rad(grid.lat_mesh)) + rng.standard_normal((nlat, nlon))
+        alb = np.clip(0.3 + 0.05 * rng.standard_normal((nlat, nlon)), 0.0, 1.0)
+        qn = 50.0 * rng.standard_normal((nlat, nlon))
+        nd = max(10, min(args.steps, 50))
+        for k in range(3 + nd):
+            if k == 3:
+                torch.cuda.synchronize(); wd = time.perf_counter()
+            gcm.time_step(Teq, dt, albedo=alb)
+            u_h, v_h = gcm.u, gcm.v
+            oc.step(dt, u_h, v_h, Q_net=qn, ice_mask=gcm.h_ice > 0.0)
+            gcm.T_s = np.where(tp["land_mask"] == 0, oc.Ts, gcm.T_s)          # run_simulation.py:2252-2253
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - wd) / nd
+        fb = ncell * 8
+        dropin = {"value": (1.0 / sec) * dt / DAY, "unit": "planet-days/s", "ms_per_step": sec * 1e3,
+                  "h2d_bytes_per_step": 6 * fb + ncell, "d2h_bytes_per_step": 5 * fb,
+                  "note": "drop-in SpectralModel.time_step + WindDrivenSlabOcean.step with host NumPy arrays in and out every step (cores only, no loop physics)"}
 
     # -------- per-kernel device time (CUDA events around every launch) -> roofline of the dominant kernel
     roof = None
@@ -301,8 +335,9 @@ def main():
                            "l2": f"256 MiB L2 flush before every timed step (state ~{state_bytes / 1e6:.0f} MB per GPU)",
                            "loop_with_albedo": True},
                 "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": "planet-days/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": 2 * nscal,
-                        "note": "Simulation.step(1) per step: forcing scalars H2D, per-member step scalars D2H, host sync every step"},
+                "e2e": {"value": e2e_val, "unit": "planet-days/s", "h2d_bytes_per_step": 80, "d2h_bytes_per_step": metric_bytes,
+                        "note": "Simulation.step(1) per step through the C ABI: forcing scalars H2D (the loop has no other per-step host input), then the step's global diagnostics (one reduction launch) D2H; host sync every step",
+                        "host_array_dropin": dropin},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
