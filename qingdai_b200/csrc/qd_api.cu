@@ -72,7 +72,7 @@ struct qd_ctx {
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
     const long long tiles_i = (nlon + 63) / 64;                  // launch_hyper4: large grids take the stream + pole-tile pair
     const bool stream = h4_stream && nlat >= 96 && nlon >= 64 && tiles_i * ((nlat + 31) / 32) * batch * 3 >= 2 * 148;
-    return 4 + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
+    return 3 + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
   }
 #endif
   char err[512];
@@ -1287,20 +1287,18 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   }
   QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
   Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
+  Co.sst = F(c, QD_F_SST); Co.tb = F(c, QD_F_X7);
   Co.ticket = c->d_ticket + 5 * c->batch;
-  BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}), BL(Co.eta));
+  BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}, {Co.sst, 2}), BL(Co.eta, Co.tb));
   QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
   { int rcb = band_allreduce(c, {QD_S_ETA_NUM}, false); if (rcb) return rcb; }
-  QdOcSstAArgs Sa; memset(&Sa, 0, sizeof(Sa));
-  Sa.sst = F(c, QD_F_SST); Sa.ub = ub; Sa.vb = vb; Sa.eta = F(c, QD_F_ETA); Sa.tb = F(c, QD_F_X7);
-  BP(c, BL({Sa.sst, 2}, {Sa.ub, 0}, {Sa.vb, 0}, {Sa.eta, 0}), BL(Sa.eta, Sa.tb));
-  QD_K(c, k_ocean_sst_advect, c->geo, Sa, sc);
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
   Sb.tb = F(c, QD_F_X7); Sb.ub = ub; Sb.vb = vb; Sb.qnet = F(c, QD_F_QNET);
-  Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS);
+  Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS); Sb.eta = F(c, QD_F_ETA);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
-  BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}), BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm));
+  BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}, {Sb.eta, 0}),
+     BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm, Sb.eta));
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
   return QD_OK;
 }

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
 // `cr` tables carry, behind the cosine row and its 1/c, 1/c^2 rows, the three centred-stencil coefficient
 // rows ap, am, bl of the tile kernel (filled on the host by qd_cos_companions with the same expressions).
 template <int R>
-__global__ void __launch_bounds__(32 * QD_H4S_WARPS, 6) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
+__global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
   static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
   const int b = blockIdx.y;
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;
@@ -293,14 +293,14 @@ __global__ void __launch_bounds__(32 * QD_H4S_WARPS, 6) k_hyper4_stream(QdGeo g,
   {                                                                                                  \
     const double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];        \
     p += 4 * (size_t)nlon;                                                                           \
-    const double a0 = cap[(jr)], a1 = cap[(jr) + 1], a2 = cap[(jr) + 2], a3 = cap[(jr) + 3];         \
-    const double m0 = cam[(jr)], m1 = cam[(jr) + 1], m2 = cam[(jr) + 2], m3 = cam[(jr) + 3];         \
-    const double b0 = cbl[(jr)], b1 = cbl[(jr) + 1], b2 = cbl[(jr) + 2], b3 = cbl[(jr) + 3];         \
-    QD_H4S_STEP(n0, a0, m0, b0, 0, emit) QD_H4S_STEP(n1, a1, m1, b1, 1, emit)                        \
-    QD_H4S_STEP(n2, a2, m2, b2, 2, emit) QD_H4S_STEP(n3, a3, m3, b3, 3, emit)                        \
+    QD_H4S_STEP(n0, cap[(jr)], cam[(jr)], cbl[(jr)], 0, emit)                                        \
+    QD_H4S_STEP(n1, cap[(jr) + 1], cam[(jr) + 1], cbl[(jr) + 1], 1, emit)                            \
+    QD_H4S_STEP(n2, cap[(jr) + 2], cam[(jr) + 2], cbl[(jr) + 2], 2, emit)                            \
+    QD_H4S_STEP(n3, cap[(jr) + 3], cam[(jr) + 3], cbl[(jr) + 3], 3, emit)                            \
   }
-#define QD_H4S_STEP(nv, ap, am, bl, s, emit)                                                         \
+#define QD_H4S_STEP(nv, apx, amx, blx, s, emit)                                                      \
   {                                                                                                  \
+    const double ap = (apx), am = (amx), bl = (blx);       /* warp-uniform L1 hits, loaded next to their use */ \
     const double f4 = qd_clean_sel(nv);                                                             \
     const double l4 = lap_row(f0, f2, f4, ap, am, bl);                                               \
     if (emit) {                                                                                      \

@@ -138,10 +138,14 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_hyper(QdGeo g, QdFields f,
   }
 }
 
-// Continuity (ocean.py:364-367) + the area-weighted ocean sum of eta for the mean removal (:369-375).
+// Continuity (ocean.py:364-367) + the area-weighted ocean sum of eta for the mean removal (:369-375), fused with the
+// SST semi-Lagrangian blend (ocean.py:380-382): both read the post-del^4 currents, so one pass loads them once.
+// The mean removal and hygiene of eta (ocean.py:375,436-443) need the global sum and are finished by
+// k_ocean_sst_finish.  Grid-stride, one resident wave (ends in a grid-wide reduction).
 struct QdOcContArgs {
   const double *ub, *vb, *eta_in;      // eta_in: where del^4 left eta (may be a scratch slot)
-  double *eta, *part;
+  const double* sst;
+  double *eta, *tb, *part;
   const uint8_t* land;
   unsigned* ticket;
 };
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
   const bool done = qd_sub_done(g, blockIdx.y, sc);
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
+  const double al = P[QD_P_OC_ADV_ALPHA];
   double contrib = 0.0;
   QD_CELL_LOOP_N(g, done ? 0 : g.ncomp) {
     QD_CELL_JI(g)
@@ -159,6 +164,10 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
     if (land) e = 0.0;
     A.eta[c] = e;
     if (qd_owned(g, j)) contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
+    double y, x;
+    qd_departure(A.ub[c], A.vb[c], sub_dt, g.a, qd_row(g, QD_R_COS_ADV_HALF)[j], g.dlat, g.dlon, j, i, &y, &x);
+    const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
+    A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
   }
   double t;
   double* part = A.part + (size_t)b * gridDim.x;
@@ -168,46 +177,38 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
   }
 }
 
-// eta mean removal + hygiene (ocean.py:375,436-443) and SST semi-Lagrangian blend (ocean.py:380-382): A -> TB.
-struct QdOcSstAArgs {
-  const double *sst, *ub, *vb;
-  double *eta, *tb;
-};
-__global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_advect(QdGeo g, QdOcSstAArgs A, QdSubCtl sc) {
-  QD_CELL_PROLOGUE(g)
-  if (!active || qd_sub_done(g, b, sc)) return;
-  const size_t c = off + idx;
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
-  const double* S = g.scal + (size_t)b * QD_S_COUNT;
-  const double sub_dt = S[QD_S_SUB_DT];
-  double e = A.eta[c];
-  if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - S[QD_S_ETA_NUM] / (P[QD_P_OC_WSUM_OCEAN] + 1e-15);
-  A.eta[c] = qd_clip(qd_nan_to_num(e), -P[QD_P_OC_ETA_CAP], P[QD_P_OC_ETA_CAP]);
-  double y, x;
-  qd_departure(A.ub[c], A.vb[c], sub_dt, g.a, qd_row(g, QD_R_COS_ADV_HALF)[j], g.dlat, g.dlon, j, i, &y, &x);
-  const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
-  const double al = P[QD_P_OC_ADV_ALPHA];
-  A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
-}
-
 // SST diffusion + Q_net heating (ocean.py:384-406), outlier handling of currents (ocean.py:408-434): B -> A.
 // On the member's last sub-step the non-polar rows also get the final Ts clip (ocean.py:531-533) and,
 // in loop mode, the SST injection into the atmosphere's T_s (run_simulation.py:2252-2253); the two
 // polar rows are finished by k_ocean_polar.
 struct QdOcSstBArgs {
   const double *tb, *ub, *vb, *qnet;
-  double *sst, *uo, *vo, *ts_atm;
+  double *sst, *uo, *vo, *ts_atm, *eta;
   const uint8_t *land, *ice;
   int has_q, has_ice, inject;
 };
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
   QD_CELL_PROLOGUE(g)
+  // the ocean-mean of eta (one true division) once per block instead of once per cell
+  __shared__ double s_eta_mean;
+  if (threadIdx.x == 0) {
+    const double* Pm = g.prm + (size_t)b * QD_P_COUNT;
+    s_eta_mean = g.scal[(size_t)b * QD_S_COUNT + QD_S_ETA_NUM] / (Pm[QD_P_OC_WSUM_OCEAN] + 1e-15);
+  }
+#if !QD_EMU
+  __syncthreads();
+#endif
   if (!active || qd_sub_done(g, b, sc)) return;
   const size_t c = off + idx;
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const double* S = g.scal + (size_t)b * QD_S_COUNT;
   const double sub_dt = S[QD_S_SUB_DT];
   const int nlon = g.nlon, nlat = g.nlat;
+  {   // eta: mean removal over the ocean + hygiene (ocean.py:375,436-443); the sum comes from k_ocean_continuity
+    double e = A.eta[c];
+    if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - s_eta_mean;
+    A.eta[c] = qd_clip(qd_nan_to_num(e), -P[QD_P_OC_ETA_CAP], P[QD_P_OC_ETA_CAP]);
+  }
   double T = A.tb[c];
   if (P[QD_P_OC_K_H] > 0.0) {
     QdCleanLoad F{A.tb + off, nlon};
