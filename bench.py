@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- throughput of the fused Qingdai loop step on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload full181|ensemble64|hires] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload full181|config3|ensemble64|hires] [--impl b200|reference]
 
 A "step" is one pass of the per-timestep loop (scripts/run_simulation.py:1760-2344: precipitation /
 cloud diagnosis, dual-star forcing, P019 snow, albedo, SpectralModel.time_step, slab ocean,
@@ -10,6 +10,7 @@ hydrology bucket) over every ensemble member resident on the GPU.  Prints ONE JS
 Workloads (BASELINE.json configs):
   full181     configs[1]: 181x360 full physics (topography + orography, energy branch + sea ice,
               cloud coupling, dynamic ocean, hydrology), dt=300 s, one member per GPU.  DEFAULT.
+  config3     configs[2]: full181 + D8 river routing (6 h events) + sub-daily ecology albedo feedback.
   ensemble64  configs[3]: 64 independent 181x360 members (topography seeds 42..105) split across GPUs.
   hires       configs[4] at one GPU: 1441x2880 full physics, dt=37 s.
 Multi-GPU: ensemble members are independent -> no data-path collective; `--workload hires` at N>1 splits ONE
@@ -60,6 +61,9 @@ def workload(name):
     if name == "full181":
         return dict(nlat=181, nlon=360, dt=300, members_total=None, members_per_gpu=1, params=QDParams(**full),
                     label="configs[1] 181x360 full physics (topography+orography, energy branch+sea ice, cloud coupling, dynamic ocean, hydrology)")
+    if name == "config3":
+        return dict(nlat=181, nlon=360, dt=300, members_total=None, members_per_gpu=1, params=QDParams(**full), config3=True,
+                    label="configs[2] 181x360 full physics + P014 D8 routing (C++-built network, 6 h events) + P015 sub-daily ecology albedo feedback (NB=16)")
     if name == "ensemble64":
         return dict(nlat=181, nlon=360, dt=300, members_total=64, members_per_gpu=None, params=QDParams(**full),
                     label="configs[3] 64-member 181x360 full-physics ensemble (topography seeds 42..105) split across GPUs")
@@ -188,8 +192,16 @@ def main():
         members = spec["members_per_gpu"]
         scaling, seeds = "weak", [42 + rank * members + m for m in range(members)]
     topos = [make_topography(nlat, nlon, seed=s, land_frac=0.40) for s in seeds]
+    extra = {}
+    if spec.get("config3"):
+        from qingdai_b200.grid import SphericalGrid
+        from qingdai_b200.hydrology_network import build_network
+        t0 = time.perf_counter()
+        net = build_network(SphericalGrid(nlat, nlon), topos[0]["elevation"], topos[0]["land_mask"])
+        print(f"[bench] routing network built in {time.perf_counter() - t0:.2f} s (n_lakes={net['n_lakes']}, pit sweeps={net['pit_sweeps']})", file=sys.stderr)
+        extra = dict(with_eco=True, eco_env={}, routing_network=net, dt_hydro_hours=6.0)
     sim = Simulation(nlat, nlon, topos, spec["params"], dt=dt, batch=members, with_ocean=True, with_hydrology=True,
-                     loop_with_albedo=True, device=f"cuda:{local}", band=band)
+                     loop_with_albedo=True, device=f"cuda:{local}", band=band, **extra)
     eng = sim.engine
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     state_bytes = members * ncell * 8 * 45

@@ -287,6 +287,14 @@ int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alph
 /* A_b^surface [B][nb][nlat][nlon] (NaN on ocean) from the cached canopy factor */
 int  qd_eco_bands(qd_ctx* ctx, int nb, const double* r_eff_host, double soil_ref, double* out_dev);
 
+/* ------------------------------------------------------------------ routing-network builder (host C++)
+ * scripts/generate_hydrology_maps.py:85-273: pit_fill, compute_flow_to_index, identify_lakes, compute_lake_outlets,
+ * topo_sort_flow_order with their sequential semantics (bit-identical outputs).  dist[3][nlat][3][3]: centre distance
+ * to the neighbour at (dj, di), evaluated by the caller with the reference's NumPy expression (:65-82). */
+int  qd_net_build(int nlat, int nlon, double* elev_inout, const uint8_t* land_mask, const double* dist, int pit_iters,
+                  double pit_eps, int64_t* flow_to, int64_t* flow_order, int64_t* n_order, uint8_t* lake_mask,
+                  int32_t* lake_id, int32_t* lake_outlet, int* n_lakes, int* sweeps);
+
 /* ------------------------------------------------------------------ global diagnostics (one launch, warp-shuffle reductions)
  * energy.compute_energy_diagnostics (energy.py:494-538), hydrology.diagnose_water_closure (hydrology.py:270-340),
  * WindDrivenSlabOcean.diagnostics (ocean.py:535-561).  out_host: [B][qd_diag_count()] doubles: slot 0 = sum of the

@@ -113,6 +113,7 @@ PROTOTYPES = {
     "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
     "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),
     "qd_eco_bands": (_I, [_P, _I, _P, _D, _P]),
+    "qd_net_build": (_I, [_I, _I, _P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
     "qd_diag_count": (_I, []),
     "qd_diag": (_I, [_P, _P]),
     "qd_phyto_advect_diffuse": (_I, [_P, _P, _I, _P, _P, _D, _D, _D]),

@@ -1608,3 +1608,20 @@ extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcin
 }
 
 #include "qd_route.cuh"
+#include "qd_netbuild.h"
+
+// Routing-network builder (host; no context, no device): see qd_netbuild.h.  elev is filled in place.
+extern "C" int qd_net_build(int nlat, int nlon, double* elev /* in: elevation, out: pit-filled */, const uint8_t* land_mask,
+                            const double* dist /* [3][nlat][3][3] */, int pit_iters, double pit_eps,
+                            int64_t* flow_to /* [nlat*nlon] */, int64_t* flow_order /* [nlat*nlon] */, int64_t* n_order,
+                            uint8_t* lake_mask, int32_t* lake_id, int32_t* lake_outlet /* [nlat*nlon] capacity */, int* n_lakes, int* sweeps) {
+  if (nlat < 2 || nlon < 2 || !elev || !land_mask || !dist || !flow_to || !flow_order || !n_order || !lake_mask || !lake_id || !lake_outlet || !n_lakes)
+    return QD_E_INVALID;
+  const int it = qd_net_pit_fill(nlat, nlon, elev, land_mask, pit_iters, pit_eps);
+  if (sweeps) *sweeps = it;
+  qd_net_flow_to(nlat, nlon, elev, land_mask, dist, flow_to);
+  *n_lakes = qd_net_lakes(nlat, nlon, flow_to, land_mask, lake_mask, lake_id);
+  if (*n_lakes > 0) qd_net_outlets(nlat, nlon, elev, lake_mask, lake_id, land_mask, *n_lakes, lake_outlet);
+  *n_order = qd_net_topo_order(nlat, nlon, flow_to, land_mask, flow_order);
+  return QD_OK;
+}

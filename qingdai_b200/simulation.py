@@ -31,7 +31,7 @@ def q_sat_host(T, p0):
 class Simulation:
     def __init__(self, nlat, nlon, topo: dict | Sequence[dict], params: Optional[QDParams | Sequence[QDParams]] = None,
                  dt=300, batch=1, with_ocean=True, with_hydrology=True, with_eco=False, loop_with_albedo=False,
-                 device=None, lib=None, t0=0.0, eco_env=None, band=None):
+                 device=None, lib=None, t0=0.0, eco_env=None, band=None, routing_network=None, dt_hydro_hours=6.0):
         self.grid = SphericalGrid(nlat, nlon)
         plist = list(params) if isinstance(params, (list, tuple)) else [params or QDParams.from_env()] * batch
         self.engine = Engine(nlat, nlon, batch=batch, params=plist, dt=dt, device=device, lib=lib, band=band)
@@ -53,6 +53,16 @@ class Simulation:
             for b, tp in enumerate(topos):
                 e.set_elevation(tp["elevation"], member=b)
         self.reset_state()
+        self.routing = None
+        if routing_network is not None:
+            # run_simulation.py:1297-1311: P014 river routing on the land runoff of the bucket, events every dt_hydro
+            from .engine import _ENGINES
+            from .routing import RiverRouting
+            if batch != 1:
+                raise ValueError("river routing drives one ensemble member per Simulation")
+            _ENGINES[id(self.grid)] = e                      # the drop-in binds to the engine of its grid object
+            self.routing = RiverRouting(self.grid, routing_network, dt_hydro_hours=dt_hydro_hours, diag=False)
+            self.cfg["with_routing"] = True
         self.eco = None
         if with_eco:
             # run_simulation.py:1335-1337 builds the adapter; :1716-1723 calls it once at t=0 before the loop
@@ -84,10 +94,22 @@ class Simulation:
         return Forcing(t, fa, sa, ca, aa, fb, sb, cb, ab, self.forcing.star_geometry(t)[1])
 
     def step(self, nsteps=1):
-        fl = [self.forcing_for(self.t + k * self.dt) for k in range(nsteps)]
-        self.engine.loop_steps(fl, self.dt, **self.cfg)
-        self.t += nsteps * self.dt
-        self.step_index += nsteps
+        done = 0
+        while done < nsteps:
+            n = nsteps - done
+            rr = self.routing
+            if rr is not None:      # stop at the next routing event (routing.py:238: t_accum >= dt_hydro)
+                left = rr.dt_hydro_seconds - rr.t_accum
+                n = max(1, min(n, int(np.ceil((left - 1e-9) / self.dt))))
+            fl = [self.forcing_for(self.t + k * self.dt) for k in range(n)]
+            self.engine.loop_steps(fl, self.dt, **self.cfg)
+            self.t += n * self.dt
+            self.step_index += n
+            done += n
+            if rr is not None:      # the fused step accumulated R * area * dt on the device (k_route_accumulate)
+                rr.t_accum += n * self.dt
+                if rr.t_accum + 1e-9 >= rr.dt_hydro_seconds:
+                    rr.maybe_route(self.engine.get("precip"), self.engine.get("eflux"))
 
     def diagnostics(self, member=0):
         """Area-weighted means used by the reference's periodic prints, from one device reduction kernel."""

@@ -123,3 +123,20 @@ def test_phyto_transport(lib, golden, tag):
 
 def test_global_diagnostics(lib):
     qdcheck.check_diag(lib)
+
+
+def test_config3_routing_and_ecology_in_one_loop(lib, golden):
+    qdcheck.check_config3(lib, golden("routing_golden.npz"))
+
+
+@pytest.mark.parametrize("tag", ["r1", "r2"])
+def test_network_builder_in_cuda_library(lib, golden, tag):
+    """The host C++ routing-network builder as shipped inside libqd_b200.so (bit-exact vs the reference's builder)."""
+    from qingdai_b200.grid import SphericalGrid
+    from qingdai_b200.hydrology_network import build_network
+    G = golden("routing_golden.npz")
+    land = G[f"{tag}_land_mask"]
+    net = build_network(SphericalGrid(*land.shape), G[f"{tag}_elev_in"], land, lib=lib)
+    for k in ("flow_to_index", "flow_order", "lake_mask", "lake_id"):
+        assert np.array_equal(net[k], G[f"{tag}_{k}"]), k
+    assert np.array_equal(net["elevation_filled"], G[f"{tag}_elev_filled"])

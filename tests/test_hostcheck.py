@@ -110,3 +110,7 @@ def test_phyto_transport(lib, golden, tag):
 
 def test_global_diagnostics(lib):
     qdcheck.check_diag(lib)
+
+
+def test_config3_routing_and_ecology_in_one_loop(lib, golden):
+    qdcheck.check_config3(lib, golden("routing_golden.npz"))
