@@ -23,8 +23,8 @@
 #endif
 
 // sizes of the exact-median kernel (qd_select.cuh), shared with the mailboxes below
-#define QD_SEL_PASSES 5
-#define QD_SEL_MAXBINS 8192
+#define QD_SEL_PASSES 6
+#define QD_SEL_MAXBINS 2048
 #define QD_SEL_THREADS 512
 #define QD_SEL_CAP 2048          // candidates finished by an in-block sort instead of further radix passes
 

@@ -2,7 +2,7 @@
 //
 // np.median(x[x>0]) (physics.py:298-301, run_simulation.py:1872-1873, dynamics.py:344-348) is an
 // exact order statistic; the loop needs three of them per step.  Positive IEEE doubles order like
-// their 63-bit patterns, so the lower-middle element is found by an MSD radix select with 13-bit digits.
+// their 63-bit patterns, so the lower-middle element is found by an MSD radix select with 11-bit digits.
 // Every pass builds a shared-memory histogram per block, merges it into a per-(pass, member) global
 // histogram, and after one grid-wide sync every block locates the digit redundantly (no second sync, no
 // host round trip).  As soon as <= QD_SEL_CAP candidates remain they are gathered and sorted by one block,
@@ -29,7 +29,7 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
   const int t = threadIdx.x;
   for (int k = t; k < nbins; k += QD_SEL_THREADS) sh[k] = __ldcg(hist + k);
   __syncthreads();
-  const int per = QD_SEL_MAXBINS / QD_SEL_THREADS;        // 16 bins per thread
+  const int per = QD_SEL_MAXBINS / QD_SEL_THREADS;        // 4 bins per thread
   unsigned long long s = 0;
   for (int k = 0; k < per; ++k) { const int idx = t * per + k; if (idx < nbins) s += sh[idx]; }
   part[t] = s;
@@ -62,7 +62,7 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
   return r;
 }
 
-// Radix passes of 13 bits (the first covers the exponent and two mantissa bits) narrow the candidates
+// Radix passes of 11 bits (the first is the exponent) narrow the candidates
 // until at most QD_SEL_CAP share the prefix -- two passes for continuous data of any size here -- then ONE
 // gather pass appends them to a list (and records the smallest key above the prefix bucket); block 0 sorts
 // the list in shared memory and reads both middle elements.  Heavily duplicated data simply keeps taking
@@ -73,15 +73,17 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
                                                                unsigned long long* list, unsigned* lcount,
                                                                unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ __align__(16) unsigned sh[QD_SEL_MAXBINS];
+  __shared__ __align__(16) unsigned sh[QD_SEL_MAXBINS > 2 * QD_SEL_CAP ? QD_SEL_MAXBINS : 2 * QD_SEL_CAP];   // histogram, later the candidate keys
   __shared__ unsigned long long part[QD_SEL_THREADS];
   const int b = blockIdx.y;
   const size_t off = (size_t)b * g.ncell;
   const int stride = gridDim.x * QD_SEL_THREADS;
   const int t0 = blockIdx.x * QD_SEL_THREADS + threadIdx.x;
   const int c0 = g.own0 * g.nlon, c1 = g.own1 * g.nlon;        // this rank's own rows (all rows without latitude bands)
-  const int shifts[QD_SEL_PASSES] = {50, 37, 24, 11, 0};
-  const int nbits[QD_SEL_PASSES] = {13, 13, 13, 13, 11};
+  // 11-bit digits: the first is exactly the exponent (positive doubles), the second the top of the mantissa; a
+  // 2048-bin histogram keeps the per-pass merge + locate short (every block scans it redundantly)
+  const int shifts[QD_SEL_PASSES] = {52, 41, 30, 19, 8, 0};
+  const int nbits[QD_SEL_PASSES] = {11, 11, 11, 11, 11, 8};
   unsigned long long prefix = 0, rank = 0, count = 0, inbin = ~0ull;
   int npass = 0, lo_shift = 63;
   // latitude bands: epoch of the k-th cross-rank collective of this launch = word at launch + k (same in every block)
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     radix_pass(2, more);
     radix_pass(3, more && inbin > QD_SEL_CAP);
     radix_pass(4, more && inbin > QD_SEL_CAP);
+    radix_pass(5, more && inbin > QD_SEL_CAP);
     gather_pass(more);
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *more_flag = 0;
   }
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
     for (int k = t0; k < (1 << nbits[p]); k += stride) gh[k] = 0u;
   }
   const bool fits = inbin <= QD_SEL_CAP;                   // false only when one VALUE fills the last bucket
-  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // 4096 x u64 = 32 KB
+  unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // QD_SEL_CAP x u64
   __shared__ unsigned long long s_mingt;
   int mband = 0;
   if (B.world > 1 && count > 0) {                          // merge every rank's candidates and "next above" key
