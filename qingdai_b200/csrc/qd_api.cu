@@ -47,7 +47,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream;
+  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -262,7 +262,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->cur_nblk = c->nblk;
-  c->h4_stream = 1;
+  c->h4_stream = 1; c->polar_advances_step = 0;
   c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
@@ -1356,10 +1356,11 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   P0.u = F(c, QD_F_U); P0.v = F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
+  P0.dt = dt; P0.sub_ctr = c->band_on ? nullptr : c->d_sub_ctr;      // bands: n_sub needs the all-reduced maxima first
   BP(c, BL({P0.u, 0}, {P0.v, 0}, {P0.uo, 0}, {P0.vo, 0}), BL(P0.taux, P0.tauy));
   QD_KR(c, k_ocean_prep, c->geo, P0);
   { int rcb = band_allreduce(c, {QD_S_MAX_UOCEAN, QD_S_MAX_VA}, true); if (rcb) return rcb; }
-  QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
+  if (c->band_on) QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
   QD_CHECK_LAUNCH(c);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
   const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
@@ -1417,6 +1418,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   QdOcPolarArgs Po; memset(&Po, 0, sizeof(Po));
   Po.sst = F(c, QD_F_SST); Po.uo = F(c, QD_F_UO); Po.vo = F(c, QD_F_VO); Po.ts_atm = F(c, QD_F_TS);
   Po.land = M(c, QD_M_LAND); Po.ice = M(c, QD_M_ICE); Po.has_ice = cfg->oc_has_ice; Po.inject = inject;
+  Po.step_idx = c->polar_advances_step ? c->d_step_idx : nullptr;
   QD_KG(c, k_ocean_polar, dim3(2, c->batch), dim3(QD_THREADS), c->geo, Po);
   if (c->band_on) for (int id : {(int)QD_F_SST, (int)QD_F_UO, (int)QD_F_VO, (int)QD_F_TS}) c->band_valid[id] = 0;   // pole rows changed on their owners only
   QD_CHECK_LAUNCH(c);
@@ -1445,11 +1447,11 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if ((c->w_set & 3) != 3) return qd_fail(c, QD_E_STATE, "qd_set_gauss(0|1) must be called before qd_loop_step", cudaSuccess);
   const QdGaussW w1 = c->w_sigma1;
   int rc;
-  QD_KG(c, k_forcing_cols, dim3((c->nlon + 127) / 128), dim3(128), c->geo, c->d_forcing, c->d_step_idx, c->d_hcos);
   // precipitation (physics.py:253-354)
   QdPrecipAArgs Pa; memset(&Pa, 0, sizeof(Pa));
   Pa.u = F(c, QD_F_U); Pa.v = F(c, QD_F_V); Pa.pcond = F(c, QD_F_PCOND); Pa.nx = F(c, QD_F_OROG_NX); Pa.ny = F(c, QD_F_OROG_NY);
   Pa.pos = F(c, QD_F_X0); Pa.orog_raw = F(c, QD_F_X1); Pa.part = c->d_part[0]; Pa.ticket = c->d_ticket + 6 * c->batch;
+  Pa.forcing = c->d_forcing; Pa.step_idx = c->d_step_idx; Pa.hcos = c->d_hcos;      // this step's hour-angle cosines ride along
   BP(c, BL({Pa.u, 1}, {Pa.v, 1}, {Pa.pcond, 0}, {Pa.nx, 0}, {Pa.ny, 0}), BL(Pa.pos, Pa.orog_raw));
   QD_KR(c, k_precip_a, c->geo, Pa);
   if ((rc = band_allreduce(c, {QD_S_SUM_PQW}, false))) return rc;
@@ -1510,11 +1512,13 @@ static int loop_step_enqueue(qd_ctx* c, const qd_step_cfg_t* cfg) {
     return qd_fail(c, QD_E_STATE, "latitude bands: river routing is a global DAG and is not partitioned (SURVEY 8e)", cudaSuccess);
   if ((rc = loop_physics(c, cfg))) return rc;
   if ((rc = atmos_core(c, cfg, 1))) return rc;
-  if (cfg->with_ocean) { if ((rc = ocean_core(c, cfg, 1))) return rc; }
+  // the ocean's closing kernel advances the forcing-table index when it is the last field kernel of the step
+  c->polar_advances_step = (cfg->with_ocean && !(cfg->with_routing && c->route.ready)) ? 1 : 0;
+  if (cfg->with_ocean) { rc = ocean_core(c, cfg, 1); c->polar_advances_step = 0; if (rc) return rc; }
   if (cfg->with_routing && c->route.ready) {
     QD_K(c, k_route_accumulate, c->geo, F(c, QD_F_RLAND), c->route.d_land, c->route.d_buffer, cfg->dt);
   }
-  QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
+  if (!(cfg->with_ocean && !(cfg->with_routing && c->route.ready))) QD_KG(c, k_step_advance, dim3(1), dim3(32), c->d_step_idx);
   if (c->band_on) band_set_ext(c, 0);
   return QD_OK;
 }

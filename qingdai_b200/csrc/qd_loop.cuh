@@ -12,9 +12,13 @@ struct QdPrecipAArgs {
   const double *u, *v, *pcond, *nx, *ny;
   double *pos, *orog_raw, *part;
   unsigned* ticket;
+  const qd_forcing_t* forcing; const int* step_idx; double* hcos;    // first kernel of the step: also fills cos(hour angle) per column
 };
 __global__ void __launch_bounds__(QD_THREADS) k_precip_a(QdGeo g, QdPrecipAArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
+  if (A.hcos && blockIdx.y == 0) {           // forcing.py:118-131, consumed by k_column later in the step
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nlon; i += gridDim.x * blockDim.x) qd_forcing_col(g, A.forcing, A.step_idx, A.hcos, i);
+  }
   double contrib = 0.0;
   QD_CELL_LOOP(g) {
     QD_CELL_JI(g)

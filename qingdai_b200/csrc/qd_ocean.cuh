@@ -18,10 +18,12 @@ QD_HD bool qd_sub_done(const QdGeo& g, int b, const QdSubCtl& sc) {
 }
 
 // Wind stress (ocean.py:285-290) + the two maxima behind n_sub (ocean.py:298-299).
+QD_D void qd_ocean_nsub_member(const QdGeo& g, int b, double dt);
 struct QdOcPrepArgs {
   const double *u, *v, *uo, *vo;
   double *taux, *tauy, *part_u, *part_va;
   unsigned* ticket;
+  double dt; int* sub_ctr;   // sub_ctr != nullptr: the last block also derives n_sub (no cross-rank maxima pending)
 };
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
@@ -53,15 +55,13 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_prep(QdGeo g, QdOcPrepArgs
       double* S = g.scal + (size_t)b * QD_S_COUNT;
       S[QD_S_MAX_UOCEAN] = m1;
       S[QD_S_MAX_VA] = m2;
+      if (A.sub_ctr) { if (b == 0) *A.sub_ctr = 0; qd_ocean_nsub_member(g, b, A.dt); }
     }
   }
 }
 
 // n_sub = clip(ceil(max(c, uadv) * (dt / max(1e-12, dx_min)) / max(1e-3, cfl)), 1, 500)  (ocean.py:297-303)
-__global__ void k_ocean_nsub(QdGeo g, double dt, int* sub_ctr) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) *sub_ctr = 0;
-  if (b >= g.batch) return;
+QD_D void qd_ocean_nsub_member(const QdGeo& g, int b, double dt) {
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   double* S = g.scal + (size_t)b * QD_S_COUNT;
   const double c = sqrt(P[QD_P_OC_G] * P[QD_P_OC_H]);
@@ -72,6 +72,12 @@ __global__ void k_ocean_nsub(QdGeo g, double dt, int* sub_ctr) {
   if (n > 500.0) n = 500.0;
   S[QD_S_NSUB] = n;
   S[QD_S_SUB_DT] = dt / n;
+}
+__global__ void k_ocean_nsub(QdGeo g, double dt, int* sub_ctr) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *sub_ctr = 0;
+  if (b >= g.batch) return;
+  qd_ocean_nsub_member(g, b, dt);
 }
 
 // Momentum + land zeroing + polar sponge (ocean.py:306-336): A -> B.
@@ -276,9 +282,11 @@ struct QdOcPolarArgs {
   double *sst, *uo, *vo, *ts_atm;
   const uint8_t *land, *ice;
   int has_ice, inject;
+  int* step_idx;           // loop mode: the step counter of the forcing table advances here (last kernel of the step)
 };
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarArgs A) {
   const int b = blockIdx.y, north = blockIdx.x;
+  if (A.step_idx && b == 0 && north == 0 && threadIdx.x == 0) *A.step_idx = *A.step_idx + 1;
   const int j = north ? g.nlat - 1 : 0, n = g.nlon;
   if (!qd_owned(g, j)) return;               // latitude bands: the rank that owns the pole row (full longitude circle)
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
@@ -291,13 +299,31 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarAr
   const double* cl = g.cols + (size_t)QD_C_COS_LON * n;
   const double sgn = north ? -1.0 : 1.0;
   if (P[QD_P_OC_POLAR_FIX] != 0.0) {
-    const double cnt = qd_block_sum_n<0>(n, [&](int k) { return land[k] != 1 ? 1.0 : 0.0; });
+    // one sweep over the ring for the four sums (count, T, tangent-plane x / y)
+    __shared__ double tot[4];
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    QD_BLOCK_FIRST_FOR(k, n) {
+      if (land[k] != 1) {
+        const double u = U[k], v = V[k];
+        c0 += 1.0; c1 += T[k];
+        c2 += (-sl[k] * u + sgn * cl[k] * v);
+        c3 += (cl[k] * u + sgn * sl[k] * v);
+      }
+    }
+    double t;
+#if QD_EMU
+    if (threadIdx.x == 0) { tot[0] = c0; tot[1] = c1; tot[2] = c2; tot[3] = c3; }
+    (void)t;
+#else
+    if (qd_block_sum<0>(c0, &t)) tot[0] = t;
+    if (qd_block_sum<1>(c1, &t)) tot[1] = t;
+    if (qd_block_sum<2>(c2, &t)) tot[2] = t;
+    if (qd_block_sum<3>(c3, &t)) tot[3] = t;
+    __syncthreads();
+#endif
+    const double cnt = tot[0];
     if (cnt > 0.0) {
-      const double st = qd_block_sum_n<1>(n, [&](int k) { return land[k] != 1 ? T[k] : 0.0; });
-      const double sx = qd_block_sum_n<2>(n, [&](int k) { return land[k] != 1 ? (-sl[k] * U[k] + sgn * cl[k] * V[k]) : 0.0; });
-      const double sy = qd_block_sum_n<3>(n, [&](int k) { return land[k] != 1 ? (cl[k] * U[k] + sgn * sl[k] * V[k]) : 0.0; });
-      const double mt = st / cnt, mx = sx / cnt, my = sy / cnt;
-      __syncthreads();
+      const double mt = tot[1] / cnt, mx = tot[2] / cnt, my = tot[3] / cnt;
       QD_BLOCK_FIRST_FOR(k, n) {
         if (land[k] != 1) {
           T[k] = mt;

@@ -111,13 +111,15 @@ QD_HD void qd_seaice_cell(double Ts, double Q, double dt, int land, double h_ice
 
 // ------------------------------------------------------------------------------ forcing columns
 // cos(theta + lon - alpha) per column and star (forcing.py:126-131); one thread per column.
-__global__ void k_forcing_cols(QdGeo g, const qd_forcing_t* forcing, const int* step_idx, double* hcos /*[2][nlon]*/) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.nlon) return;
+QD_D void qd_forcing_col(const QdGeo& g, const qd_forcing_t* forcing, const int* step_idx, double* hcos /*[2][nlon]*/, int i) {
   const qd_forcing_t F = forcing[*step_idx];
   const double lon = g.cols[(size_t)QD_C_LON_RAD * g.nlon + i];
   hcos[i] = cos(F.theta + lon - F.alpha_a);
   hcos[g.nlon + i] = cos(F.theta + lon - F.alpha_b);
+}
+__global__ void k_forcing_cols(QdGeo g, const qd_forcing_t* forcing, const int* step_idx, double* hcos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.nlon) qd_forcing_col(g, forcing, step_idx, hcos, i);
 }
 
 // ------------------------------------------------------------------------------ column physics
