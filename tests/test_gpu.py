@@ -140,3 +140,7 @@ def test_network_builder_in_cuda_library(lib, golden, tag):
     for k in ("flow_to_index", "flow_order", "lake_mask", "lake_id"):
         assert np.array_equal(net[k], G[f"{tag}_{k}"]), k
     assert np.array_equal(net["elevation_filled"], G[f"{tag}_elev_filled"])
+
+
+def test_multiday_global_diagnostics(lib):
+    qdcheck.check_multiday(lib)

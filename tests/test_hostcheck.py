@@ -114,3 +114,7 @@ def test_global_diagnostics(lib):
 
 def test_config3_routing_and_ecology_in_one_loop(lib, golden):
     qdcheck.check_config3(lib, golden("routing_golden.npz"))
+
+
+def test_multiday_global_diagnostics(lib):
+    qdcheck.check_multiday(lib)
