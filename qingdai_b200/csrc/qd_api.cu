@@ -47,7 +47,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step;
+  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step, spec_attr_set;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -262,7 +262,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->cur_nblk = c->nblk;
-  c->h4_stream = 1; c->polar_advances_step = 0;
+  c->h4_stream = 1; c->polar_advances_step = 0; c->spec_attr_set = 0;
   c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
@@ -836,8 +836,22 @@ static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
   kcut = std::max(1, std::min(kN, kcut));
   const double fac = std::max(0.0, 1.0 - std::min(1.0, damp));
   BP(c, BL({fld, 0}), BL(fld));
-  QD_KG(c, k_zonal_bandstop, dim3((c->geo.sa1 - c->geo.sa0) + (c->geo.sb1 - c->geo.sb0), c->batch), dim3(QD_THREADS), c->geo, fld, c->d_twid, kcut, 1.0 - fac,
-        c->d_spec_coef, c->d_spec_out);
+  {
+    const dim3 grid((c->geo.sa1 - c->geo.sa0) + (c->geo.sb1 - c->geo.sb0), c->batch);
+#ifdef QD_HOST_EMU
+    QD_KG(c, k_zonal_bandstop, grid, dim3(QD_THREADS), c->geo, fld, c->d_twid, kcut, 1.0 - fac, c->d_spec_coef, c->d_spec_out);
+#else
+    const size_t shm = 3 * (size_t)c->nlon * sizeof(double);
+    if (shm > 200 * 1024) return qd_fail(c, QD_E_INVALID, "zonal band-stop: n_lon too large for the shared-memory DFT", cudaSuccess);
+    if (shm > 48 * 1024 && !c->spec_attr_set) {
+      QD_CUDA(c, cudaFuncSetAttribute(k_zonal_bandstop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      c->spec_attr_set = 1;
+    }
+    const int pi_ = qd_prof_begin(c, "k_zonal_bandstop");
+    k_zonal_bandstop<<<grid, dim3(QD_THREADS), shm, c->stream>>>(c->geo, fld, c->d_twid, kcut, 1.0 - fac, c->d_spec_coef, c->d_spec_out);
+    qd_prof_end(c, pi_); c->launches++;
+#endif
+  }
   QD_CHECK_LAUNCH(c);
   return QD_OK;
 }

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(QD_THREADS) k_divvort(QdGeo g, const double* u
 // dynamics.py:233-258: rfft -> bins >= kcut scaled by (1-damp) -> irfft.  Row-local equivalent used
 // here: y = x - d * HP(x), HP = projection on the stop band kcut..kN, evaluated as a real DFT
 // restricted to that band (n_lon*n_stop MACs forward and back per row); d = 1 - max(0, 1-min(1,damp)).
-// One block per (row, member).  twid = cos|sin(2 pi m / n) [2][nlon] from the host.
+// One block per (row, member).  twid = cos|sin(2 pi m / n) [2][nlon] from the host.  re/im (global scratch) are only
+// read back by the block that wrote them.
 __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* f, const double* twid,
                                                               int kcut, double d, double* coef, double* outbuf) {
   const int b = blockIdx.y, j = qd_seg_row(g, blockIdx.x), n = g.nlon;      // one block per row of the compute region
@@ -314,6 +315,43 @@ __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* 
   const int nstop = kN - kcut + 1;
   double* re = coef + ((size_t)b * g.nlat + j) * 2 * (size_t)(kN + 1);
   double* im = re + (kN + 1);
+#if !QD_EMU
+  // Shared-memory real DFT restricted to the stop band: the cleaned row and the cos / sin tables are staged once
+  // (3 n doubles, 69 KB at n = 2880); the phase index (k m) mod n advances by addition instead of a 64-bit modulo.
+  extern __shared__ double smem[];
+  double* xs = smem;                 // [n] nan_to_num(row)
+  double* ct = smem + n;             // [n]
+  double* st = smem + 2 * (size_t)n; // [n]
+  for (int m = threadIdx.x; m < n; m += blockDim.x) { xs[m] = qd_nan_to_num(row[m]); ct[m] = twid[m]; st[m] = twid[n + m]; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nstop; k += blockDim.x) {
+    const int kk = kcut + k;
+    double sr = 0.0, si = 0.0;
+    int ph = 0;
+    for (int m = 0; m < n; ++m) {
+      const double x = xs[m];
+      sr = sr + x * ct[ph];
+      si = si - x * st[ph];
+      ph += kk; if (ph >= n) ph -= n;
+    }
+    re[k] = sr; im[k] = si;
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    double acc = 0.0;
+    int ph = (int)(((long long)kcut * m) % n);
+    for (int k = 0; k < nstop; ++k) {
+      const int kk = kcut + k;
+      const bool nyq = (2 * kk == n);
+      const double wgt = (kk == 0 || nyq) ? 1.0 : 2.0;
+      const double term = nyq ? re[k] * ct[ph] : (re[k] * ct[ph] - im[k] * st[ph]);
+      acc = acc + wgt * term;
+      ph += m; if (ph >= n) ph -= n;
+    }
+    row[m] = qd_nan_to_num(xs[m] - d * (acc / (double)n));
+  }
+  (void)outbuf;
+#else
   double* orow = outbuf + (size_t)b * g.ncell + (size_t)j * n;
   const double* ct = twid;
   const double* st = twid + n;
@@ -344,6 +382,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* 
   }
   __syncthreads();
   QD_BLOCK_FIRST_FOR(m, n) { row[m] = orow[m]; }
+#endif
 }
 
 // ------------------------------------------------------------------------------ reductions

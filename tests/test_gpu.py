@@ -144,3 +144,7 @@ def test_network_builder_in_cuda_library(lib, golden, tag):
 
 def test_multiday_global_diagnostics(lib):
     qdcheck.check_multiday(lib)
+
+
+def test_bandstop_long_rows(lib):
+    qdcheck.check_bandstop_large(lib)

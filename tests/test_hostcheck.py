@@ -118,3 +118,7 @@ def test_config3_routing_and_ecology_in_one_loop(lib, golden):
 
 def test_multiday_global_diagnostics(lib):
     qdcheck.check_multiday(lib)
+
+
+def test_bandstop_long_rows(lib):
+    qdcheck.check_bandstop_large(lib)
