@@ -287,6 +287,16 @@ int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alph
 /* A_b^surface [B][nb][nlat][nlon] (NaN on ocean) from the cached canopy factor */
 int  qd_eco_bands(qd_ctx* ctx, int nb, const double* r_eff_host, double soil_ref, double* out_dev);
 
+/* ------------------------------------------------------------------ individual pool sub-steps
+ * IndividualPool.try_substep (pygcm/ecology/individuals.py:142-191) with the NB-band split of the dual-star insolation
+ * (spectral.dual_star_insolation_to_bands, spectral.py:388-426).  cell_host[n] = j * nlon + i of each individual's
+ * sampled cell, ab_host[n][nb], tol_host[n]; spec_a / spec_b / t_ray [nb] = per-star blackbody band weights and the
+ * Rayleigh factors.  qd_indiv_substep reads the context's per-star insolation fields QD_F_ISR_A / QD_F_ISR_B. */
+int  qd_indiv_setup(qd_ctx* ctx, int n_indiv, int nb, const int* cell_host, const double* ab_host, const double* tol_host,
+                    const double* spec_a, const double* spec_b, const double* t_ray);
+int  qd_indiv_substep(qd_ctx* ctx, const double* soil_dev, double soil_scalar, double period, double day_length);
+int  qd_indiv_state(qd_ctx* ctx, double* e_day_host, double* stress_host, int upload);
+
 /* ------------------------------------------------------------------ routing-network builder (host C++)
  * scripts/generate_hydrology_maps.py:85-273: pit_fill, compute_flow_to_index, identify_lakes, compute_lake_outlets,
  * topo_sort_flow_order with their sequential semantics (bit-identical outputs).  dist[3][nlat][3][3]: centre distance

@@ -113,6 +113,9 @@ PROTOTYPES = {
     "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
     "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),
     "qd_eco_bands": (_I, [_P, _I, _P, _D, _P]),
+    "qd_indiv_setup": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "qd_indiv_substep": (_I, [_P, _P, _D, _D, _D]),
+    "qd_indiv_state": (_I, [_P, _P, _P, _I]),
     "qd_net_build": (_I, [_I, _I, _P, _P, _P, _I, _D, _P, _P, _P, _P, _P, _P, C.POINTER(_I), C.POINTER(_I)]),
     "qd_diag_count": (_I, []),
     "qd_diag": (_I, [_P, _P]),

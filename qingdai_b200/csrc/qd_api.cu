@@ -7,6 +7,7 @@
 #include "qd_hyper4.cuh"
 #include "qd_eco.cuh"
 #include "qd_phyto.cuh"
+#include "qd_indiv.cuh"
 #include "qd_diag.cuh"
 #include <stdio.h>
 #include <stdlib.h>
@@ -81,6 +82,7 @@ struct qd_ctx {
   // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
   QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
+  QdIndivArgs indiv; int indiv_ready;                     // individual pool (qd_indiv.cuh); device arrays owned here
   double *d_diag_part, *d_diag_out;                       // qd_diag scratch
   double* d_phyto_tmp; size_t phyto_cap;                  // scratch of qd_phyto_advect_diffuse
   // ecology sub-daily (qd_eco.cuh)
@@ -270,6 +272,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   memset(c->band_peer_map, 0, sizeof(c->band_peer_map)); memset(c->band_shm, 0, sizeof(c->band_shm)); c->band_maxext = 0;
   for (int k = 0; k < QD_F_COUNT + QD_M_COUNT; ++k) c->band_valid[k] = 1 << 28;
   c->d_phyto_tmp = nullptr; c->phyto_cap = 0;
+  memset(&c->indiv, 0, sizeof(c->indiv)); c->indiv_ready = 0;
   c->d_lai = nullptr; c->eco_nl = 0; c->eco_every_nphys = 1; c->eco_steps = 0; c->eco_have_alpha = 0;
   c->eco_k = 0.5; c->eco_every_hours = 6.0; c->eco_delta = 0.05;
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
@@ -358,6 +361,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   qd_route_free(c->route);
   band_release(c);
   cudaFree(c->d_phyto_tmp); cudaFree(c->d_diag_part); cudaFree(c->d_diag_out);
+  cudaFree((void*)c->indiv.cell); cudaFree((void*)c->indiv.ab); cudaFree((void*)c->indiv.tol); cudaFree(c->indiv.e_day); cudaFree(c->indiv.stress);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
@@ -1064,6 +1068,57 @@ extern "C" int qd_eco_subdaily(qd_ctx* c, const double* isr, double dt, double* 
   QD_K(c, k_eco_cell, c->geo, A);
   QD_CHECK_LAUNCH(c);
   if (produced) *produced = want;
+  return QD_OK;
+}
+// Individual pool: static per-individual tables (cell index, per-band weights, drought tolerance) and the per-star
+// band spectra / Rayleigh factors (host NumPy, spectral.py:236-303); state (E_day, stress days) starts at zero.
+extern "C" int qd_indiv_setup(qd_ctx* c, int n, int nb, const int* cell_host, const double* ab_host, const double* tol_host,
+                              const double* spec_a, const double* spec_b, const double* t_ray) {
+  if (!c || n < 1 || nb < 1 || nb > QD_INDIV_MAX_BANDS || !cell_host || !ab_host || !tol_host || !spec_a || !spec_b || !t_ray) return QD_E_INVALID;
+  for (int k = 0; k < n; ++k) if (cell_host[k] < 0 || cell_host[k] >= c->ncell) return qd_fail(c, QD_E_INVALID, "qd_indiv_setup: cell index out of range", cudaSuccess);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QdIndivArgs& A = c->indiv;
+  cudaFree((void*)A.cell); cudaFree((void*)A.ab); cudaFree((void*)A.tol); cudaFree(A.e_day); cudaFree(A.stress);
+  memset(&A, 0, sizeof(A)); c->indiv_ready = 0;
+  A.n = n; A.nb = nb;
+  QD_CUDA(c, cudaMalloc((void**)&A.cell, (size_t)n * sizeof(int)));
+  QD_CUDA(c, cudaMalloc((void**)&A.ab, (size_t)n * nb * 8));
+  QD_CUDA(c, cudaMalloc((void**)&A.tol, (size_t)n * 8));
+  QD_CUDA(c, cudaMalloc((void**)&A.e_day, (size_t)n * 8));
+  QD_CUDA(c, cudaMalloc((void**)&A.stress, (size_t)n * 8));
+  QD_CUDA(c, cudaMemcpy((void*)A.cell, cell_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+  QD_CUDA(c, cudaMemcpy((void*)A.ab, ab_host, (size_t)n * nb * 8, cudaMemcpyHostToDevice));
+  QD_CUDA(c, cudaMemcpy((void*)A.tol, tol_host, (size_t)n * 8, cudaMemcpyHostToDevice));
+  QD_CUDA(c, cudaMemset(A.e_day, 0, (size_t)n * 8));
+  QD_CUDA(c, cudaMemset(A.stress, 0, (size_t)n * 8));
+  for (int k = 0; k < nb; ++k) { A.spec_a[k] = spec_a[k]; A.spec_b[k] = spec_b[k]; A.t_ray[k] = t_ray[k]; }
+  c->indiv_ready = 1;
+  return QD_OK;
+}
+// One fired sub-step (individuals.py:159-191) from the context's per-star insolation fields (member 0).
+// soil_dev: [nlat][nlon] soil index or NULL for the scalar.
+extern "C" int qd_indiv_substep(qd_ctx* c, const double* soil_dev, double soil_scalar, double period, double day_length) {
+  if (!c || !c->indiv_ready) return QD_E_STATE;
+  QD_BOUND(c);
+  QdIndivArgs A = c->indiv;
+  A.isr_a = F(c, QD_F_ISR_A); A.isr_b = F(c, QD_F_ISR_B); A.soil = soil_dev; A.soil_scalar = soil_scalar;
+  A.period = period; A.stress_inc = period / day_length;
+  QD_KG(c, k_indiv_substep, dim3((A.n + QD_THREADS - 1) / QD_THREADS), dim3(QD_THREADS), A);
+  QD_CHECK_LAUNCH(c);
+  return QD_OK;
+}
+// upload = 0: device -> host, 1: host -> device (the daily ecology on the host resets / edits the buffers)
+extern "C" int qd_indiv_state(qd_ctx* c, double* e_day_host, double* stress_host, int upload) {
+  if (!c || !c->indiv_ready || !e_day_host || !stress_host) return QD_E_INVALID;
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t nb = (size_t)c->indiv.n * 8;
+  if (upload) {
+    QD_CUDA(c, cudaMemcpy(c->indiv.e_day, e_day_host, nb, cudaMemcpyHostToDevice));
+    QD_CUDA(c, cudaMemcpy(c->indiv.stress, stress_host, nb, cudaMemcpyHostToDevice));
+  } else {
+    QD_CUDA(c, cudaMemcpy(e_day_host, c->indiv.e_day, nb, cudaMemcpyDeviceToHost));
+    QD_CUDA(c, cudaMemcpy(stress_host, c->indiv.stress, nb, cudaMemcpyDeviceToHost));
+  }
   return QD_OK;
 }
 // Global diagnostics of every member in one launch (qd_diag.cuh); out_host [B][QD_DIAG_COUNT].  Sync.

@@ -233,8 +233,9 @@ class EcologyAdapter:
             self.pop = PopulationState.__new__(PopulationState)
             self.pop._substep_every = self.substep_every_nphys
             PopulationState.__init__(self.pop, engine, self.land_mask, env)
-            R = [reflectance_from_peaks(self.bands, gene_peaks_from_env(
-                f"QD_ECO_SPECIES_{i}_" if (f"QD_ECO_SPECIES_{i}_PEAKS" in env) else "QD_ECO_GENE_", env)) for i in range(self.pop.Ns)]
+            # adapter.py:93-100: every species reads its own QD_ECO_SPECIES_{i}_* genes (defaults when unset)
+            R = [reflectance_from_peaks(self.bands, gene_peaks_from_env(f"QD_ECO_SPECIES_{i}_", env)) for i in range(self.pop.Ns)]
+            self.species_drought_tol = [_envf(env, f"QD_ECO_SPECIES_{i}_DROUGHT_TOL", 0.3) for i in range(self.pop.Ns)]   # genes.py:84
             self.pop.set_species_reflectance_bands(np.stack(R, axis=0))   # adapter.py:86-112
         else:                                                            # M1: alpha = clip(alpha_leaf_scalar) on land
             engine.bind_eco(None, 0, 0.5, 6.0, 0.05, self.substep_every_nphys)

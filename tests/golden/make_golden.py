@@ -564,6 +564,56 @@ def gen_phyto():
     print("phyto_golden.npz:", len(out), "arrays")
 
 
+# ------------------------------------------------------------------------------------ individual pool sub-steps
+def gen_indiv():
+    """IndividualPool.try_substep (pygcm/ecology/individuals.py:142-191) with the NB=16 band split of the dual-star
+    insolation (spectral.dual_star_insolation_to_bands, spectral.py:304-426).  SURVEY 8f row 2."""
+    from pygcm.grid import SphericalGrid
+    from pygcm.ecology import EcologyAdapter
+    from pygcm.ecology.individuals import IndividualPool
+    from pygcm.ecology.spectral import dual_star_insolation_to_bands
+    out = {}
+    cases = {"i1": ({}, (19, 36)),
+             "i2": ({"QD_ECO_NS": "4", "QD_ECO_SPECIES_WEIGHTS": "0.4,0.3,0.2,0.1", "QD_ECO_RAND_SEED": "3", "QD_ECO_TOA_TO_SURF_MODE": "rayleigh",
+                     "QD_ECO_INDIV_SAMPLE_FRAC": "0.2", "QD_ECO_INDIV_PER_CELL": "7", "QD_ECO_INDIV_SUBSTEPS_PER_DAY": "24",
+                     "QD_ECO_SPECIES_2_PEAKS": "520:30:0.9", "QD_ECO_SPECIES_1_DROUGHT_TOL": "0.7"}, (15, 27))}
+    for tag, (env, (nlat, nlon)) in cases.items():
+        set_env(env)
+        rng = np.random.default_rng(700 + nlat)
+        grid = SphericalGrid(nlat, nlon)
+        land = (rng.uniform(size=(nlat, nlon)) < 0.45).astype(np.uint8)
+        with quiet():
+            eco = EcologyAdapter(grid, land)
+            pool = IndividualPool(grid, land, eco, diag=False)
+        out[f"{tag}_env"] = np.array(repr(env))
+        out[f"{tag}_land"] = land
+        for k in ("sample_j", "sample_i", "indiv_cell_index", "indiv_species_id", "indiv_Ab", "indiv_tol", "sp_weights"):
+            out[f"{tag}_{k}"] = np.array(getattr(pool, k))
+        out[f"{tag}_cfg"] = np.array([pool.cfg.sample_frac, pool.cfg.per_cell, pool.cfg.substeps_per_day, pool.nb], dtype=float)
+        dt, day = 1800.0, 72000.0
+        out[f"{tag}_dt"], out[f"{tag}_day"] = np.array(dt), np.array(day)
+        ncalls = 12
+        out[f"{tag}_ncalls"] = np.array(ncalls)
+        for n in range(ncalls):
+            isrA = np.maximum(0.0, rng.standard_normal((nlat, nlon)) * 250.0 + 150.0)
+            isrB = np.maximum(0.0, rng.standard_normal((nlat, nlon)) * 120.0 + 20.0)
+            if n == 4:
+                isrA[:, : nlon // 2] = 0.0
+                isrB[:, : nlon // 2] = 0.0                             # night side
+            soil = rng.uniform(0.0, 1.0, (nlat, nlon))
+            out[f"{tag}_c{n}_isrA"], out[f"{tag}_c{n}_isrB"], out[f"{tag}_c{n}_soil"] = isrA, isrB, soil
+            e0 = pool.indiv_E_day.copy()
+            pool.try_substep(isrA, isrB, eco, soil, dt, day)
+            out[f"{tag}_c{n}_fired"] = np.array(not np.array_equal(e0, pool.indiv_E_day) or n == 4)
+            out[f"{tag}_c{n}_E"] = pool.indiv_E_day.copy()
+            out[f"{tag}_c{n}_stress"] = pool.indiv_water_stress_days.copy()
+            out[f"{tag}_c{n}_accum"] = np.array(pool._substep_accum)
+        Ib = dual_star_insolation_to_bands(isrA, isrB, eco.bands)
+        out[f"{tag}_Ib_last"] = Ib
+    np.savez_compressed(os.path.join(OUT, "indiv_golden.npz"), **out)
+    print("indiv_golden.npz:", len(out), "arrays")
+
+
 def gen_routing():
     """Network from the reference's own builder (scripts/generate_hydrology_maps.py:85-273) on a small
     procedural elevation, then pygcm.routing.RiverRouting (unmodified, fed through an in-memory stand-in
@@ -636,6 +686,8 @@ def main():
         gen_eco()
     if "phyto" in which:
         gen_phyto()
+    if "indiv" in which:
+        gen_indiv()
 
 
 if __name__ == "__main__":

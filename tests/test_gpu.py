@@ -148,3 +148,8 @@ def test_multiday_global_diagnostics(lib):
 
 def test_bandstop_long_rows(lib):
     qdcheck.check_bandstop_large(lib)
+
+
+@pytest.mark.parametrize("tag", ["i1", "i2"])
+def test_individual_pool_substeps(lib, golden, tag):
+    qdcheck.check_indiv(lib, golden("indiv_golden.npz"), tag)
