@@ -90,8 +90,8 @@ class Simulation:
         e.set_counters(0, 0, 0)
 
     def forcing_for(self, t):
-        (fa, sa, ca, aa), (fb, sb, cb, ab) = self.forcing.star_geometry(t)[0]
-        return Forcing(t, fa, sa, ca, aa, fb, sb, cb, ab, self.forcing.star_geometry(t)[1])
+        ((fa, sa, ca, aa), (fb, sb, cb, ab)), theta = self.forcing.star_geometry(t)
+        return Forcing(t, fa, sa, ca, aa, fb, sb, cb, ab, theta)
 
     def step(self, nsteps=1):
         done = 0
