@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=0, help="oracle steps for cpu_baseline (0 = auto, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--all-kernels", action="store_true", help="list every kernel in roofline.top_kernels")
     ap.add_argument("--halo", type=int, default=16, help="latitude bands: halo rows per exchange")
     ap.add_argument("--replicas", action="store_true", help="hires at N>1: independent replicas instead of latitude bands")
     args = ap.parse_args()
@@ -326,7 +327,7 @@ def main():
                 "share_of_step": ms / tot,
                 "whole_step": {"alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "note": "233 B/cell-step (SURVEY 8d) over the whole fused step"},
-                "top_kernels": [{"kernel": r[0], "launches_per_step": r[1] / nprof, "us_per_launch": r[2] / r[1] * 1e3, "share": r[2] / tot} for r in rows[:(40 if band else 8)]]}
+                "top_kernels": [{"kernel": r[0], "launches_per_step": r[1] / nprof, "us_per_launch": r[2] / r[1] * 1e3, "share": r[2] / tot} for r in rows[:(40 if (band or args.all_kernels) else 8)]]}
 
     # -------- CPU baseline (oracle port, rank 0, N=1 only)
     cpu = None

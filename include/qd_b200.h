@@ -249,6 +249,7 @@ int  qd_use_graphs(qd_ctx* ctx, int enable);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */
+int  qd_set_gauss2d(qd_ctx* ctx, int enable);                 /* 0: force the two-pass Gaussian kernels (tests); default 1 */
 int  qd_set_h4_stream(qd_ctx* ctx, int enable);               /* 0: force the tile kernel for del^4 (tests); default 1 */
 int  qd_launch_count(qd_ctx* ctx, long long* out);            /* kernels launched so far */
 /* per-kernel device time: CUDA events on the launching stream around every launch while enabled */

@@ -101,6 +101,7 @@ PROTOTYPES = {
     "qd_use_graphs": (_I, [_P, _I]),
     "qd_set_counters": (_I, [_P, _I, _I, _I]),
     "qd_get_counters": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "qd_set_gauss2d": (_I, [_P, _I]),
     "qd_set_h4_stream": (_I, [_P, _I]),
     "qd_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "qd_profile": (_I, [_P, _I]),

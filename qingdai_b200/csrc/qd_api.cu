@@ -6,6 +6,7 @@
 #include "qd_loop.cuh"
 #include "qd_hyper4.cuh"
 #include "qd_eco.cuh"
+#include "qd_gauss2d.cuh"
 #include "qd_phyto.cuh"
 #include "qd_indiv.cuh"
 #include "qd_diag.cuh"
@@ -48,7 +49,7 @@ struct qd_route {
 };
 
 struct qd_ctx {
-  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step, spec_attr_set;
+  int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step, spec_attr_set, g2_fused;
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
@@ -264,7 +265,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->nlat = nlat; c->nlon = nlon; c->ncell = nlat * nlon; c->batch = batch; c->device = device;
   c->nblk = (c->ncell + QD_THREADS - 1) / QD_THREADS;
   c->cur_nblk = c->nblk;
-  c->h4_stream = 1; c->polar_advances_step = 0; c->spec_attr_set = 0;
+  c->h4_stream = 1; c->polar_advances_step = 0; c->spec_attr_set = 0; c->g2_fused = 1;
   c->red_blk = std::max(1, c->nblk / 3);          // host check build: exercise the grid-stride loops
   c->stream = 0; c->fields = nullptr; c->masks = nullptr; c->launches = 0;
   c->atm_counter = 0; c->oc_counter = 0; c->has_cloud_eff = 0; c->last_nsub_max = 1;
@@ -429,6 +430,8 @@ extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double*
   return QD_OK;
 }
 // test / tuning switch: 0 forces the shared-memory tile kernel for del^4 at every size (default 1: large grids stream)
+// test / tuning switch: 0 forces the two-pass Gaussian kernels at every size (default 1: large grids use the fused tile kernel)
+extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->g2_fused = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->h4_stream = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
@@ -816,8 +819,49 @@ extern "C" int qd_set_gauss(qd_ctx* c, int which, int radius, int wrap, const do
   c->w_set |= (1 << (which ? 1 : 0));
   return QD_OK;
 }
-static int op_gauss(qd_ctx* c, int n, double* const* fld, double* const* scratch, const QdGaussW& w) {
+#ifndef QD_HOST_EMU
+// Fused two-axis Gaussian (qd_gauss2d.cuh) over every segment of the compute region.
+template <int MODE>
+static int launch_gauss2d(qd_ctx* c, QdG2Args A, const QdGaussW& w, const std::vector<BIn>& ins, const std::vector<const void*>& outs, const char* name) {
+  BPV(c, ins, outs);
+  const int tiles_i = (c->nlon + QD_G2_TI - 1) / QD_G2_TI;
+  const int seg[2][2] = {{c->geo.sa0, c->geo.sa1}, {c->geo.sb0, c->geo.sb1}};
+  for (int q = 0; q < 2; ++q) {
+    if (seg[q][1] <= seg[q][0]) continue;
+    A.row0 = seg[q][0]; A.row1 = seg[q][1];
+    const int tiles_j = (A.row1 - A.row0 + QD_G2_TJ - 1) / QD_G2_TJ;
+    const dim3 grid(tiles_i * tiles_j, c->batch), block(QD_G2_NX, QD_G2_NY);
+    if (w.r == 4) QD_KGN(c, name, (k_gauss2d_tile<MODE, 4>), grid, block, c->geo, A, w);          // sigma = 1 (physics.py:44,69,111,159,330)
+    else if (w.r == 1) QD_KGN(c, name, (k_gauss2d_tile<MODE, 1>), grid, block, c->geo, A, w);     // sigma = 0.2 (run_simulation.py:1931)
+    else QD_KGN(c, name, (k_gauss2d_tile<MODE, 0>), grid, block, c->geo, A, w);
+  }
+  return QD_OK;
+}
+// large grids only: at 181x360 a launch has 72 tiles (< 148 SMs) and the two short passes are faster
+static inline bool gauss2d_ok(qd_ctx* c, const QdGaussW& w) {
+  const long long tiles = (long long)((c->nlon + QD_G2_TI - 1) / QD_G2_TI) * ((c->nlat + QD_G2_TJ - 1) / QD_G2_TJ) * c->batch;
+  return c->g2_fused && w.r >= 1 && w.r <= QD_G2_RMAX && tiles >= 2 * 148;
+}
+#endif
+// in place on fld[k] (two-pass form); with `out` given and the fused kernel available the result is left in out[k]
+// instead (fld untouched, no intermediate field) and *in_out is set
+static int op_gauss(qd_ctx* c, int n, double* const* fld, double* const* scratch, const QdGaussW& w, bool* in_out = nullptr) {
+  if (in_out) *in_out = false;
   if (w.r == 0) return QD_OK;
+#ifndef QD_HOST_EMU
+  if (in_out && gauss2d_ok(c, w)) {
+    for (int k0 = 0; k0 < n; k0 += 2) {
+      QdG2Args A; memset(&A, 0, sizeof(A));
+      A.n = std::min(2, n - k0);
+      std::vector<BIn> bi; std::vector<const void*> bo;
+      for (int k = 0; k < A.n; ++k) { A.src[k] = fld[k0 + k]; A.dst[k] = scratch[k0 + k]; bi.push_back({fld[k0 + k], w.r}); bo.push_back(scratch[k0 + k]); }
+      int rc = launch_gauss2d<QD_G2_PLAIN>(c, A, w, bi, bo, "k_gauss2d_tile<plain>"); if (rc) return rc;
+    }
+    QD_CHECK_LAUNCH(c);
+    *in_out = true;
+    return QD_OK;
+  }
+#endif
   QdFields a = mk_fields(n), b2 = mk_fields(n);
   std::vector<BIn> i1, i2; std::vector<const void*> o1, o2;
   for (int k = 0; k < n; ++k) {
@@ -908,7 +952,11 @@ extern "C" int qd_gaussian(qd_ctx* c, double* f, double* scratch, int radius, in
   if (!c || !f || !scratch || !weights || radius < 0 || radius > QD_GAUSS_MAXR) return QD_E_INVALID;
   const QdGaussW w = mk_gauss_w(radius, wrap, weights);
   double* fl[1] = {f}; double* sc[1] = {scratch};
-  return op_gauss(c, 1, fl, sc, w);
+  bool moved = false;
+  int rc = op_gauss(c, 1, fl, sc, w, &moved);
+  if (rc) return rc;
+  if (moved) QD_CUDA(c, cudaMemcpyAsync(f, scratch, (size_t)c->batch * c->ncell * 8, cudaMemcpyDeviceToDevice, c->stream));
+  return QD_OK;
 }
 extern "C" int qd_zonal_bandstop(qd_ctx* c, double* f, double cutoff, double damp) {
   if (!c || !f) return QD_E_INVALID;
@@ -1524,34 +1572,57 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   BP(c, BL({Pa.u, 1}, {Pa.v, 1}, {Pa.pcond, 0}, {Pa.nx, 0}, {Pa.ny, 0}), BL(Pa.pos, Pa.orog_raw));
   QD_KR(c, k_precip_a, c->geo, Pa);
   if ((rc = band_allreduce(c, {QD_S_SUM_PQW}, false))) return rc;
-  if (orog) { double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X2)}; if ((rc = op_gauss(c, 1, fl, sx, w1))) return rc; }
+  double* orog_f = F(c, QD_F_X1);
+  if (orog) {
+    double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X5)}; bool moved = false;
+    if ((rc = op_gauss(c, 1, fl, sx, w1, &moved))) return rc;
+    if (moved) orog_f = sx[0];
+  }
   if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT))) return rc;
   QdPrecipBArgs Pb; memset(&Pb, 0, sizeof(Pb));
-  Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = F(c, QD_F_X1); Pb.praw = F(c, QD_F_X2);
+  Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = orog_f; Pb.praw = F(c, QD_F_X2);
   Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
   BP(c, BL({Pb.pos, 0}, {Pb.pcond, 0}, {Pb.orog, 0}), BL(Pb.praw));
   QD_KR(c, k_precip_b, c->geo, Pb);
   if ((rc = band_allreduce(c, {QD_S_SUM_PRAWW}, false))) return rc;
-  QdPrecipCArgs Pc; Pc.praw = F(c, QD_F_X2); Pc.pos = F(c, QD_F_X0); Pc.g0 = F(c, QD_F_X3); Pc.g1 = F(c, QD_F_X4);
-  BP(c, BL({Pc.praw, w1.r}, {Pc.pos, w1.r}, {Pc.g1, 0}), BL(Pc.g0, Pc.g1));
-  QD_K(c, k_precip_c, c->geo, Pc, w1);
-  QdPrecipDArgs Pd; Pd.g0 = F(c, QD_F_X3); Pd.g1 = F(c, QD_F_X4); Pd.precip = F(c, QD_F_PRECIP);
-  BP(c, BL({Pd.g0, 0}, {Pd.g1, 0}), BL(Pd.precip));
-  QD_K(c, k_precip_d, c->geo, Pd, w1);
+  bool fused = false;
+#ifndef QD_HOST_EMU
+  fused = gauss2d_ok(c, w1);
+  if (fused) {       // Gaussian of P_raw * s (and of k_precip * pos in the fallback) + blend + clip in one tile kernel
+    QdG2Args A; memset(&A, 0, sizeof(A));
+    A.n = 2; A.src[0] = F(c, QD_F_X2); A.src[1] = F(c, QD_F_X0); A.dst[0] = F(c, QD_F_PRECIP);
+    if ((rc = launch_gauss2d<QD_G2_PRECIP>(c, A, w1, {{A.src[0], w1.r}, {A.src[1], w1.r}}, {A.dst[0]}, "k_gauss2d_tile<precip>"))) return rc;
+  }
+#endif
+  if (!fused) {
+    QdPrecipCArgs Pc; Pc.praw = F(c, QD_F_X2); Pc.pos = F(c, QD_F_X0); Pc.g0 = F(c, QD_F_X3); Pc.g1 = F(c, QD_F_X4);
+    BP(c, BL({Pc.praw, w1.r}, {Pc.pos, w1.r}, {Pc.g1, 0}), BL(Pc.g0, Pc.g1));
+    QD_K(c, k_precip_c, c->geo, Pc, w1);
+    QdPrecipDArgs Pd; Pd.g0 = F(c, QD_F_X3); Pd.g1 = F(c, QD_F_X4); Pd.precip = F(c, QD_F_PRECIP);
+    BP(c, BL({Pd.g0, 0}, {Pd.g1, 0}), BL(Pd.precip));
+    QD_K(c, k_precip_d, c->geo, Pd, w1);
+  }
   // clouds (run_simulation.py:1866-1934)
   if ((rc = op_median(c, F(c, QD_F_PRECIP), 1e-6, c->d_scal + QD_S_PREF, c->d_scal + QD_S_CNT_PRECIP, QD_S_COUNT))) return rc;
   QdCloudAArgs Ca; Ca.precip = F(c, QD_F_PRECIP); Ca.ts = F(c, QD_F_TS); Ca.u = F(c, QD_F_U); Ca.v = F(c, QD_F_V);
   Ca.craw = F(c, QD_F_X0); Ca.sraw = F(c, QD_F_X1);
   BP(c, BL({Ca.precip, 0}, {Ca.ts, 1}, {Ca.u, 1}, {Ca.v, 1}), BL(Ca.craw, Ca.sraw));
   QD_K(c, k_cloud_a, c->geo, Ca);
-  {
+#ifndef QD_HOST_EMU
+  if (fused) {
+    QdG2Args A; memset(&A, 0, sizeof(A));
+    A.n = 2; A.src[0] = F(c, QD_F_X0); A.src[1] = F(c, QD_F_X1); A.dst[0] = F(c, QD_F_CLOUD); A.dt = dt;
+    if ((rc = launch_gauss2d<QD_G2_CLOUD_B>(c, A, w1, {{A.src[0], w1.r}, {A.src[1], w1.r}, {A.dst[0], 0}}, {A.dst[0]}, "k_gauss2d_tile<cloud_b>"))) return rc;
+  }
+#endif
+  if (!fused) {
     QdFields f = mk_fields(2); f.src[0] = F(c, QD_F_X0); f.src[1] = F(c, QD_F_X1); f.dst[0] = F(c, QD_F_X2); f.dst[1] = F(c, QD_F_X3);
     BP(c, BL({f.src[0], w1.r}, {f.src[1], w1.r}), BL(f.dst[0], f.dst[1]));
     QD_K(c, k_gauss_lat, c->geo, f, w1);
+    QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt;
+    BP(c, BL({Cb.g0, 0}, {Cb.g1, 0}, {Cb.cloud, 0}), BL(Cb.cloud));
+    QD_K(c, k_cloud_b, c->geo, Cb, w1);
   }
-  QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt;
-  BP(c, BL({Cb.g0, 0}, {Cb.g1, 0}, {Cb.cloud, 0}), BL(Cb.cloud));
-  QD_K(c, k_cloud_b, c->geo, Cb, w1);
   if (P[QD_P_CLOUD_ADVECT] != 0.0) {
     QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X0);
     BP(c, BL({f.src[0], band_radv(c, dt)}, {F(c, QD_F_U), 0}, {F(c, QD_F_V), 0}), BL(f.dst[0]));
@@ -1560,15 +1631,26 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
     QdGaussW wc = c->w_cloud;
     if (!(sig > 0.0)) wc.r = 0;
     const double* src = F(c, QD_F_X0);
-    if (wc.r > 0) {
-      QdFields g1 = mk_fields(1); g1.src[0] = F(c, QD_F_X0); g1.dst[0] = F(c, QD_F_X1);
-      BP(c, BL({g1.src[0], wc.r}), BL(g1.dst[0]));
-      QD_K(c, k_gauss_lat, c->geo, g1, wc);
-      src = F(c, QD_F_X1);
+    bool fused_c = false;
+#ifndef QD_HOST_EMU
+    fused_c = gauss2d_ok(c, wc);
+    if (fused_c) {
+      QdG2Args A; memset(&A, 0, sizeof(A));
+      A.n = 1; A.src[0] = F(c, QD_F_X0); A.dst[0] = F(c, QD_F_CLOUD);
+      if ((rc = launch_gauss2d<QD_G2_CLOUD_C>(c, A, wc, {{A.src[0], wc.r}, {A.dst[0], 0}}, {A.dst[0]}, "k_gauss2d_tile<cloud_c>"))) return rc;
     }
-    QdCloudCArgs Cc; Cc.g0 = src; Cc.cloud = F(c, QD_F_CLOUD);
-    BP(c, BL({Cc.g0, 0}, {Cc.cloud, 0}), BL(Cc.cloud));
-    QD_K(c, k_cloud_c, c->geo, Cc, wc);
+#endif
+    if (!fused_c) {
+      if (wc.r > 0) {
+        QdFields g1 = mk_fields(1); g1.src[0] = F(c, QD_F_X0); g1.dst[0] = F(c, QD_F_X1);
+        BP(c, BL({g1.src[0], wc.r}), BL(g1.dst[0]));
+        QD_K(c, k_gauss_lat, c->geo, g1, wc);
+        src = F(c, QD_F_X1);
+      }
+      QdCloudCArgs Cc; Cc.g0 = src; Cc.cloud = F(c, QD_F_CLOUD);
+      BP(c, BL({Cc.g0, 0}, {Cc.cloud, 0}), BL(Cc.cloud));
+      QD_K(c, k_cloud_c, c->geo, Cc, wc);
+    }
   }
   QD_CHECK_LAUNCH(c);
   return QD_OK;

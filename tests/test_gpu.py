@@ -153,3 +153,11 @@ def test_bandstop_long_rows(lib):
 @pytest.mark.parametrize("tag", ["i1", "i2"])
 def test_individual_pool_substeps(lib, golden, tag):
     qdcheck.check_indiv(lib, golden("indiv_golden.npz"), tag)
+
+
+def test_gaussian_fused_tile_kernel(lib):
+    qdcheck.check_gauss2d_large(lib)
+
+
+def test_large_grid_kernels_match_small_grid_kernels(lib):
+    qdcheck.check_large_grid_paths_agree(lib)

@@ -127,3 +127,7 @@ def test_bandstop_long_rows(lib):
 @pytest.mark.parametrize("tag", ["i1", "i2"])
 def test_individual_pool_substeps(lib, golden, tag):
     qdcheck.check_indiv(lib, golden("indiv_golden.npz"), tag)
+
+
+def test_gaussian_fused_tile_kernel(lib):
+    qdcheck.check_gauss2d_large(lib)
