@@ -93,6 +93,7 @@ typedef enum {
   QD_R_AREA,          /* cell area m^2 (routing) */
   QD_R_INV_ACOS_HALF, /* 1/(a*max(cos,0.5)): ocean pressure-gradient metric (ocean.py:309) */
   QD_R_INV_ACOS_CAP,  /* 1/(a*max(cos,1e-6)): divergence / vorticity metric (grid.py:66,87) */
+  QD_R_IAC_ADV_ATM,   /* RN(1/(a*max(1e-6,cos))): exact-division helper of the atmospheric departure points (dynamics.py:104) */
   QD_R_COUNT
 } qd_row_id;
 

@@ -280,7 +280,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
 #endif
-  const size_t nrows = (size_t)(QD_R_COUNT + 6 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
+  const size_t nrows = (size_t)(QD_R_COUNT + 7 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
 #define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
   QD_ALLOC(c->d_rows, (size_t)batch * nrows * 8);
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
@@ -333,7 +333,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.nlat = nlat; g.nlon = nlon; g.ncell = c->ncell; g.batch = batch;
   g.a = a; g.dlat = dlat; g.dlon = dlon; g.a_sq = a_sq; g.dlon_sq = dlon_sq;
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
-  g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a;
+  g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a; g.inv_dlon = 1.0 / dlon;
   g.own0 = 0; g.own1 = nlat; g.sa0 = 0; g.sa1 = nlat; g.sb0 = 0; g.sb1 = 0; g.ncomp = c->ncell;
   g.div_nlon = (1ull << 40) / (unsigned long long)nlon + 1ull;
   if ((unsigned long long)c->ncell * (unsigned long long)nlon >= (1ull << 40)) { delete c; return QD_E_INVALID; }
@@ -407,14 +407,15 @@ extern "C" int qd_get_scalars(qd_ctx* c, double* out) {
   QD_CUDA(c, cudaMemcpy(out, c->d_scal, (size_t)c->batch * QD_S_COUNT * 8, cudaMemcpyDeviceToHost));
   return QD_OK;
 }
-extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + 6 * QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
-#define QD_USER_ROW(c, slot) ((c)->d_rows + (size_t)(QD_R_COUNT + 6 * (slot)) * (c)->nlat)
+extern "C" const double* qd_row_dev(qd_ctx* c, int id) { return (c && id >= 0 && id < QD_R_COUNT + 7 * QD_NUSER_ROWS) ? ROW(c, id) : nullptr; }
+#define QD_USER_ROW(c, slot) ((c)->d_rows + (size_t)(QD_R_COUNT + 7 * (slot)) * (c)->nlat)
 extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_host) {
   if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host) return nullptr;
   cudaStreamSynchronize(c->stream);
-  std::vector<double> tmp(6 * (size_t)c->nlat);
+  std::vector<double> tmp(7 * (size_t)c->nlat);
   for (int j = 0; j < c->nlat; ++j) tmp[j] = rows_host[j];
   qd_cos_companions(c->geo, c->nlat, tmp.data());
+  for (int j = 0; j < c->nlat; ++j) tmp[6 * (size_t)c->nlat + j] = 1.0 / (c->geo.a * rows_host[j]);    // RN(1/(a c)): gather departure points
   double* dst = QD_USER_ROW(c, slot);
   for (int b = 0; b < c->batch; ++b)
     if (cudaMemcpy(dst + (size_t)b * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
@@ -423,9 +424,10 @@ extern "C" const double* qd_user_row(qd_ctx* c, int slot, const double* rows_hos
 extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double* rows_host) {
   if (!c || slot < 0 || slot >= QD_NUSER_ROWS || !rows_host || member < 0 || member >= c->batch) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  std::vector<double> tmp(6 * (size_t)c->nlat);
+  std::vector<double> tmp(7 * (size_t)c->nlat);
   for (int j = 0; j < c->nlat; ++j) tmp[j] = rows_host[j];
   qd_cos_companions(c->geo, c->nlat, tmp.data());
+  for (int j = 0; j < c->nlat; ++j) tmp[6 * (size_t)c->nlat + j] = 1.0 / (c->geo.a * rows_host[j]);    // RN(1/(a c)): gather departure points
   QD_CUDA(c, cudaMemcpy(QD_USER_ROW(c, slot) + (size_t)member * c->geo.row_bstride, tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
   return QD_OK;
 }
@@ -921,6 +923,14 @@ static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst
   return QD_OK;
 }
 
+// RN(1/(a c)) row that belongs to a cosine row table handed to the operator API, or null (plain divisions)
+static const double* qd_iac_for(qd_ctx* c, const double* cosr) {
+  if (cosr == ROW(c, QD_R_COS_ADV_ATM)) return ROW(c, QD_R_IAC_ADV_ATM);
+  if (cosr == ROW(c, QD_R_COS_ADV_HALF)) return ROW(c, QD_R_INV_ACOS_HALF);
+  for (int slot = 0; slot < QD_NUSER_ROWS; ++slot) if (cosr == QD_USER_ROW(c, slot)) return cosr + 6 * (size_t)c->nlat;
+  return nullptr;
+}
+
 // ------------------------------------------------------------------------------ operator C ABI
 extern "C" int qd_laplacian(qd_ctx* c, const double* in, double* out, const double* cosr) {
   if (!c || !in || !out || !cosr) return QD_E_INVALID;
@@ -939,7 +949,7 @@ extern "C" int qd_hyperdiffuse(qd_ctx* c, double* f, double* scratch, const doub
 extern "C" int qd_advect(qd_ctx* c, const double* in, const double* u, const double* v, double* out, double dt, const double* cosr) {
   if (!c || !in || !u || !v || !out || !cosr) return QD_E_INVALID;
   QdFields f = mk_fields(1); f.src[0] = in; f.dst[0] = out;
-  QD_K(c, k_advect, c->geo, f, u, v, dt, cosr);
+  QD_K(c, k_advect, c->geo, f, u, v, dt, cosr, qd_iac_for(c, cosr));
   QD_CHECK_LAUNCH(c);
   return QD_OK;
 }
@@ -1336,7 +1346,7 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   {
     QdFields f = mk_fields(1); f.src[0] = cur[iC]; f.dst[0] = F(c, QD_F_X9);
     BP(c, BL({f.src[0], band_radv(c, dt)}, {cur[iU], 0}, {cur[iV], 0}), BL(f.dst[0]));
-    QD_K(c, k_advect, c->geo, f, cur[iU], cur[iV], dt, ROW(c, QD_R_COS_ADV_ATM));
+    QD_K(c, k_advect, c->geo, f, cur[iU], cur[iV], dt, ROW(c, QD_R_COS_ADV_ATM), ROW(c, QD_R_IAC_ADV_ATM));
     QdTailArgs T; memset(&T, 0, sizeof(T));
     T.u_in = cur[iU]; T.v_in = cur[iV]; T.h_in = cur[iH]; T.q_in = cur[iQ];
     T.u = F(c, QD_F_U); T.v = F(c, QD_F_V); T.h = F(c, QD_F_H); T.ts = F(c, QD_F_TS); T.q = F(c, QD_F_Q); T.cloud = F(c, QD_F_CLOUD);
@@ -1626,7 +1636,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (P[QD_P_CLOUD_ADVECT] != 0.0) {
     QdFields f = mk_fields(1); f.src[0] = F(c, QD_F_CLOUD); f.dst[0] = F(c, QD_F_X0);
     BP(c, BL({f.src[0], band_radv(c, dt)}, {F(c, QD_F_U), 0}, {F(c, QD_F_V), 0}), BL(f.dst[0]));
-    QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_HALF));
+    QD_K(c, k_advect, c->geo, f, F(c, QD_F_U), F(c, QD_F_V), dt, ROW(c, QD_R_COS_ADV_HALF), ROW(c, QD_R_INV_ACOS_HALF));
     const double sig = P[QD_P_CLOUD_SMOOTH_SIGMA];
     QdGaussW wc = c->w_cloud;
     if (!(sig > 0.0)) wc.r = 0;

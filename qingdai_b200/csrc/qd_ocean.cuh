@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
     A.eta[c] = e;
     if (qd_owned(g, j)) contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
     double y, x;
-    qd_departure(A.ub[c], A.vb[c], sub_dt, g.a, qd_row(g, QD_R_COS_ADV_HALF)[j], g.dlat, g.dlon, j, i, &y, &x);
+    qd_departure(A.ub[c], A.vb[c], sub_dt, g, qd_row(g, QD_R_COS_ADV_HALF)[j], qd_row(g, QD_R_INV_ACOS_HALF)[j], j, i, &y, &x);
     const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
     A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
   }

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_advect_momentum(QdGeo g, QdAdvMo
   const double dt = A.dt;
   const double u0 = A.u[c], v0 = A.v[c];
   double y, x;
-  qd_departure(u0, v0, dt, g.a, qd_row(g, QD_R_COS_ADV_ATM)[j], g.dlat, g.dlon, j, i, &y, &x);
+  qd_departure(u0, v0, dt, g, qd_row(g, QD_R_COS_ADV_ATM)[j], qd_row(g, QD_R_IAC_ADV_ATM)[j], j, i, &y, &x);
   const double adv_t = qd_bilinear_wrap(A.ts_pre + off, g.nlat, g.nlon, y, x);
   const double adv_q = qd_bilinear_wrap(A.q_pre + off, g.nlat, g.nlon, y, x);
   A.ts[c] = (1.0 - 0.2) * A.ts_pre[c] + 0.2 * adv_t;

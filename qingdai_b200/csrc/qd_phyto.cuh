@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_phyto_advect(QdGeo g, QdPhytoArg
   QD_CELL_PROLOGUE(g)                      // b = species
   if (!active) return;
   double y, x;
-  qd_departure(A.uo[idx], A.vo[idx], A.dt, g.a, qd_row(g, QD_R_COS_ADV_HALF)[j], g.dlat, g.dlon, j, i, &y, &x);
+  qd_departure(A.uo[idx], A.vo[idx], A.dt, g, qd_row(g, QD_R_COS_ADV_HALF)[j], qd_row(g, QD_R_INV_ACOS_HALF)[j], j, i, &y, &x);
   const double* Cs = A.C + off;
   const double adv = qd_bilinear_wrap(Cs, g.nlat, g.nlon, y, x);
   A.tmp[off + idx] = (1.0 - A.alpha) * Cs[idx] + A.alpha * adv;

@@ -87,6 +87,7 @@ def row_tables(nlat, nlon, p: QDParams, dt):
     rows[R["area"]] = (a * a) * dlam * band
     rows[R["inv_acos_half"]] = 1.0 / (a * rows[R["cos_adv_half"]])
     rows[R["inv_acos_cap"]] = 1 / (a * rows[R["cos_cap"]])            # grid.py:66 evaluates exactly this factor
+    rows[R["iac_adv_atm"]] = 1.0 / (a * rows[R["cos_adv_atm"]])       # correctly rounded reciprocal of the divisor in dynamics.py:104
     cols = np.zeros((NC, nlon), dtype=np.float64)
     lon_rad = np.deg2rad(lon)
     cols[ENUM["QD_C_LON_RAD"]] = lon_rad
