@@ -53,6 +53,7 @@ struct qd_ctx {
   cudaStream_t stream;
   QdGeo geo;
   double *d_rows, *d_cols, *d_prm, *d_scal, *h_prm;
+  QdRcp* d_udiv = nullptr; double udiv_dt = 0.0; int udiv_valid = 0;   // derived divisor table (qd_derive)
   double* fields; uint8_t* masks;
   double* d_part[QD_NPART]; unsigned* d_ticket;
   unsigned* d_hist; unsigned long long* d_mingt; int sel_gx;
@@ -286,6 +287,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
   QD_ALLOC(c->d_prm, (size_t)batch * QD_P_COUNT * 8);
   QD_ALLOC(c->d_scal, (size_t)batch * QD_S_COUNT * 8);
+  QD_ALLOC(c->d_udiv, (size_t)batch * QD_U_COUNT * sizeof(QdRcp));
   for (int k = 0; k < QD_NPART; ++k) QD_ALLOC(c->d_part[k], (size_t)batch * c->nblk * 8);
   QD_ALLOC(c->d_ticket, (size_t)batch * 8 * sizeof(unsigned));
   QD_ALLOC(c->d_hist, (size_t)QD_SEL_PASSES * batch * QD_SEL_MAXBINS * sizeof(unsigned));
@@ -337,7 +339,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.own0 = 0; g.own1 = nlat; g.sa0 = 0; g.sa1 = nlat; g.sb0 = 0; g.sb1 = 0; g.ncomp = c->ncell;
   g.div_nlon = (1ull << 40) / (unsigned long long)nlon + 1ull;
   if ((unsigned long long)c->ncell * (unsigned long long)nlon >= (1ull << 40)) { delete c; return QD_E_INVALID; }
-  g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal;
+  g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal; g.udiv = c->d_udiv;
   for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { delete c; return QD_E_CUDA; }
   if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
   *out = c;
@@ -354,7 +356,7 @@ static void qd_route_free(qd_route& r) {
 extern "C" int qd_destroy(qd_ctx* c) {
   if (!c) return QD_E_INVALID;
   cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal);
+  cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal); cudaFree(c->d_udiv);
   for (int k = 0; k < QD_NPART; ++k) cudaFree(c->d_part[k]);
   cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_sel_list); cudaFree(c->d_sel_cnt); cudaFree(c->d_sel_more); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
   cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
@@ -387,6 +389,7 @@ extern "C" int qd_set_params(qd_ctx* c, const double* p) {
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
   memcpy(c->h_prm, p, (size_t)c->batch * QD_P_COUNT * 8);
   QD_CUDA(c, cudaMemcpy(c->d_prm, p, (size_t)c->batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice));
+  c->udiv_valid = 0;
   return QD_OK;
 }
 extern "C" int qd_set_rows(qd_ctx* c, const double* rows) {
@@ -1233,6 +1236,46 @@ extern "C" int qd_eco_bands(qd_ctx* c, int nb, const double* r_eff, double soil,
   return QD_OK;
 }
 
+// The per-member table of parameter-only divisors (QdUdivId in qd_ops.cuh): every entry is the reference's divisor
+// expression evaluated in fp64 on the host plus its correctly rounded reciprocal, rebuilt only when the parameters or
+// dt change.  Called by the step entry points before anything is enqueued or captured.
+static int qd_derive(qd_ctx* c, double dt) {
+  if (c->udiv_valid && c->udiv_dt == dt) return QD_OK;
+  std::vector<QdRcp> T((size_t)c->batch * QD_U_COUNT);
+  for (int b = 0; b < c->batch; ++b) {
+    const double* P = c->h_prm + (size_t)b * QD_P_COUNT;
+    QdRcp* D = T.data() + (size_t)b * QD_U_COUNT;
+    D[QD_U_MCOL] = qd_rcp(fmax(1e-6, P[QD_P_RHO_A] * P[QD_P_H_MBL]));
+    D[QD_U_TAU_COND] = qd_rcp(fmax(1e-6, P[QD_P_TAU_COND]));
+    D[QD_U_RHO_SNOW] = qd_rcp(qd_max(P[QD_P_RHO_SNOW], 1e-6));
+    D[QD_U_1000] = qd_rcp(1000.0);
+    D[QD_U_SNOW_BAND] = qd_rcp(qd_max(1e-6, P[QD_P_SNOW_T_BAND]));
+    D[QD_U_DT] = qd_rcp(dt);
+    D[QD_U_SWE_REF] = qd_rcp(qd_max(1e-6, P[QD_P_SWE_REF]));
+    D[QD_U_SIGMA] = qd_rcp(QD_SIGMA_SB);
+    D[QD_U_RUNOFF_TAU] = qd_rcp(fmax(1.0, P[QD_P_RUNOFF_TAU_DAYS] * 86400.0));
+    D[QD_U_C_SFC] = qd_rcp(fmax(1e-12, P[QD_P_C_SFC]));
+    D[QD_U_TAU_RAD] = qd_rcp(P[QD_P_TAU_RAD]);
+    D[QD_U_HICE_REF] = qd_rcp(qd_max(1e-6, P[QD_P_HICE_REF]));
+    D[QD_U_RHO_I_LF] = qd_rcp(P[QD_P_RHO_I] * P[QD_P_L_F]);
+    D[QD_U_CS_LAND] = qd_rcp(qd_seaice_cs(P[QD_P_CS_LAND]));
+    D[QD_U_CS_ICE] = qd_rcp(qd_seaice_cs(P[QD_P_CS_ICE]));
+    D[QD_U_CS_OCEAN] = qd_rcp(qd_seaice_cs(P[QD_P_CS_OCEAN]));
+    D[QD_U_ATM] = qd_rcp(fmax(1e-6, P[QD_P_RHO_A]) * fmax(1.0, P[QD_P_ATM_H]) * P[QD_P_G]);
+    D[QD_U_12K] = qd_rcp(12.0);
+    D[QD_U_ADV_REF] = qd_rcp(2e-5);
+    D[QD_U_2DY] = qd_rcp(2 * (c->geo.dlat * c->geo.a));
+    D[QD_Q_G_CP].b = D[QD_Q_G_CP].r = P[QD_P_G] / 1004.0;
+    D[QD_Q_R_G].b = D[QD_Q_R_G].r = 287 / P[QD_P_G];
+    D[QD_Q_DDF].b = D[QD_Q_DDF].r = P[QD_P_SNOW_DDF] / 86400.0;
+    D[QD_Q_MELT].b = D[QD_Q_MELT].r = P[QD_P_SNOW_MELT_RATE] / 86400.0;
+  }
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));          // a step in flight may still be reading the old table
+  QD_CUDA(c, cudaMemcpy(c->d_udiv, T.data(), T.size() * sizeof(QdRcp), cudaMemcpyHostToDevice));
+  c->udiv_dt = dt; c->udiv_valid = 1;
+  return QD_OK;
+}
+
 static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
   const double dt = cfg->dt;
   const int has_alb = mode_loop ? cfg->loop_with_albedo : cfg->has_albedo;
@@ -1367,6 +1410,7 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
 extern "C" int qd_atmos_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (!c || !cfg) return QD_E_INVALID;
   QD_BOUND(c);
+  { const int rc = qd_derive(c, cfg->dt); if (rc) return rc; }
   return atmos_core(c, cfg, 0);
 }
 
@@ -1621,7 +1665,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
 #ifndef QD_HOST_EMU
   if (fused) {
     QdG2Args A; memset(&A, 0, sizeof(A));
-    A.n = 2; A.src[0] = F(c, QD_F_X0); A.src[1] = F(c, QD_F_X1); A.dst[0] = F(c, QD_F_CLOUD); A.dt = dt;
+    A.n = 2; A.src[0] = F(c, QD_F_X0); A.src[1] = F(c, QD_F_X1); A.dst[0] = F(c, QD_F_CLOUD); A.dt = dt / (6 * 3600);
     if ((rc = launch_gauss2d<QD_G2_CLOUD_B>(c, A, w1, {{A.src[0], w1.r}, {A.src[1], w1.r}, {A.dst[0], 0}}, {A.dst[0]}, "k_gauss2d_tile<cloud_b>"))) return rc;
   }
 #endif
@@ -1629,7 +1673,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
     QdFields f = mk_fields(2); f.src[0] = F(c, QD_F_X0); f.src[1] = F(c, QD_F_X1); f.dst[0] = F(c, QD_F_X2); f.dst[1] = F(c, QD_F_X3);
     BP(c, BL({f.src[0], w1.r}, {f.src[1], w1.r}), BL(f.dst[0], f.dst[1]));
     QD_K(c, k_gauss_lat, c->geo, f, w1);
-    QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt;
+    QdCloudBArgs Cb; Cb.g0 = F(c, QD_F_X2); Cb.g1 = F(c, QD_F_X3); Cb.cloud = F(c, QD_F_CLOUD); Cb.dt = dt / (6 * 3600);
     BP(c, BL({Cb.g0, 0}, {Cb.g1, 0}, {Cb.cloud, 0}), BL(Cb.cloud));
     QD_K(c, k_cloud_b, c->geo, Cb, w1);
   }
@@ -1749,6 +1793,7 @@ static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
 extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps) {
   if (!c || !cfg || !forcing || nsteps < 1) return QD_E_INVALID;
   QD_BOUND(c);
+  { const int rc = qd_derive(c, cfg->dt); if (rc) return rc; }
   if (nsteps > c->forcing_cap) {
     QD_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->d_forcing);

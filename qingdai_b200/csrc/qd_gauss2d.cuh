@@ -21,7 +21,7 @@ struct QdG2Args {
   int n;                               // inputs
   const double* src[2];
   double* dst[2];                      // PLAIN: one output per input; otherwise dst[0] is the call site's output field
-  double dt;                           // CLOUD_B
+  double dt;                           // CLOUD_B: dt / (6 * 3600), the quotient formed on the host
   int row0, row1;                      // output rows of this launch (latitude bands: one launch per segment)
 };
 
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(QD_G2_NX * QD_G2_NY) k_gauss2d_tile(QdGeo g, Q
     } else if (MODE == QD_G2_CLOUD_B) {                           // k_cloud_b
       const double C_P = qd_clip(res[0][m], 0.0, 1.0);
       const double src = qd_clip(res[1][m], 0.0, 1.0);
-      const double tend = src * (A.dt / (6 * 3600));
+      const double tend = src * A.dt;
       double cl = A.dst[0][c];
       cl = P[QD_P_W_MEM] * cl + P[QD_P_W_P] * C_P + P[QD_P_W_SRC] * qd_clip(cl + tend, 0.0, 1.0);
       if (P[QD_P_CLOUD_FLOOR] > 0.0) cl = qd_max(cl, qd_clip(P[QD_P_CLOUD_FLOOR] * C_P, 0.0, 1.0));

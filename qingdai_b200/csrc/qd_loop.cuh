@@ -48,14 +48,14 @@ struct QdPrecipBArgs {
 __global__ void __launch_bounds__(QD_THREADS) k_precip_b(QdGeo g, QdPrecipBArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double contrib = 0.0;
+  // the median scale is the same for every cell of a member (one reciprocal per thread, amortised over its cells);
+  // pos is zero wherever the flow diverges
+  const QdRcp scale = qd_rcp(fmax(qd_scal(g, (int)blockIdx.y, QD_S_MED_POS), 1e-12));
   QD_CELL_LOOP(g) {
     QD_CELL_JI(g)
     const size_t c = off + idx;
     double F_div = 0.0;
-    if (qd_scal(g, b, QD_S_CNT_POS) > 0.0) {
-      const double scale = fmax(qd_scal(g, b, QD_S_MED_POS), 1e-12);
-      F_div = qd_clip(A.pos[c] / scale, 0.0, 5.0);
-    }
+    if (qd_scal(g, b, QD_S_CNT_POS) > 0.0) F_div = qd_clip(qd_div_u(A.pos[c], scale), 0.0, 5.0);
     double F_or = 1.0;
     if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) F_or = qd_clip(A.orog[c], 1.0, 3.0);
     const double F = (1.0 + P[QD_P_BETA_DIV] * F_div) * F_or;
@@ -124,36 +124,36 @@ __global__ void __launch_bounds__(QD_THREADS) k_precip_d(QdGeo g, QdPrecipDArgs 
 struct QdCloudAArgs { const double *precip, *ts, *u, *v; double *craw, *sraw; };
 __global__ void __launch_bounds__(QD_THREADS) k_cloud_a(QdGeo g, QdCloudAArgs A) {
   QD_CELL_PROLOGUE(g)
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;
   if (!active) return;
   const size_t c = off + idx;
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const int nlon = g.nlon, nlat = g.nlat;
   double P_ref = 1e-6;
   if (qd_scal(g, b, QD_S_CNT_PRECIP) > 0.0) {
     const double ov = P[QD_P_PREF];
     P_ref = (ov == ov) ? ov : qd_scal(g, b, QD_S_PREF);
   }
-  A.craw[c] = P[QD_P_CMAX] * tanh(A.precip[c] / (P_ref + 1e-12));
+  A.craw[c] = P[QD_P_CMAX] * tanh(qd_div_z(A.precip[c], P_ref + 1e-12));      // dry cells have precip == 0
   // source
   const double* T = A.ts + off;
   const double Ts = T[idx], u = A.u[c], v = A.v[c];
-  double src = 0.5 * qd_clip(tanh((Ts - 285.0) / 12.0), 0.0, 1.0);
+  double src = 0.5 * qd_clip(tanh(qd_div_u(Ts - 285.0, D[QD_U_12K])), 0.0, 1.0);
   const double vort = qd_vort_cell(A.u + off, A.v + off, j, i, g);
-  const double rel = vort / (qd_row(g, QD_R_FCOR)[j] + 1e-12);
+  const double rel = qd_div_z(vort, qd_row(g, QD_R_FCOR)[j] + 1e-12);
   src = src + 0.4 * qd_clip(tanh((rel - 0.5) / 2.0), 0.0, 1.0);
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
   const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;
   const double dx = g.dlon * g.a * qd_row(g, QD_R_COS_ADV_ATM)[j];
-  const double dy = g.dlat * g.a;
-  const double gx = (T[(size_t)j * nlon + ip] - T[(size_t)j * nlon + im]) / (2 * dx);
-  const double gy = (T[(size_t)jp * nlon + i] - T[(size_t)jm * nlon + i]) / (2 * dy);
+  const double gx = qd_div_z(T[(size_t)j * nlon + ip] - T[(size_t)j * nlon + im], 2 * dx);
+  const double gy = qd_div_u(T[(size_t)jp * nlon + i] - T[(size_t)jm * nlon + i], D[QD_U_2DY]);
   const double adv = -(u * gx + v * gy);
-  src = src + 0.3 * qd_clip(tanh(fabs(adv) / 2e-5), 0.0, 1.0);
+  src = src + 0.3 * qd_clip(tanh(qd_div_u(fabs(adv), D[QD_U_ADV_REF])), 0.0, 1.0);
   A.sraw[c] = src;
 }
 // ---- cloud phase B: Gaussian along longitude of both fields, then the blend
 //      (run_simulation.py:1890-1913)
-struct QdCloudBArgs { const double *g0, *g1; double* cloud; double dt; };
+struct QdCloudBArgs { const double *g0, *g1; double* cloud; double dt; /* dt / (6 * 3600), formed on the host */ };
 __global__ void __launch_bounds__(QD_THREADS) k_cloud_b(QdGeo g, QdCloudBArgs A, QdGaussW w) {
   QD_CELL_PROLOGUE(g)
   if (!active) return;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_cloud_b(QdGeo g, QdCloudBArgs A,
   auto E1 = [&](int ii) -> double { return r1[ii]; };
   const double C_P = qd_clip(qd_gauss_tap(E0, i, g.nlon, w), 0.0, 1.0);
   const double src = qd_clip(qd_gauss_tap(E1, i, g.nlon, w), 0.0, 1.0);
-  const double tend = src * (A.dt / (6 * 3600));
+  const double tend = src * A.dt;
   double cl = A.cloud[c];
   cl = P[QD_P_W_MEM] * cl + P[QD_P_W_P] * C_P + P[QD_P_W_SRC] * qd_clip(cl + tend, 0.0, 1.0);
   if (P[QD_P_CLOUD_FLOOR] > 0.0) cl = qd_max(cl, qd_clip(P[QD_P_CLOUD_FLOOR] * C_P, 0.0, 1.0));

@@ -235,22 +235,24 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   double uo = qd_nan_to_num(ub[idx]), vo = qd_nan_to_num(vb[idx]);
   const double cap = P[QD_P_OC_MAX_U];
   const double speed = sqrt(uo * uo + vo * vo);
-  if (P[QD_P_OC_MEAN4] != 0.0) {
-    if (speed > cap) {
+  if (speed > cap) {
+    // ocean.py:408-434.  Cells at or below the cap (and NaN speeds) fall through unchanged: there the reference
+    // multiplies by exactly 1.0, so skipping the second sqrt and the scale is bit-identical.
+    if (P[QD_P_OC_MEAN4] != 0.0) {
       const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
       const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;
       const size_t n_ = (size_t)jp * nlon + i, s_ = (size_t)jm * nlon + i, e_ = (size_t)j * nlon + ip, w_ = (size_t)j * nlon + im;
       uo = 0.25 * (qd_nan_to_num(ub[n_]) + qd_nan_to_num(ub[s_]) + qd_nan_to_num(ub[e_]) + qd_nan_to_num(ub[w_]));
       vo = 0.25 * (qd_nan_to_num(vb[n_]) + qd_nan_to_num(vb[s_]) + qd_nan_to_num(vb[e_]) + qd_nan_to_num(vb[w_]));
+      const double sp2 = sqrt(uo * uo + vo * vo);
+      const double sc2 = (sp2 > cap) ? cap / (sp2 + 1e-12) : 1.0;
+      uo = uo * sc2;
+      vo = vo * sc2;
+    } else {
+      const double sc1 = cap / (speed + 1e-12);
+      uo = uo * sc1;
+      vo = vo * sc1;
     }
-    const double sp2 = sqrt(uo * uo + vo * vo);
-    const double sc2 = (sp2 > cap) ? cap / (sp2 + 1e-12) : 1.0;
-    uo = uo * sc2;
-    vo = vo * sc2;
-  } else {
-    const double sc1 = (speed > cap) ? cap / (speed + 1e-12) : 1.0;
-    uo = uo * sc1;
-    vo = vo * sc1;
   }
   A.uo[c] = uo;
   A.vo[c] = vo;

@@ -14,6 +14,37 @@
 #define QD_GAUSS_MAXR 8
 #define QD_SIGMA_SB 5.670374e-8   /* constants.py:10 */
 
+// A divisor with its correctly rounded reciprocal (qd_div_u below), or a ready quotient in .r
+struct alignas(16) QdRcp { double b, r; };
+// Per-member table of the parameter-only divisors and quotients of the physics kernels, formed on the host whenever
+// the parameters or dt change (qd_derive in qd_api.cu).  The expressions are the reference's, operand for operand.
+enum QdUdivId {
+  QD_U_MCOL = 0,      // max(1e-6, rho_a h_mbl)                humidity.py:160-176
+  QD_U_TAU_COND,      // max(1e-6, tau_cond)
+  QD_U_RHO_SNOW,      // max(rho_snow, 1e-6)                   run_simulation.py:1962
+  QD_U_1000,          // 1000 (m per km of the lapse rate)
+  QD_U_SNOW_BAND,     // max(1e-6, snow_t_band)                hydrology.py:121
+  QD_U_DT,            // dt
+  QD_U_SWE_REF,       // max(1e-6, swe_ref)
+  QD_U_SIGMA,         // Stefan-Boltzmann constant
+  QD_U_RUNOFF_TAU,    // max(1, runoff_tau_days 86400)         hydrology.py:244
+  QD_U_C_SFC,         // max(1e-12, c_sfc)                     dynamics.py:316
+  QD_U_TAU_RAD,       // tau_rad
+  QD_U_HICE_REF,      // max(1e-6, H_ice_ref)
+  QD_U_RHO_I_LF,      // rho_i L_f                             energy.py:340-372
+  QD_U_CS_LAND, QD_U_CS_ICE, QD_U_CS_OCEAN,   // heat capacities after the 1e3 sanitiser, energy.py:395-399
+  QD_U_ATM,           // max(1e-6, rho_a) max(1, H_atm) g      energy.py:476-480
+  QD_U_12K,           // 12 K                                  physics.py:94
+  QD_U_ADV_REF,       // 2e-5 K/s                              physics.py:107
+  QD_U_2DY,           // 2 (dlat a)                            physics.py:103
+  QD_U_NDIV,
+  QD_Q_G_CP = QD_U_NDIV,   // .r = g / 1004
+  QD_Q_R_G,                // .r = 287 / g
+  QD_Q_DDF,                // .r = snow_ddf / 86400
+  QD_Q_MELT,               // .r = snow_melt_rate / 86400
+  QD_U_COUNT
+};
+
 struct QdGeo {
   int nlat, nlon, ncell, batch;
   double a, dlat, dlon, a_sq, dlon_sq;
@@ -24,6 +55,7 @@ struct QdGeo {
   const double* cols;    // [QD_C_COUNT][nlon]
   const double* prm;     // [B][QD_P_COUNT]
   double* scal;          // [B][QD_S_COUNT]
+  const QdRcp* udiv;     // [B][QD_U_COUNT]
   // Latitude-band decomposition (qd_band.cuh).  Every rank stores full-size fields but computes only the
   // rows of up to two segments [sa0,sa1) u [sb0,sb1) (its own rows [own0,own1) widened by the halo the
   // inputs allow; the second segment is the part that wraps over a pole).  One rank: sa = own = [0, nlat).
@@ -202,6 +234,43 @@ __device__ __forceinline__ double qd_div_exact(double x, double b, double y) {
   return __fma_rn(r, y, q);
 }
 #endif
+// ---- divisions by block-uniform divisors
+// nvcc's inline fp64 division is ~25 instructions and sends the whole warp through a 64-instruction out-of-line slow
+// path whenever a numerator is zero -- dry cells, open ocean, the night side: 7.5 slow-path calls per warp in k_column,
+// a quarter of its instructions (profiles/README.md).  For divisors that are the same for every cell of a block
+// (parameters, dt) the host forms RN(1/b) once (QdGeo::udiv); the cell code then gets the correctly rounded quotient
+// from qd_div_exact.  Outside the range where its residuals are exact it falls back to
+// an exact shortcut (zero numerator) or to the plain division, so every path returns the bits of x / b.
+QD_HD QdRcp qd_rcp(double b) {
+  QdRcp d;
+  d.b = b;
+  d.r = (fabs(b) > 1e-100 && fabs(b) < 1e100) ? 1.0 / b : NAN;      // NaN: always take the plain division
+  return d;
+}
+QD_HD double qd_div_u(double x, const QdRcp& d) {
+#if !QD_EMU && defined(__CUDA_ARCH__)
+  const double q = x * d.r;
+  const unsigned e = ((unsigned)__double2hiint(q) >> 20) & 0x7ffu;  // biased exponent of the first estimate
+  if (e - 523u < 1000u) {                                           // 2^-500 <= |q| < 2^500: residuals are exact
+    double r = __fma_rn(-d.b, q, x);
+    const double q1 = __fma_rn(r, d.r, q);
+    r = __fma_rn(-d.b, q1, x);
+    return __fma_rn(r, d.r, q1);
+  }
+  if (x == 0.0 && d.r == d.r) return q;                             // +-0 with the sign of x / b
+  return x / d.b;
+#else
+  return x / d.b;
+#endif
+}
+// x / b for a per-cell divisor: only skips the slow path of a zero numerator (0 / b = +-0 for any non-zero, non-NaN b)
+QD_HD double qd_div_z(double x, double b) {
+#if !QD_EMU && defined(__CUDA_ARCH__)
+  if (x == 0.0 && b == b && b != 0.0)
+    return __hiloint2double((__double2hiint(x) ^ __double2hiint(b)) & 0x80000000, 0);
+#endif
+  return x / b;
+}
 // departure point of cell (j,i): dynamics.py:104-115.  iac = RN(1 / (a cosj)) from the row tables, or 0 when the
 // caller has no such table (then the quotients are plain divisions).
 QD_HD void qd_departure(double u, double v, double dt, const QdGeo& g, double cosj, double iac,

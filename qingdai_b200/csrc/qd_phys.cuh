@@ -77,29 +77,33 @@ QD_HD QdLW qd_longwave(double Ts, double Ta, double cloud, int land, double ice_
 QD_HD double qd_ice_frac(double h_ice, double href) {              // dynamics.py:362, run_simulation.py:2065
   return 1.0 - exp(-qd_max(h_ice, 0.0) / qd_max(1e-6, href));
 }
+QD_HD double qd_ice_frac_u(double h_ice, const QdRcp& href) {      // same, href = RN-reciprocal pair of max(1e-6, H_ice_ref)
+  return 1.0 - exp(qd_div_u(-qd_max(h_ice, 0.0), href));
+}
 QD_HD double qd_sensible(double Ts, double Ta, double u, double v, const double* P) {   // energy.py:439-442
   const double V = sqrt(u * u + v * v);
   return P[QD_P_RHO_A] * P[QD_P_CP_AIR] * P[QD_P_C_H] * V * (Ts - Ta);
 }
-// energy.py:291-420 for one cell.  pole_row: 1 = south row, 2 = north row, 0 otherwise.
-QD_HD void qd_seaice_cell(double Ts, double Q, double dt, int land, double h_ice, int pole_row,
-                          const double* P, double* Ts_out, double* hice_out) {
+QD_HD double qd_seaice_cs(double Cs) { return (isfinite(Cs) && (Cs > 1e3)) ? Cs : 1e3; }    // energy.py:395-399
+// energy.py:291-420 for one cell.  pole_row: 1 = south row, 2 = north row, 0 otherwise.  D: the member's divisor table
+// (rho_i L_f, dt and the three sanitised heat capacities are the same for every cell).
+QD_HD void qd_seaice_cell_u(double Ts, double Q, double dt, int land, double h_ice, int pole_row,
+                            const double* P, const QdRcp* D, double* Ts_out, double* hice_out) {
   const bool ocean = !land;
   double Tn = Ts, hi = h_ice;
   const double rho_i = P[QD_P_RHO_I], L_f = P[QD_P_L_F], t_frz = P[QD_P_T_FREEZE];
   if ((hi > 0.0) && ocean && (Q > 0.0)) {
-    const double dh = qd_min((Q * dt) / (rho_i * L_f), hi);
+    const double dh = qd_min(qd_div_u(Q * dt, D[QD_U_RHO_I_LF]), hi);
     hi = hi - dh;
-    Q = Q - (dh * rho_i * L_f) / dt;
+    Q = Q - qd_div_u(dh * rho_i * L_f, D[QD_U_DT]);
   }
   if (ocean && (Q < 0.0) && (Tn <= (t_frz + 0.5))) {
-    hi = hi + (-Q * dt) / (rho_i * L_f);
+    hi = hi + qd_div_u(-Q * dt, D[QD_U_RHO_I_LF]);
     Q = 0.0;
     Tn = qd_min(Tn, t_frz);
   }
-  double Cs = land ? P[QD_P_CS_LAND] : ((hi > 0.0) ? P[QD_P_CS_ICE] : P[QD_P_CS_OCEAN]);
-  if (!(isfinite(Cs) && (Cs > 1e3))) Cs = 1e3;
-  Tn = Tn + (Q / Cs) * dt;
+  const QdRcp& Cs = land ? D[QD_U_CS_LAND] : ((hi > 0.0) ? D[QD_U_CS_ICE] : D[QD_U_CS_OCEAN]);
+  Tn = Tn + qd_div_u(Q, Cs) * dt;
   if ((pole_row == 1 && P[QD_P_POLAR_FIX_S] != 0.0) || (pole_row == 2 && P[QD_P_POLAR_FIX_N] != 0.0)) {
     if (ocean && (Q < 0.0) && (Tn > t_frz)) Tn = t_frz;
   }
@@ -148,24 +152,25 @@ struct QdColArgs {
 
 __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
   QD_CELL_PROLOGUE(g)
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;
+  const double dt = A.dt;
   if (!active) return;
   const size_t c = off + idx;
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
-  const double dt = A.dt;
   const int land = A.land[c] == 1;
   const double h = A.h[c], Ts = A.ts[c], q0 = A.q[c], u = A.u[c], v = A.v[c], hice = A.hice[c];
   // ---- humidity (dynamics.py:274-297, humidity.py:145-183): start-of-step Ts, q, u, v, h
-  const double Ta = 288.0 + (P[QD_P_G] / 1004.0) * h;
+  const double Ta = 288.0 + D[QD_Q_G_CP].r * h;
   const double fac = qd_evap_factor(land, hice, P[QD_P_EVAP_OCEAN], P[QD_P_EVAP_LAND], P[QD_P_EVAP_ICE]);
   const double V = sqrt(u * u + v * v);
   const double deficit = qd_max(0.0, qd_qsat(Ts, P[QD_P_P0]) - q0);
   const double E = qd_nan_to_num(P[QD_P_RHO_A] * P[QD_P_C_E] * V * deficit * fac);
   const double LH = P[QD_P_L_V] * E;
-  const double M_col = fmax(1e-6, P[QD_P_RHO_A] * P[QD_P_H_MBL]);
-  const double q_evap = q0 + (E / M_col) * dt;
+  const double M_col = D[QD_U_MCOL].b;
+  const double q_evap = q0 + qd_div_u(E, D[QD_U_MCOL]) * dt;
   const double excess = qd_max(0.0, q_evap - qd_qsat(Ta, P[QD_P_P0]));
-  double P_cond = (excess / fmax(1e-6, P[QD_P_TAU_COND])) * M_col;
-  double q_next = q_evap - (P_cond / M_col) * dt;
+  double P_cond = qd_div_u(excess, D[QD_U_TAU_COND]) * M_col;
+  double q_next = q_evap - qd_div_u(P_cond, D[QD_U_MCOL]) * dt;
   q_next = qd_clip(qd_nan_to_num(q_next), 0.0, 0.5);
   P_cond = qd_nan_to_num(P_cond);
   A.eflux[c] = E; A.pcond[c] = P_cond; A.lh[c] = LH; A.lhrel[c] = P[QD_P_L_V] * P_cond;
@@ -188,11 +193,11 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     const double Ta_proxy = 288.0 + (9.81 / 1004.0) * h;
     const double Hb = (P[QD_P_HAS_ELEVATION] != 0.0) ? A.elevation[c] : 0.0;
     const double S0 = A.ssnow[c];
-    const double hs_geom = land ? qd_max(S0, 0.0) / qd_max(P[QD_P_RHO_SNOW], 1e-6) : 0.0;
+    const double hs_geom = land ? qd_div_u(qd_max(S0, 0.0), D[QD_U_RHO_SNOW]) : 0.0;
     const double hs_eff = (qd_mrow(g, QD_R_POLAR, b)[j] != 0.0) ? qd_min(hs_geom, P[QD_P_POLAR_ICE_THICK_MAX]) : hs_geom;
     const double H_eff = qd_min(Hb + hs_eff, P[QD_P_LAND_ELEV_MAX]);
-    const double T_hat = (P[QD_P_LAPSE_ENABLE] != 0.0) ? Ta_proxy - P[QD_P_LAPSE_KPM] * (H_eff / 1000.0) : Ta_proxy;
-    const double f_snow = qd_clip(1.0 / (1.0 + exp((T_hat - P[QD_P_SNOW_THRESH]) / qd_max(1e-6, P[QD_P_SNOW_T_BAND]))), 0.0, 1.0);
+    const double T_hat = (P[QD_P_LAPSE_ENABLE] != 0.0) ? Ta_proxy - P[QD_P_LAPSE_KPM] * qd_div_u(H_eff, D[QD_U_1000]) : Ta_proxy;
+    const double f_snow = qd_clip(1.0 / (1.0 + exp(qd_div_u(T_hat - P[QD_P_SNOW_THRESH], D[QD_U_SNOW_BAND]))), 0.0, 1.0);
     const double P_snow = qd_nan_to_num(f_snow * precip);
     const double P_rain = qd_nan_to_num((1.0 - f_snow) * precip);
     double C_snow = 0.0, S_next = S0, melt = 0.0;
@@ -200,14 +205,14 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     if (P[QD_P_SWE_ENABLE] != 0.0) {
       const double Ps_land = P_snow * (land ? 1.0 : 0.0);
       double mflux;
-      if (P[QD_P_SNOW_DEGREE_DAY] != 0.0) mflux = (P[QD_P_SNOW_DDF] / 86400.0) * qd_max(T_hat - P[QD_P_SNOW_MELT_TREF], 0.0);
-      else mflux = (T_hat >= P[QD_P_SNOW_THRESH]) ? P[QD_P_SNOW_MELT_RATE] / 86400.0 : 0.0;
+      if (P[QD_P_SNOW_DEGREE_DAY] != 0.0) mflux = D[QD_Q_DDF].r * qd_max(T_hat - P[QD_P_SNOW_MELT_TREF], 0.0);
+      else mflux = (T_hat >= P[QD_P_SNOW_THRESH]) ? D[QD_Q_MELT].r : 0.0;
       const double amt = qd_min(qd_max(S0, 0.0), mflux * dt);
       S_next = S0 + Ps_land * dt - amt;
       if (P[QD_P_SWE_MAX] > 0.0) S_next = qd_min(S_next, P[QD_P_SWE_MAX]);
       S_next = qd_max(0.0, S_next);
-      melt = qd_nan_to_num(amt / dt);
-      C_snow = qd_clip(1.0 - exp(-qd_max(S_next, 0.0) / qd_max(1e-6, P[QD_P_SWE_REF])), 0.0, 1.0);
+      melt = qd_nan_to_num(qd_div_u(amt, D[QD_U_DT]));
+      C_snow = qd_clip(1.0 - exp(qd_div_u(-qd_max(S_next, 0.0), D[QD_U_SWE_REF])), 0.0, 1.0);
       S_next = qd_nan_to_num(S_next);
       glacier = land && ((C_snow >= P[QD_P_GLACIER_FRAC]) || (S_next >= P[QD_P_GLACIER_SWE]));
       const double rain_gl = (P_rain * (land ? 1.0 : 0.0)) * (glacier ? 1.0 : 0.0);
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     A.glacier[c] = (uint8_t)glacier;
 
     // ---- albedo synthesis
-    const double ice_frac = qd_ice_frac(hice, P[QD_P_HICE_REF]);
+    const double ice_frac = qd_ice_frac_u(hice, D[QD_U_HICE_REF]);
     const double cloud_rad = A.has_cloud_eff ? A.cloud_eff[c] : A.cloud[c];
     double base = (P[QD_P_USE_TOPO_ALBEDO] != 0.0) ? A.base_albedo[c] : P[QD_P_ALPHA_WATER];
     if (A.with_eco) {
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     A.albedo[c] = albedo;
     double num = isr * (1 - albedo);
     if (num < 0) num = 0.0;
-    Teq = sqrt(sqrt(num / QD_SIGMA_SB));
+    Teq = sqrt(sqrt(qd_div_u(num, D[QD_U_SIGMA])));
     A.teq[c] = Teq;
 
     // ---- hydrology commit (run_simulation.py:2304-2339, hydrology.py:219-260) with this step's E
@@ -258,15 +263,14 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
       const double non_gl = (land && !glacier) ? 1.0 : 0.0;
       const double P_in = (P_rain * (land ? 1.0 : 0.0) + melt) * non_gl;
       const double W = A.wland[c];
-      const double tau = fmax(1.0, P[QD_P_RUNOFF_TAU_DAYS] * 86400.0);
-      const double R_base = W / tau;
+      const double R_base = qd_div_u(W, D[QD_U_RUNOFF_TAU]);
       const double E_land = (E * (land ? 1.0 : 0.0)) * non_gl;
       double W_next = qd_max(0.0, W + (P_in - E_land - R_base) * dt);
       double R_fast = 0.0;
       if (P[QD_P_WLAND_CAP] > 0.0) {
         const double over = qd_max(0.0, W_next - P[QD_P_WLAND_CAP]);
         W_next = W_next - over;
-        R_fast = over / dt;
+        R_fast = qd_div_u(over, D[QD_U_DT]);
       }
       A.wland[c] = qd_nan_to_num(W_next);
       A.rland[c] = qd_nan_to_num(R_base + R_fast) + melt * (glacier ? 1.0 : 0.0);
@@ -278,13 +282,13 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
   // ---- Newtonian surface update (dynamics.py:304-322)
   const double olr_old = QD_SIGMA_SB * qd_pow4(Ts);
   const double net_old = QD_SIGMA_SB * qd_pow4(Teq) + P[QD_P_GH_NEWTON] * QD_SIGMA_SB * qd_pow4(Ta) - olr_old;
-  const double Ts_newton = Ts + (net_old / fmax(1e-12, P[QD_P_C_SFC])) * dt;
+  const double Ts_newton = Ts + qd_div_u(net_old, D[QD_U_C_SFC]) * dt;
   A.ts_pre[c] = Ts_newton;
   if (!A.has_albedo) {
     A.olr[c] = olr_old;
     // radiative relaxation of h (dynamics.py:464-467); with albedo it is applied in k_energy
-    const double h_eq = (287 / P[QD_P_G]) * Teq;
-    A.h[c] = h + ((h_eq - h) / P[QD_P_TAU_RAD]) * dt;
+    const double h_eq = D[QD_Q_R_G].r * Teq;
+    A.h[c] = h + qd_div_u(h_eq - h, D[QD_U_TAU_RAD]) * dt;
   }
 }
 
@@ -298,50 +302,51 @@ struct QdEnergyArgs {
 };
 __global__ void __launch_bounds__(QD_THREADS) k_energy(QdGeo g, QdEnergyArgs A) {
   QD_CELL_PROLOGUE(g)
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;
+  const double dt = A.dt;
   if (!active) return;
   const size_t c = off + idx;
-  const double* P = g.prm + (size_t)b * QD_P_COUNT;
-  const double dt = A.dt;
   const int land = A.land[c] == 1;
   const double h = A.h[c], Ts = A.ts[c], hice = A.hice[c], u = A.u[c], v = A.v[c];
-  const double Ta = 288.0 + (P[QD_P_G] / 1004.0) * h;
+  const double Ta = 288.0 + D[QD_Q_G_CP].r * h;
   double cloud_eff = A.cloud[c];
   if (P[QD_P_CLOUD_COUPLE] != 0.0) {
-    const double RH = qd_clip(A.q_pre[c] / qd_max(1e-12, qd_qsat(Ta, P[QD_P_P0])), 0.0, 1.5);
+    const double RH = qd_clip(qd_div_z(A.q_pre[c], qd_max(1e-12, qd_qsat(Ta, P[QD_P_P0]))), 0.0, 1.5);
     const double rh_ex = qd_max(0.0, RH - P[QD_P_RH0]);
     const double Pc = A.pcond[c];
     const double pref_over = P[QD_P_PCOND_REF];
     const double P_ref = (pref_over == pref_over) ? pref_over : g.scal[(size_t)b * QD_S_COUNT + QD_S_PREF_ATM];
-    const double p_term = tanh((P_ref > 0) ? Pc / P_ref : 0.0);
+    const double p_term = tanh((P_ref > 0) ? qd_div_z(Pc, P_ref) : 0.0);          // Pc is zero wherever nothing condenses
     cloud_eff = qd_clip(cloud_eff + P[QD_P_K_Q] * rh_ex + P[QD_P_K_P] * p_term, 0.0, 1.0);
   }
   A.cloud_eff[c] = cloud_eff;
   const QdSW sw = qd_shortwave(A.isr[c], A.albedo[c], cloud_eff, P[QD_P_SW_A0], P[QD_P_SW_KC]);
-  const QdLW lw = qd_longwave(Ts, Ta, cloud_eff, land, qd_ice_frac(hice, P[QD_P_HICE_REF]), P);
+  const QdLW lw = qd_longwave(Ts, Ta, cloud_eff, land, qd_ice_frac_u(hice, D[QD_U_HICE_REF]), P);
   const double SH = qd_sensible(Ts, Ta, u, v, P);
   const double LH = A.lh[c];
   double Ts_e, hi_next = hice;
   if (P[QD_P_SEAICE] != 0.0) {
     const double Q = sw.sfc - lw.sfc - SH - LH;
     const int pole = (j == 0) ? 1 : ((j == g.nlat - 1) ? 2 : 0);
-    qd_seaice_cell(Ts, Q, dt, land, hice, pole, P, &Ts_e, &hi_next);
+    qd_seaice_cell_u(Ts, Q, dt, land, hice, pole, P, D, &Ts_e, &hi_next);
   } else {
     const double net = sw.sfc - lw.sfc - SH - LH;
     double Cs = A.cs_map ? A.cs_map[c] : P[QD_P_C_SFC];
-    if (A.cs_map) { if (!(isfinite(Cs) && (Cs > 1e3))) Cs = 1e3; } else Cs = fmax(1e-12, Cs);
-    Ts_e = qd_nan_to_num(qd_max(P[QD_P_T_FLOOR], Ts + (net / Cs) * dt));
+    if (A.cs_map) { if (!(isfinite(Cs) && (Cs > 1e3))) Cs = 1e3; }
+    const double dT = A.cs_map ? qd_div_z(net, Cs) : qd_div_u(net, D[QD_U_C_SFC]);
+    Ts_e = qd_nan_to_num(qd_max(P[QD_P_T_FLOOR], Ts + dT * dt));
   }
   A.olr[c] = lw.olr;
   const double w = fmin(1.0, fmax(0.0, P[QD_P_ENERGY_W]));
   A.ts_pre[c] = (1.0 - w) * A.ts_pre[c] + w * Ts_e;
   if (P[QD_P_SEAICE] != 0.0) A.hice[c] = hi_next;
   // h: radiative relaxation then M3 energy coupling (energy.py:452-491)
-  const double h_eq = (287 / P[QD_P_G]) * A.teq[c];
-  double hn = h + ((h_eq - h) / P[QD_P_TAU_RAD]) * dt;
+  const double h_eq = D[QD_Q_R_G].r * A.teq[c];
+  double hn = h + qd_div_u(h_eq - h, D[QD_U_TAU_RAD]) * dt;
   if (P[QD_P_ENERGY_W] > 0.0) {
     const double F_atm = sw.atm + lw.atm + SH + A.lhrel[c];
-    const double denom = fmax(1e-6, P[QD_P_RHO_A]) * fmax(1.0, P[QD_P_ATM_H]) * P[QD_P_G];
-    hn = qd_nan_to_num(hn + P[QD_P_ENERGY_W] * (F_atm / denom) * dt);
+    hn = qd_nan_to_num(hn + P[QD_P_ENERGY_W] * qd_div_u(F_atm, D[QD_U_ATM]) * dt);
   }
   A.h[c] = hn;
 }
@@ -371,13 +376,17 @@ __global__ void __launch_bounds__(QD_THREADS) k_advect_momentum(QdGeo g, QdAdvMo
   // gradients of the UPDATED h
   const double* hh = A.h + off;
   const int nlon = g.nlon, nlat = g.nlat;
+  // np.gradient: one-sided at both lon edges and at the poles; the four divisors are grid constants whose
+  // correctly rounded reciprocals come with the geometry
+  const QdRcp d_lon1{g.dlon, g.inv_dlon}, d_lon2{2.0 * g.dlon, g.inv_2dlon};
+  const QdRcp d_lat1{g.dlat, g.inv_dlat}, d_lat2{2.0 * g.dlat, g.inv_2dlat};
   double dh_dlon, dh_dlat;
-  if (i == 0) dh_dlon = (hh[(size_t)j * nlon + 1] - hh[(size_t)j * nlon]) / g.dlon;
-  else if (i == nlon - 1) dh_dlon = (hh[(size_t)j * nlon + i] - hh[(size_t)j * nlon + i - 1]) / g.dlon;
-  else dh_dlon = (hh[(size_t)j * nlon + i + 1] - hh[(size_t)j * nlon + i - 1]) / (2.0 * g.dlon);
-  if (j == 0) dh_dlat = (hh[(size_t)nlon + i] - hh[i]) / g.dlat;
-  else if (j == nlat - 1) dh_dlat = (hh[(size_t)j * nlon + i] - hh[(size_t)(j - 1) * nlon + i]) / g.dlat;
-  else dh_dlat = (hh[(size_t)(j + 1) * nlon + i] - hh[(size_t)(j - 1) * nlon + i]) / (2.0 * g.dlat);
+  if (i == 0) dh_dlon = qd_div_u(hh[(size_t)j * nlon + 1] - hh[(size_t)j * nlon], d_lon1);
+  else if (i == nlon - 1) dh_dlon = qd_div_u(hh[(size_t)j * nlon + i] - hh[(size_t)j * nlon + i - 1], d_lon1);
+  else dh_dlon = qd_div_u(hh[(size_t)j * nlon + i + 1] - hh[(size_t)j * nlon + i - 1], d_lon2);
+  if (j == 0) dh_dlat = qd_div_u(hh[(size_t)nlon + i] - hh[i], d_lat1);
+  else if (j == nlat - 1) dh_dlat = qd_div_u(hh[(size_t)j * nlon + i] - hh[(size_t)(j - 1) * nlon + i], d_lat1);
+  else dh_dlat = qd_div_u(hh[(size_t)(j + 1) * nlon + i] - hh[(size_t)(j - 1) * nlon + i], d_lat2);
   const double cosc = qd_row(g, QD_R_COS_CAP)[j];
   const double fr = A.friction[c];
   double un, vn;
@@ -412,9 +421,10 @@ struct QdTailArgs {
   double *part_max_u, *part_max_va; unsigned* ticket;
   double dt; int with_qnet, has_cloud_eff, with_max;
 };
-__global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, 4) k_tail(QdGeo g, QdTailArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
+  const QdRcp* D = g.udiv + (size_t)blockIdx.y * QD_U_COUNT;
   QD_CELL_LOOP(g) {
     QD_CELL_JI(g)
     const size_t c = off + idx;
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_tail(QdGeo g, QdTailArgs A) {
       const double ce = A.has_cloud_eff ? A.cloud_eff[c] : cl;
       const QdSW sw = qd_shortwave(A.isr[c], A.albedo[c], ce, P[QD_P_SW_A0], P[QD_P_SW_KC]);
       const double Ta = 288.0 + (9.81 / 1004.0) * h;
-      const QdLW lw = qd_longwave(ts, Ta, ce, land, qd_ice_frac(hice, P[QD_P_HICE_REF]), P);
+      const QdLW lw = qd_longwave(ts, Ta, ce, land, qd_ice_frac_u(hice, D[QD_U_HICE_REF]), P);
       const double SH = qd_sensible(ts, Ta, u, v, P);
       A.qnet[c] = sw.sfc - lw.sfc - SH - A.lh[c];
     }
