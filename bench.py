@@ -41,7 +41,7 @@ ALG_BYTES = {
     "k_laplacian": 5 * 16, "k_hyper_update": 5 * 24, "k_tail": (11 + 7) * 8 + 2, "k_advect": 4 * 8,
     "k_shapiro_lon": 3 * 16, "k_shapiro_lat": 3 * 16, "k_gauss_lat": 2 * 16, "k_gauss_lon": 16,
     "k_precip_a": (5 + 2) * 8, "k_precip_b": 4 * 8, "k_precip_c": 3 * 8, "k_precip_d": 2 * 8,
-    "k_cloud_a": (4 + 2) * 8, "k_cloud_b": 4 * 8, "k_cloud_c": 3 * 8, "k_select_hist": 8, "k_select_close": 8,
+    "k_cloud_a": (4 + 2) * 8, "k_cloud_b": 4 * 8, "k_cloud_c": 3 * 8, "k_select_coop": 8, "k_select_cluster": 8,
     "k_ocean_prep": 6 * 8, "k_ocean_momentum": 7 * 8 + 1, "k_ocean_lap": 3 * 16, "k_ocean_hyper": 3 * 24,
     "k_ocean_continuity": 6 * 8 + 1, "k_ocean_sst_finish": 9 * 8 + 2,
 }
