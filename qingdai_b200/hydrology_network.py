@@ -70,3 +70,34 @@ def build_network(grid, elevation, land_mask, pit_iters=200, pit_eps=1e-3, lib=N
     if n_lakes.value > 0:
         net["lake_outlet_index"] = outlet[: n_lakes.value].copy()
     return net
+
+
+def save_network(path, grid, net):
+    """Write ``build_network``'s result with the layout of scripts/generate_hydrology_maps.py:329-362 (variables,
+    types, dimensions and attributes), as NetCDF-3 through qingdai_b200.ncio: ``pygcm.routing.RiverRouting`` and
+    ``qingdai_b200.routing.RiverRouting`` both read it, with or without netCDF4 installed."""
+    import os
+    from .ncio import Dataset
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    land = np.asarray(net["land_mask"]).astype(np.uint8)
+    with Dataset(path, "w") as ds:
+        ds.createDimension("lat", grid.n_lat)
+        ds.createDimension("lon", grid.n_lon)
+        ds.createDimension("n_land", int(np.asarray(net["flow_order"]).size))
+        n_lakes = int(net.get("n_lakes", 0))
+        if n_lakes > 0:
+            ds.createDimension("n_lakes", n_lakes)
+        vlat = ds.createVariable("lat", "f4", ("lat",)); vlat[:] = np.asarray(grid.lat, dtype=np.float32)
+        vlon = ds.createVariable("lon", "f4", ("lon",)); vlon[:] = np.asarray(grid.lon, dtype=np.float32)
+        for name, dtype, dims in (("land_mask", "u1", ("lat", "lon")), ("elevation_filled", "f4", ("lat", "lon")),
+                                  ("flow_to_index", "i4", ("lat", "lon")), ("flow_order", "i4", ("n_land",)),
+                                  ("lake_mask", "u1", ("lat", "lon")), ("lake_id", "i4", ("lat", "lon"))):
+            v = ds.createVariable(name, dtype, dims)
+            v[:] = land if name == "land_mask" else np.asarray(net[name])
+        if n_lakes > 0:
+            v = ds.createVariable("lake_outlet_index", "i4", ("n_lakes",))
+            v[:] = np.asarray(net["lake_outlet_index"])
+        ds.setncattr("title", "Qingdai Hydrology Network")
+        ds.setncattr("indexing", "row-major (i=lon index, j=lat index), idx=j*n_lon+i")
+        ds.setncattr("projection", "latlon")
+        ds.setncattr("created_by", "qingdai_b200.hydrology_network.save_network")

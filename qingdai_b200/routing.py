@@ -5,7 +5,8 @@ Per model step the land runoff is accumulated on the device (``qd_route_accumula
 floating-point additions happen in exactly the order of the reference's serial loop, so the flow
 accumulation map and the ocean inflow are bit-identical.  Lake (P-E) bookkeeping and the closure
 sums are host NumPy on the arrays the event returns (event cadence: every 6 model hours).
-The network can be given as a dict of arrays or as a NetCDF path (needs netCDF4, like the reference).
+The network can be given as a dict of arrays or as a NetCDF path (netCDF4 when installed, else the NetCDF-3 reader
+of qingdai_b200.ncio).
 """
 from __future__ import annotations
 
@@ -23,8 +24,8 @@ def load_network(path_or_dict):
         return {k: np.asarray(v) for k, v in path_or_dict.items()}
     try:
         from netCDF4 import Dataset
-    except Exception as e:  # pragma: no cover
-        raise RuntimeError("netCDF4 is required to read a hydrology network file (pass a dict of arrays otherwise)") from e
+    except Exception:           # no netCDF4 on this box: NetCDF-3 files (hydrology_network.save_network) still open
+        from .ncio import Dataset
     out = {}
     with Dataset(path_or_dict, "r") as ds:
         for k in ("land_mask", "flow_to_index", "flow_order", "lake_mask", "lake_id", "lake_outlet_index", "lake_outlet_i", "lake_outlet_j"):

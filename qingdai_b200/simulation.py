@@ -89,6 +89,15 @@ class Simulation:
             e.set("sst", np.where(land == 0, Ts, 288.0), b)
         e.set_counters(0, 0, 0)
 
+    def save_checkpoint(self, path):
+        """Every field, mask, counter and the clock as float64 NetCDF-3 (restart.py); resume is bit-exact."""
+        from .restart import save_checkpoint
+        save_checkpoint(path, self)
+
+    def load_checkpoint(self, path):
+        from .restart import load_checkpoint
+        load_checkpoint(path, self)
+
     def forcing_for(self, t):
         ((fa, sa, ca, aa), (fb, sb, cb, ab)), theta = self.forcing.star_geometry(t)
         return Forcing(t, fa, sa, ca, aa, fb, sb, cb, ab, theta)

@@ -23,6 +23,7 @@ from unittest import mock
 import numpy as np
 
 REF = os.environ.get("QD_REFERENCE_ROOT", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 QUIET_ENV = {
@@ -671,6 +672,63 @@ def gen_routing():
     print("routing_golden.npz:", len(out), "arrays")
 
 
+def gen_restart():
+    """The reference's OWN file helpers -- run_simulation.save_restart / load_restart / save_topography / save_ocean /
+    load_ocean (scripts/run_simulation.py:63-246) and topography.load_topography_from_netcdf (pygcm/topography.py:
+    428-575) -- run unmodified with qingdai_b200.ncio installed as ``netCDF4`` (this container has no netCDF4).
+    Records what they return for seeded inputs, including the regrid of a coarse topography onto a finer grid, so that
+    qingdai_b200.restart can be compared without the reference."""
+    import tempfile
+    sys.path.insert(0, ROOT)
+    from qingdai_b200 import ncio
+    assert ncio.install_netcdf4_shim(), "a real netCDF4 is installed: record with it instead"
+    set_env()
+    from pygcm.grid import SphericalGrid
+    from pygcm import topography as topo_ref
+    import scripts.run_simulation as rs
+    rng = np.random.default_rng(2024)
+    g = SphericalGrid(13, 24)
+    shape = (13, 24)
+    ns = lambda: types.SimpleNamespace()          # noqa: E731
+    gcm, oc = ns(), ns()
+    for k in ("u", "v", "h", "T_s", "cloud_cover", "q", "h_ice"):
+        setattr(gcm, k, rng.standard_normal(shape) * 10 + 100)
+    for k in ("uo", "vo", "eta", "Ts"):
+        setattr(oc, k, rng.standard_normal(shape))
+    land = (rng.uniform(size=shape) < 0.4).astype(np.uint8)
+    W, S_ = rng.uniform(size=shape), rng.uniform(size=shape)
+    out = {"in_land": land, "in_W": W, "in_S": S_}
+    for k in ("u", "v", "h", "T_s", "cloud_cover", "q", "h_ice"):
+        out["in_gcm_" + k] = getattr(gcm, k)
+    for k in ("uo", "vo", "eta", "Ts"):
+        out["in_oc_" + k] = getattr(oc, k)
+    with tempfile.TemporaryDirectory() as td, quiet():
+        rp = os.path.join(td, "restart.nc")
+        rs.save_restart(rp, g, gcm, oc, land, W_land=W, S_snow=S_, C_snow=None, t_seconds=123456.789)
+        r = rs.load_restart(rp)
+        for k, v in r.items():
+            if v is not None:
+                out["restart_" + k] = np.asarray(v)
+        out["restart_none"] = np.array([k for k, v in r.items() if v is None])
+        op = os.path.join(td, "ocean.nc")
+        rs.save_ocean(op, g, oc, day_value=12.5)
+        o = rs.load_ocean(op)
+        for k, v in o.items():
+            out["ocean_" + k] = np.asarray(v)
+        # topography: coarse source (seam column included, as grid.lon has it) -> same grid and a finer grid
+        elev = rng.uniform(-500, 3000, shape)
+        alb = rng.uniform(0.05, 0.5, shape)
+        fric = rng.uniform(1e-6, 1e-4, shape)
+        tp = os.path.join(td, "topography.nc")
+        rs.save_topography(tp, g, land, alb, fric, elevation=elev)
+        out.update(in_elev=elev, in_alb=alb, in_fric=fric)
+        for tag, gt in (("same", g), ("fine", SphericalGrid(19, 40))):
+            e2, m2, a2, f2 = topo_ref.load_topography_from_netcdf(tp, gt)
+            out.update({f"topo_{tag}_elev": e2, f"topo_{tag}_mask": m2, f"topo_{tag}_alb": a2, f"topo_{tag}_fric": f2})
+    np.savez_compressed(os.path.join(OUT, "restart_golden.npz"), **out)
+    print("restart_golden.npz:", len(out), "arrays")
+
+
 def main():
     _install_stubs()
     which = sys.argv[1:] or ["ops", "cores", "loop"]
@@ -688,6 +746,8 @@ def main():
         gen_phyto()
     if "indiv" in which:
         gen_indiv()
+    if "restart" in which:
+        gen_restart()
 
 
 if __name__ == "__main__":
