@@ -161,3 +161,8 @@ def test_gaussian_fused_tile_kernel(lib):
 
 def test_large_grid_kernels_match_small_grid_kernels(lib):
     qdcheck.check_large_grid_paths_agree(lib)
+
+
+def test_checkpoint_resume_is_bit_exact(lib):
+    qdcheck.check_checkpoint_resume(lib)
+
