@@ -209,6 +209,7 @@ class Engine:
         self._eco_on = False
         rows, cols, self.dlat, self.dlon, self.lat, self.lon = row_tables(self.nlat, self.nlon, self.params[0], dt)
         self._rows = rows
+        self._params_version = 0
         a = const.PLANET_RADIUS
         pv = self._param_block()
         self.fields = torch.zeros((NF, self.batch, self.nlat, self.nlon), dtype=torch.float64, device=self.device)
@@ -303,6 +304,7 @@ class Engine:
         """Re-snapshot parameters (and K4 rows when dt changed) into the device tables."""
         if dt is not None and dt != self.dt:
             self.dt = dt
+        self._params_version = getattr(self, "_params_version", 0) + 1
         self._check_uniform_switches()
         for b, p in enumerate(self.params):                                     # K4 / sponge / polar rows are per member
             rows, *_ = row_tables(self.nlat, self.nlon, p, self.dt)
@@ -484,7 +486,13 @@ class Engine:
     def loop_steps(self, forcings: Sequence[Forcing], dt, **cfg_kw):
         """Run len(forcings) fused loop steps (run_simulation.py:1760-2344 without plotting/daily ecology)."""
         self._dt_guard(dt)
-        cfg = self.step_cfg(dt, **cfg_kw)
+        p = self.params[0]
+        key = (float(dt), self._params_version, tuple(sorted(cfg_kw.items())),
+               p.diff_enable, p.filter_type, p.diff_every, p.k4_nsub, p.diff_q, p.diff_cloud, p.shapiro_every, p.shapiro_n,
+               p.spec_every, p.spec_cutoff, p.spec_damp, p.oc_diff_every, p.oc_k4_nsub, p.oc_shapiro_n, p.oc_shapiro_every)
+        if getattr(self, "_loop_cfg_key", None) != key:          # the step configuration only changes with dt / params / switches
+            self._loop_cfg, self._loop_cfg_key = self.step_cfg(dt, **cfg_kw), key
+        cfg = self._loop_cfg
         n = len(forcings)
         arr = (Forcing * n)(*forcings)
         self._chk(self.lib.qd_loop_step(self.ctx, C.byref(cfg), arr, n), "qd_loop_step")

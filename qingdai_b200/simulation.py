@@ -110,11 +110,15 @@ class Simulation:
             if rr is not None:      # stop at the next routing event (routing.py:238: t_accum >= dt_hydro)
                 left = rr.dt_hydro_seconds - rr.t_accum
                 n = max(1, min(n, int(np.ceil((left - 1e-9) / self.dt))))
-            fl = [self.forcing_for(self.t + k * self.dt) for k in range(n)]
-            self.engine.loop_steps(fl, self.dt, **self.cfg)
+            pre = getattr(self, "_forcing_ahead", None)        # (t, Forcing) evaluated while the previous step was running
+            fl = [pre[1] if (k == 0 and pre is not None and pre[0] == self.t) else self.forcing_for(self.t + k * self.dt)
+                  for k in range(n)]
+            self.engine.loop_steps(fl, self.dt, **self.cfg)    # asynchronous: the step graph is only enqueued here
             self.t += n * self.dt
             self.step_index += n
             done += n
+            # the orbital scalars of the next step (host NumPy, ~20 us) overlap with the device work just enqueued
+            self._forcing_ahead = (self.t, self.forcing_for(self.t))
             if rr is not None:      # the fused step accumulated R * area * dt on the device (k_route_accumulate)
                 rr.t_accum += n * self.dt
                 if rr.t_accum + 1e-9 >= rr.dt_hydro_seconds:
