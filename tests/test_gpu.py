@@ -166,3 +166,7 @@ def test_large_grid_kernels_match_small_grid_kernels(lib):
 def test_checkpoint_resume_is_bit_exact(lib):
     qdcheck.check_checkpoint_resume(lib)
 
+
+
+def test_tiny_and_ragged_grids(lib):
+    qdcheck.check_tiny_grids(lib)

@@ -131,3 +131,11 @@ def test_individual_pool_substeps(lib, golden, tag):
 
 def test_gaussian_fused_tile_kernel(lib):
     qdcheck.check_gauss2d_large(lib)
+
+
+def test_tiny_and_ragged_grids(lib):
+    qdcheck.check_tiny_grids(lib)
+
+
+def test_checkpoint_resume_is_bit_exact(lib):
+    qdcheck.check_checkpoint_resume(lib)

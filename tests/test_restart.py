@@ -134,13 +134,6 @@ def test_topography_load_and_regrid_match_reference(R, tmp_path, tag, shape):
             restart.load_topography_from_netcdf(p, SphericalGrid(*shape), regrid="never")
 
 
-def test_checkpoint_resume_is_bit_exact_hostcheck():
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-    from hostcheck import library
-    import qdcheck
-    qdcheck.check_checkpoint_resume(library())
-
-
 def test_network_file_roundtrip_feeds_the_routing_loader(tmp_path):
     """hydrology_network.save_network writes generate_hydrology_maps.py's layout; routing.load_network reads it back
     (NetCDF-3 reader when netCDF4 is absent) with the arrays the dict path would have handed to RiverRouting."""
