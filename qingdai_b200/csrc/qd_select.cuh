@@ -11,6 +11,7 @@
 #pragma once
 #include "qd_band.cuh"           // QD_SEL_* sizes, QdBandCtl and the cross-rank pieces used when the field is split over ranks
 
+#define QD_SEL_UNROLL 4
 struct QdSelOut { double* value; double* count; int stride; double empty_value; };
 
 #if !QD_EMU
@@ -69,7 +70,7 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
 // radix passes down to bit 0.  3 sweeps + 3 grid syncs in the common case instead of 6 + 6.
 // The histograms are left zeroed for the next launch and the list counter / mingt are reset at the start: no
 // memset nodes in the step graph.
-__global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
+__global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
                                                                unsigned long long* list, unsigned* lcount,
                                                                unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B) {
   cg::grid_group grid = cg::this_grid();
@@ -97,12 +98,18 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) sh[k] = 0;
       __syncthreads();
       const int hi = shift + nbits[pass];
-      for (int idx = c0 + t0; idx < c1; idx += stride) {
-        const double v = x[off + idx];
-        if (v > 0.0) {
-          const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-          if (pass == 0 || (key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
-        }
+      // four independent loads per trip: with one load in flight per thread the sweep is bound by HBM latency
+      // (27 dependent trips of ~1 us at 1441x2880), not by bandwidth
+      for (int idx = c0 + t0; idx < c1; idx += QD_SEL_UNROLL * stride) {
+        double v[QD_SEL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < QD_SEL_UNROLL; ++u) { const int i2 = idx + u * stride; v[u] = (i2 < c1) ? x[off + i2] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < QD_SEL_UNROLL; ++u)
+          if (v[u] > 0.0) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[u]);
+            if (pass == 0 || (key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
+          }
       }
       __syncthreads();
       for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) { const unsigned c = sh[k]; if (c) atomicAdd(gh + k, c); }
@@ -131,14 +138,18 @@ __global__ void __launch_bounds__(QD_SEL_THREADS) k_select_coop(QdGeo g, const d
       unsigned long long m = ~0ull;
       unsigned long long* lst = list + (size_t)b * QD_SEL_CAP;
       const unsigned long long pk = prefix >> lo_shift;
-      for (int idx = c0 + t0; idx < c1; idx += stride) {
-        const double v = x[off + idx];
-        if (v > 0.0) {
-          const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-          const unsigned long long kk = key >> lo_shift;
-          if (kk == pk) { if (fits) lst[atomicAdd(lcount + b, 1u)] = key; }
-          else if (kk > pk && key < m) m = key;
-        }
+      for (int idx = c0 + t0; idx < c1; idx += QD_SEL_UNROLL * stride) {
+        double v[QD_SEL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < QD_SEL_UNROLL; ++u) { const int i2 = idx + u * stride; v[u] = (i2 < c1) ? x[off + i2] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < QD_SEL_UNROLL; ++u)
+          if (v[u] > 0.0) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v[u]);
+            const unsigned long long kk = key >> lo_shift;
+            if (kk == pk) { if (fits) lst[atomicAdd(lcount + b, 1u)] = key; }
+            else if (kk > pk && key < m) m = key;
+          }
       }
       for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_down_sync(0xffffffffu, m, o); if (y < m) m = y; }
       if ((threadIdx.x & 31) == 0 && m != ~0ull) atomicMin(mingt + b, m);
