@@ -323,7 +323,7 @@ def main():
             pass
         step_alg = 233 * ncell * members
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg, "us_per_launch": per_launch_s * 1e6,
+                "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": alg, "us_per_launch": per_launch_s * 1e6,
                 "share_of_step": ms / tot,
                 "whole_step": {"alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "note": "233 B/cell-step (SURVEY 8d) over the whole fused step"},
