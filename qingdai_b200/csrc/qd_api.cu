@@ -86,6 +86,7 @@ struct qd_ctx {
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
   QdIndivArgs indiv; int indiv_ready;                     // individual pool (qd_indiv.cuh); device arrays owned here
   double *d_diag_part, *d_diag_out;                       // qd_diag scratch
+  double *h_diag = nullptr, *h_diag_dev = nullptr;         // pinned, device-mapped result block: k_diag writes straight to the host
   double* d_phyto_tmp; size_t phyto_cap;                  // scratch of qd_phyto_advect_diffuse
   // ecology sub-daily (qd_eco.cuh)
   const double* d_lai; int eco_nl, eco_every_nphys, eco_steps, eco_have_alpha;
@@ -311,6 +312,9 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
 #endif
   QD_ALLOC(c->d_diag_part, (size_t)batch * QD_DIAG_COUNT * c->nblk * 8);
   QD_ALLOC(c->d_diag_out, (size_t)batch * QD_DIAG_COUNT * 8);
+  if (cudaHostAlloc((void**)&c->h_diag, (size_t)batch * QD_DIAG_COUNT * 8, cudaHostAllocMapped) == cudaSuccess &&
+      cudaHostGetDevicePointer((void**)&c->h_diag_dev, c->h_diag, 0) != cudaSuccess) { cudaFreeHost(c->h_diag); c->h_diag = nullptr; }
+  if (!c->h_diag) { c->h_diag_dev = nullptr; cudaGetLastError(); }        // no mapped memory: fall back to a device buffer + copy
   QD_ALLOC(c->d_step_idx, sizeof(int));
   QD_ALLOC(c->d_sub_ctr, sizeof(int));
   QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
@@ -363,7 +367,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
   band_release(c);
-  cudaFree(c->d_phyto_tmp); cudaFree(c->d_diag_part); cudaFree(c->d_diag_out);
+  cudaFree(c->d_phyto_tmp); cudaFree(c->d_diag_part); cudaFree(c->d_diag_out); if (c->h_diag) cudaFreeHost(c->h_diag);
   cudaFree((void*)c->indiv.cell); cudaFree((void*)c->indiv.ab); cudaFree((void*)c->indiv.tol); cudaFree(c->indiv.e_day); cudaFree(c->indiv.stress);
   free(c->h_prm);
 #ifndef QD_HOST_EMU
@@ -1194,11 +1198,13 @@ extern "C" int qd_diag(qd_ctx* c, double* out_host) {
   A.rland = F(c, QD_F_RLAND); A.albedo = F(c, QD_F_ALBEDO); A.sst = F(c, QD_F_SST); A.isr = F(c, QD_F_ISR);
   A.cloud_eff = F(c, QD_F_CLOUD_EFF); A.lh = F(c, QD_F_LH); A.u = F(c, QD_F_U); A.v = F(c, QD_F_V);
   A.uo = F(c, QD_F_UO); A.vo = F(c, QD_F_VO); A.eta = F(c, QD_F_ETA); A.land = M(c, QD_M_LAND);
-  A.has_cloud_eff = c->has_cloud_eff; A.part = c->d_diag_part; A.ticket = c->d_ticket + 2 * c->batch; A.out = c->d_diag_out;
+  A.has_cloud_eff = c->has_cloud_eff; A.part = c->d_diag_part; A.ticket = c->d_ticket + 2 * c->batch; A.out = c->h_diag_dev ? c->h_diag_dev : c->d_diag_out;
   QD_KR(c, k_diag, c->geo, A);
   QD_CHECK_LAUNCH(c);
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
-  QD_CUDA(c, cudaMemcpy(out_host, c->d_diag_out, (size_t)c->batch * QD_DIAG_COUNT * 8, cudaMemcpyDeviceToHost));
+  // the last block wrote the 27 numbers per member into mapped pinned memory: one synchronisation, no copy call
+  if (c->h_diag_dev) memcpy(out_host, c->h_diag, (size_t)c->batch * QD_DIAG_COUNT * 8);
+  else QD_CUDA(c, cudaMemcpy(out_host, c->d_diag_out, (size_t)c->batch * QD_DIAG_COUNT * 8, cudaMemcpyDeviceToHost));
   return QD_OK;
 }
 // PhytoManager.advect_diffuse on S tracers [S][nlat][nlon] (in place).  uo / vo: device currents [nlat][nlon], or

@@ -418,14 +418,8 @@ class Engine:
         assert n == len(self.DIAG)
         raw = np.empty((self.batch, n), dtype=np.float64)
         self._chk(self.lib.qd_diag(self.ctx, _ptr(raw)), "qd_diag")
-        out = []
-        for b in range(self.batch):
-            d = dict(zip(self.DIAG, raw[b]))
-            den = d["wsum"] + 1e-15
-            for k in self.DIAG[1:21]:
-                d[k] = d[k] / den
-            out.append(d)
-        return out
+        raw[:, 1:21] /= (raw[:, :1] + 1e-15)                 # x / (sum(w) + 1e-15), element by element as before
+        return [dict(zip(self.DIAG, row)) for row in raw.tolist()]
 
     def scalars(self):
         out = np.empty((self.batch, NS), dtype=np.float64)
