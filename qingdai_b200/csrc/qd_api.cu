@@ -1806,8 +1806,15 @@ extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcin
     c->forcing_cap = std::max(nsteps, 64);
     QD_CUDA(c, cudaMalloc((void**)&c->d_forcing, (size_t)c->forcing_cap * sizeof(qd_forcing_t)));
   }
-  QD_CUDA(c, cudaMemcpyAsync(c->d_forcing, forcing, (size_t)nsteps * sizeof(qd_forcing_t), cudaMemcpyHostToDevice, c->stream));
-  QD_CUDA(c, cudaMemsetAsync(c->d_step_idx, 0, sizeof(int), c->stream));
+  if (nsteps == 1) {
+    // one step per call (the interactive / end-to-end pattern): the 80 bytes of orbital scalars travel as a kernel
+    // argument -- one launch instead of a pageable-memory copy plus a memset on the critical path of every step
+    QD_LAUNCH(k_set_forcing, dim3(1), dim3(1), c->stream, c->d_forcing, forcing[0], c->d_step_idx);
+    c->launches++;
+  } else {
+    QD_CUDA(c, cudaMemcpyAsync(c->d_forcing, forcing, (size_t)nsteps * sizeof(qd_forcing_t), cudaMemcpyHostToDevice, c->stream));
+    QD_CUDA(c, cudaMemsetAsync(c->d_step_idx, 0, sizeof(int), c->stream));
+  }
   for (int s = 0; s < nsteps; ++s) {
     int rc;
 #ifndef QD_HOST_EMU

@@ -196,4 +196,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_route_accumulate(QdGeo g, const 
   buffer[c] = buffer[c] + incr;
 }
 
+__global__ void k_set_forcing(qd_forcing_t* dst, qd_forcing_t f, int* step_idx) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { dst[0] = f; *step_idx = 0; }
+}
 __global__ void k_step_advance(int* step_idx) { if (threadIdx.x == 0 && blockIdx.x == 0) *step_idx = *step_idx + 1; }

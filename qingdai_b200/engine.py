@@ -488,7 +488,13 @@ class Engine:
             self._loop_cfg, self._loop_cfg_key = self.step_cfg(dt, **cfg_kw), key
         cfg = self._loop_cfg
         n = len(forcings)
-        arr = (Forcing * n)(*forcings)
+        if n == 1:
+            arr = self.__dict__.get("_forcing1")
+            if arr is None:
+                arr = self._forcing1 = (Forcing * 1)()
+            arr[0] = forcings[0]
+        else:
+            arr = (Forcing * n)(*forcings)
         self._chk(self.lib.qd_loop_step(self.ctx, C.byref(cfg), arr, n), "qd_loop_step")
 
     def last_nsub(self):
