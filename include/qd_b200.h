@@ -283,6 +283,7 @@ int  qd_eco_bind(qd_ctx* ctx, const double* lai_layers_dev, int n_layers, double
 /* clocks as PopulationManager.__init__ leaves them (hours=0, next=update_every_hours, no cache), the LAI
  * snapshot = total LAI, adapter step counter = 0 */
 int  qd_eco_reset(qd_ctx* ctx, double hours, double next_hours, int cached, int step_count);
+int  qd_eco_state(qd_ctx* ctx, int* step_count, int* have_alpha, int set);   /* cadence counters of step_subdaily (adapter.py:150-156): read (set=0) / restore (set=1); checkpoints */
 /* one EcologyAdapter.step_subdaily call outside the fused loop: isr_dev [B][nlat][nlon]; alpha_dev receives the
  * land alpha map (NaN on ocean) when the call is on the QD_ECO_SUBSTEP_EVERY_NPHYS cadence (*produced = 1) */
 int  qd_eco_subdaily(qd_ctx* ctx, const double* isr_dev, double dt, double* alpha_dev, int* produced);

@@ -112,6 +112,7 @@ PROTOTYPES = {
     "qd_band_info": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "qd_eco_bind": (_I, [_P, _P, _I, _D, _D, _D, _I]),
     "qd_eco_reset": (_I, [_P, _D, _D, _I, _I]),
+    "qd_eco_state": (_I, [_P, _P, _P, _I]),
     "qd_eco_subdaily": (_I, [_P, _P, _D, _P, C.POINTER(_I)]),
     "qd_eco_bands": (_I, [_P, _I, _P, _D, _P]),
     "qd_indiv_setup": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P]),

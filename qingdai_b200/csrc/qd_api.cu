@@ -1122,6 +1122,14 @@ extern "C" int qd_eco_reset(qd_ctx* c, double hours, double next_hours, int cach
   }
   return QD_OK;
 }
+// Host-side counters of the ecology cadence (QD_ECO_SUBSTEP_EVERY_NPHYS): calls so far and whether an alpha map exists.
+// Read (set = 0) or written (set = 1) by the checkpoint code.
+extern "C" int qd_eco_state(qd_ctx* c, int* step_count, int* have_alpha, int set) {
+  if (!c || !step_count || !have_alpha) return QD_E_INVALID;
+  if (set) { c->eco_steps = *step_count; c->eco_have_alpha = *have_alpha ? 1 : 0; }
+  else { *step_count = c->eco_steps; *have_alpha = c->eco_have_alpha; }
+  return QD_OK;
+}
 extern "C" int qd_eco_subdaily(qd_ctx* c, const double* isr, double dt, double* alpha, int* produced) {
   if (!c || !isr) return QD_E_INVALID;
   QD_BOUND(c);

@@ -10,8 +10,9 @@ reference (netCDF4 opens NetCDF-3 classic files):
   save_ocean / load_ocean                scripts/run_simulation.py:186-246
 
 Additions: ``dtype="f8"`` on the writers (the reference stores float32; a float64 restart resumes bit-exactly) and
-``save_checkpoint`` / ``load_checkpoint`` for a ``Simulation``: EVERY device field, mask, counter and clock, so that
-run(n) -> save -> load -> run(m) equals run(n + m) bit for bit (tests/test_restart.py, tests/test_gpu.py).
+``save_checkpoint`` / ``load_checkpoint`` for a ``Simulation``: EVERY device field, mask, counter and clock, plus the
+routing buffer / lake volumes and the sub-daily ecology state when those are coupled, so that
+run(n) -> save -> load -> run(m) equals run(n + m) bit for bit (tests/test_hostcheck.py, tests/test_gpu.py).
 """
 from __future__ import annotations
 
@@ -211,18 +212,14 @@ def load_ocean(path):
 
 
 # ------------------------------------------------------------------------------------------------ exact checkpoints
-def _no_host_state(sim):
-    if sim.routing is not None or sim.eco is not None:
-        raise NotImplementedError("checkpoints cover the physics loop; routing buffers and the ecology population are "
-                                  "persisted by their own drop-ins (routing.py:337, adapter.py save_autosave), not here")
-
-
 def save_checkpoint(path, sim):
     """Every float64 field and mask of every member of ``sim``'s engine, the step counters that drive the Shapiro /
-    band-stop cadences and the simulation clock."""
+    band-stop cadences and the simulation clock; with routing: the runoff buffer, the accumulation clock and the lake
+    volumes (routing.py:232-331); with the sub-daily ecology: the LAI layers, the canopy-cache clock and the cadence
+    counters (population.py:57-71,252-286, adapter.py:150-156)."""
     from .engine import F, M
+    import ctypes as C
     e = sim.engine
-    _no_host_state(sim)
     _mkdir_for(path)
     with Dataset(path, "w") as ds:
         ds.createDimension("member", e.batch)
@@ -245,13 +242,42 @@ def save_checkpoint(path, sim):
         ds.setncattr("oc_counter", int(oc))
         ds.setncattr("has_cloud_eff", int(ce))
         ds.setncattr("dt", float(sim.dt))
+        ds.setncattr("with_routing", int(sim.routing is not None))
+        ds.setncattr("with_eco", int(sim.eco is not None))
+        if sim.routing is not None:
+            rr = sim.routing
+            ds.createDimension("cell", rr.n_cells)
+            v = ds.createVariable("routing_buffer_kg", "f8", ("cell",))
+            v[:] = rr.buffer_kg
+            ds.setncattr("routing_t_accum", float(rr.t_accum))
+            if rr.lake_volume_kg is not None and rr.lake_volume_kg.size:
+                ds.createDimension("lake", int(rr.lake_volume_kg.size))
+                v = ds.createVariable("routing_lake_volume_kg", "f8", ("lake",))
+                v[:] = rr.lake_volume_kg
+        if sim.eco is not None:
+            steps, have = C.c_int(0), C.c_int(0)
+            e._chk(e.lib.qd_eco_state(e.ctx, C.byref(steps), C.byref(have), 0), "qd_eco_state")
+            ds.setncattr("eco_step_count", int(steps.value))
+            ds.setncattr("eco_have_alpha", int(have.value))
+            from .engine import S
+            sc = e.scalars()[0]
+            ds.setncattr("eco_hours", float(sc[S["eco_hours"]]))
+            ds.setncattr("eco_next_hours", float(sc[S["eco_next"]]))
+            ds.setncattr("eco_cached", int(sc[S["eco_cached"]] != 0.0))
+            pop = sim.eco.pop
+            if pop is not None:
+                lay = pop.LAI_layers_SK
+                ds.createDimension("species", lay.shape[0])
+                ds.createDimension("cohort", lay.shape[1])
+                v = ds.createVariable("eco_lai_layers", "f8", ("species", "cohort", "lat", "lon"))
+                v[:] = lay
 
 
 def load_checkpoint(path, sim):
     """Inverse of save_checkpoint into a Simulation built with the same grid, batch, parameters and topography."""
     from .engine import F, M
+    import ctypes as C
     e = sim.engine
-    _no_host_state(sim)
     with Dataset(path, "r") as ds:
         if ds.getncattr("format") != "qd-checkpoint-v1":
             raise ValueError(f"{path!r} is not a qingdai_b200 checkpoint")
@@ -260,6 +286,25 @@ def load_checkpoint(path, sim):
             raise ValueError(f"checkpoint holds {shape}, the simulation is {(e.batch, e.nlat, e.nlon)}")
         if float(ds.getncattr("dt")) != float(sim.dt):
             raise ValueError("checkpoint was written with a different dt")
+        if bool(ds.getncattr("with_routing")) != (sim.routing is not None) or bool(ds.getncattr("with_eco")) != (sim.eco is not None):
+            raise ValueError("checkpoint and simulation disagree about routing / ecology")
+        if sim.eco is not None:
+            # first the population and its clocks (qd_eco_reset re-snapshots the LAI), then every field on top of it
+            pop = sim.eco.pop
+            if pop is not None:
+                pop.set_lai_layers(ds.variables["eco_lai_layers"][:].data, reset_clock=False)
+            e.eco_reset(float(ds.getncattr("eco_hours")), float(ds.getncattr("eco_next_hours")),
+                        cached=bool(ds.getncattr("eco_cached")), step_count=int(ds.getncattr("eco_step_count")))
+            steps, have = C.c_int(int(ds.getncattr("eco_step_count"))), C.c_int(int(ds.getncattr("eco_have_alpha")))
+            e._chk(e.lib.qd_eco_state(e.ctx, C.byref(steps), C.byref(have), 1), "qd_eco_state")
+        if sim.routing is not None:
+            rr = sim.routing
+            buf = np.ascontiguousarray(ds.variables["routing_buffer_kg"][:].data, dtype=np.float64)
+            e._chk(e.lib.qd_route_buffer(e.ctx, rr.member, C.c_void_p(buf.ctypes.data), 1), "qd_route_buffer")
+            rr.t_accum = float(ds.getncattr("routing_t_accum"))
+            if rr.lake_volume_kg is not None and rr.lake_volume_kg.size:
+                rr.lake_volume_kg[:] = ds.variables["routing_lake_volume_kg"][:].data
+            rr._diag_cache = None
         for name in sorted(F, key=F.get):
             data = ds.variables["f_" + name][:].data
             for b in range(e.batch):

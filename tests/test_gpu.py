@@ -170,3 +170,7 @@ def test_checkpoint_resume_is_bit_exact(lib):
 
 def test_tiny_and_ragged_grids(lib):
     qdcheck.check_tiny_grids(lib)
+
+
+def test_checkpoint_resume_with_routing_and_ecology(lib, golden):
+    qdcheck.check_checkpoint_resume_config3(lib, golden("routing_golden.npz"))
