@@ -830,26 +830,41 @@ extern "C" int qd_set_gauss(qd_ctx* c, int which, int radius, int wrap, const do
 }
 #ifndef QD_HOST_EMU
 // Fused two-axis Gaussian (qd_gauss2d.cuh) over every segment of the compute region.
-template <int MODE>
-static int launch_gauss2d(qd_ctx* c, QdG2Args A, const QdGaussW& w, const std::vector<BIn>& ins, const std::vector<const void*>& outs, const char* name) {
-  BPV(c, ins, outs);
-  const int tiles_i = (c->nlon + QD_G2_TI - 1) / QD_G2_TI;
+#define QD_G2S_TJ 8
+#define QD_G2S_TI 32
+// large grids: 16 x 64 tiles; grids on which those would leave most SMs idle (181x360: 72 tiles): 8 x 32 tiles
+static inline bool gauss2d_small(qd_ctx* c) {
+  const long long tiles = (long long)((c->nlon + QD_G2_TI - 1) / QD_G2_TI) * ((c->nlat + QD_G2_TJ - 1) / QD_G2_TJ) * c->batch;
+  return tiles < 2 * 148;
+}
+template <int MODE, int TJ, int TI>
+static int launch_gauss2d_t(qd_ctx* c, QdG2Args A, const QdGaussW& w, const char* name) {
+  const int tiles_i = (c->nlon + TI - 1) / TI;
   const int seg[2][2] = {{c->geo.sa0, c->geo.sa1}, {c->geo.sb0, c->geo.sb1}};
   for (int q = 0; q < 2; ++q) {
     if (seg[q][1] <= seg[q][0]) continue;
     A.row0 = seg[q][0]; A.row1 = seg[q][1];
-    const int tiles_j = (A.row1 - A.row0 + QD_G2_TJ - 1) / QD_G2_TJ;
-    const dim3 grid(tiles_i * tiles_j, c->batch), block(QD_G2_NX, QD_G2_NY);
-    if (w.r == 4) QD_KGN(c, name, (k_gauss2d_tile<MODE, 4>), grid, block, c->geo, A, w);          // sigma = 1 (physics.py:44,69,111,159,330)
-    else if (w.r == 1) QD_KGN(c, name, (k_gauss2d_tile<MODE, 1>), grid, block, c->geo, A, w);     // sigma = 0.2 (run_simulation.py:1931)
-    else QD_KGN(c, name, (k_gauss2d_tile<MODE, 0>), grid, block, c->geo, A, w);
+    const int tiles_j = (A.row1 - A.row0 + TJ - 1) / TJ;
+    const dim3 grid(tiles_i * tiles_j, c->batch), block(TI, (QD_G2_NX * QD_G2_NY) / TI);
+    if (w.r == 4) QD_KGN(c, name, (k_gauss2d_tile<MODE, 4, TJ, TI>), grid, block, c->geo, A, w);          // sigma = 1 (physics.py:44,69,111,159,330)
+    else if (w.r == 1) QD_KGN(c, name, (k_gauss2d_tile<MODE, 1, TJ, TI>), grid, block, c->geo, A, w);     // sigma = 0.2 (run_simulation.py:1931)
+    else QD_KGN(c, name, (k_gauss2d_tile<MODE, 0, TJ, TI>), grid, block, c->geo, A, w);
   }
   return QD_OK;
 }
-// large grids only: at 181x360 a launch has 72 tiles (< 148 SMs) and the two short passes are faster
+template <int MODE>
+static int launch_gauss2d(qd_ctx* c, QdG2Args A, const QdGaussW& w, const std::vector<BIn>& ins, const std::vector<const void*>& outs, const char* name) {
+  BPV(c, ins, outs);
+  if (gauss2d_small(c)) return launch_gauss2d_t<MODE, QD_G2S_TJ, QD_G2S_TI>(c, A, w, name);
+  return launch_gauss2d_t<MODE, QD_G2_TJ, QD_G2_TI>(c, A, w, name);
+}
+// Fused two-axis Gaussian or the two one-axis passes?  Default: fused wherever at least 148 tiles (of either size) exist.
 static inline bool gauss2d_ok(qd_ctx* c, const QdGaussW& w) {
-  const long long tiles = (long long)((c->nlon + QD_G2_TI - 1) / QD_G2_TI) * ((c->nlat + QD_G2_TJ - 1) / QD_G2_TJ) * c->batch;
-  return c->g2_fused && w.r >= 1 && w.r <= QD_G2_RMAX && tiles >= 2 * 148;
+  const long long small_tiles = (long long)((c->nlon + QD_G2S_TI - 1) / QD_G2S_TI) * ((c->nlat + QD_G2S_TJ - 1) / QD_G2S_TJ) * c->batch;
+#ifdef QD_G2_LARGE_ONLY
+  if (gauss2d_small(c)) return false;
+#endif
+  return c->g2_fused && w.r >= 1 && w.r <= QD_G2_RMAX && small_tiles >= 148;
 }
 #endif
 // in place on fld[k] (two-pass form); with `out` given and the fused kernel available the result is left in out[k]

@@ -25,10 +25,12 @@ struct QdG2Args {
   int row0, row1;                      // output rows of this launch (latitude bands: one launch per segment)
 };
 
-// R = compile-time radius (4: sigma = 1; 1: sigma = 0.2; 0: generic radius <= QD_G2_RMAX taken from w.r)
-template <int MODE, int R>
+// R = compile-time radius (4: sigma = 1; 1: sigma = 0.2; 0: generic radius <= QD_G2_RMAX taken from w.r).
+// TJ x TI = output tile of a block of 256 threads: 16 x 64 on large grids, 8 x 32 where that would leave most SMs
+// without a tile (181x360: 276 tiles instead of 72).
+template <int MODE, int R, int TJ = QD_G2_TJ, int TI = QD_G2_TI>
 __global__ void __launch_bounds__(QD_G2_NX * QD_G2_NY) k_gauss2d_tile(QdGeo g, QdG2Args A, QdGaussW w) {
-  constexpr int TJ = QD_G2_TJ, TI = QD_G2_TI, RM = R > 0 ? R : QD_G2_RMAX, NX = QD_G2_NX, NY = QD_G2_NY;
+  constexpr int RM = R > 0 ? R : QD_G2_RMAX, NX = TI, NY = (QD_G2_NX * QD_G2_NY) / TI;
   constexpr int PER = TJ / NY;                                  // outputs per thread
   __shared__ double in[(TJ + 2 * RM) * (TI + 2 * RM)];
   __shared__ double mid[TJ * (TI + 2 * RM)];

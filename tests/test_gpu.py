@@ -174,3 +174,10 @@ def test_tiny_and_ragged_grids(lib):
 
 def test_checkpoint_resume_with_routing_and_ecology(lib, golden):
     qdcheck.check_checkpoint_resume_config3(lib, golden("routing_golden.npz"))
+
+
+def test_small_tile_gaussian_paths_agree(lib):
+    """141x280: too few 16x64 tiles, enough 8x32 tiles -- the small-tile fused Gaussian kernels against the two-pass
+    kernels, operator level and through three fused loop steps."""
+    qdcheck.check_gauss2d_large(lib, shape=(141, 280))
+    qdcheck.check_large_grid_paths_agree(lib, shape=(141, 280))
