@@ -725,6 +725,24 @@ def gen_restart():
         for tag, gt in (("same", g), ("fine", SphericalGrid(19, 40))):
             e2, m2, a2, f2 = topo_ref.load_topography_from_netcdf(tp, gt)
             out.update({f"topo_{tag}_elev": e2, f"topo_{tag}_mask": m2, f"topo_{tag}_alb": a2, f"topo_{tag}_fric": f2})
+        # a foreign layout: latitude descending, longitude in [-180, 180) without a seam column, coarser than the target
+        fl_lat = np.linspace(90.0, -90.0, 10)
+        fl_lon = np.linspace(-180.0, 180.0, 18, endpoint=False)
+        f_elev = rng.uniform(-500, 3000, (10, 18))
+        f_mask = (rng.uniform(size=(10, 18)) < 0.5).astype(np.uint8)
+        f_alb = rng.uniform(0.05, 0.5, (10, 18))
+        f_fric = rng.uniform(1e-6, 1e-4, (10, 18))
+        fp = os.path.join(td, "foreign.nc")
+        with ncio.Dataset(fp, "w") as ds:
+            ds.createDimension("lat", 10)
+            ds.createDimension("lon", 18)
+            v = ds.createVariable("lat", "f8", ("lat",)); v[:] = fl_lat
+            v = ds.createVariable("lon", "f8", ("lon",)); v[:] = fl_lon
+            for name, dt_, arr in (("elevation", "f8", f_elev), ("land_mask", "u1", f_mask), ("base_albedo", "f8", f_alb), ("friction", "f8", f_fric)):
+                v = ds.createVariable(name, dt_, ("lat", "lon")); v[:] = arr
+        out.update(foreign_lat=fl_lat, foreign_lon=fl_lon, foreign_elev=f_elev, foreign_mask=f_mask, foreign_alb=f_alb, foreign_fric=f_fric)
+        e2, m2, a2, f2 = topo_ref.load_topography_from_netcdf(fp, SphericalGrid(13, 24))
+        out.update(topo_foreign_elev=e2, topo_foreign_mask=m2, topo_foreign_alb=a2, topo_foreign_fric=f2)
     np.savez_compressed(os.path.join(OUT, "restart_golden.npz"), **out)
     print("restart_golden.npz:", len(out), "arrays")
 

@@ -153,3 +153,19 @@ def test_network_file_roundtrip_feeds_the_routing_loader(tmp_path):
     for k in ("land_mask", "flow_to_index", "flow_order", "lake_mask", "lake_id", "lake_outlet_index"):
         assert np.array_equal(back[k], net[k]), k
     assert back["land_mask"].dtype == np.uint8
+
+
+def test_topography_foreign_layout_matches_reference(R, tmp_path):
+    """Latitude descending, longitudes in [-180, 180) without a seam column, coarser than the target grid: the loader
+    flips, renormalises, sorts and regrids exactly like topography.load_topography_from_netcdf."""
+    p = str(tmp_path / "foreign.nc")
+    with ncio.Dataset(p, "w") as ds:
+        ds.createDimension("lat", 10)
+        ds.createDimension("lon", 18)
+        v = ds.createVariable("lat", "f8", ("lat",)); v[:] = R["foreign_lat"]
+        v = ds.createVariable("lon", "f8", ("lon",)); v[:] = R["foreign_lon"]
+        for name, dt_, key in (("elevation", "f8", "elev"), ("land_mask", "u1", "mask"), ("base_albedo", "f8", "alb"), ("friction", "f8", "fric")):
+            v = ds.createVariable(name, dt_, ("lat", "lon")); v[:] = R["foreign_" + key]
+    e, m, a, f = restart.load_topography_from_netcdf(p, SphericalGrid(13, 24))
+    for got, key in ((e, "elev"), (m, "mask"), (a, "alb"), (f, "fric")):
+        assert np.array_equal(got, R["topo_foreign_" + key]), key
