@@ -91,6 +91,42 @@ class Simulation:
             e.set("sst", np.where(land == 0, Ts, 288.0), b)
         e.set_counters(0, 0, 0)
 
+    # reference restart variable -> device field (run_simulation.py:63-123, 1436-1470)
+    _RESTART_MAP = {"u": "u", "v": "v", "h": "h", "T_s": "ts", "cloud_cover": "cloud", "q": "q", "h_ice": "hice",
+                    "uo": "uo", "vo": "vo", "eta": "eta", "Ts": "sst", "W_land": "wland", "S_snow": "ssnow", "C_snow": "csnow"}
+
+    def save_restart(self, path, member=0, dtype="f4"):
+        """Reference-format warm-restart file (run_simulation.save_restart: minimal prognostic state, float32 unless
+        dtype="f8") of one member, readable by the reference's load_restart.  For a bit-exact resume use save_checkpoint."""
+        from types import SimpleNamespace
+        from .restart import save_restart
+        e = self.engine
+        g = {k: e.get(f, member) for k, f in self._RESTART_MAP.items()}
+        gcm = SimpleNamespace(**{k: g[k] for k in ("u", "v", "h", "T_s", "cloud_cover", "q", "h_ice")})
+        oc = SimpleNamespace(**{k: g[k] for k in ("uo", "vo", "eta", "Ts")}) if self.cfg["with_ocean"] else None
+        save_restart(path, self.grid, gcm, oc, e.get_mask("land", member), W_land=g["W_land"], S_snow=g["S_snow"],
+                     C_snow=g["C_snow"], t_seconds=self.t, dtype=dtype)
+
+    def load_restart(self, path, member=None):
+        """Warm restart from a reference-format file (run_simulation.py:1436-1470): the variables the file holds
+        replace the device fields (all members unless ``member`` is given), t_seconds becomes the clock.  Grid shapes
+        must match.  Lagged diagnostics (precipitation, cloud_eff, latent heat ...) restart from their current values,
+        as in the reference."""
+        from .restart import load_restart
+        d = load_restart(path)
+        for k, f in self._RESTART_MAP.items():
+            a = d.get(k)
+            if a is None:
+                continue
+            a = np.asarray(a, dtype=np.float64)
+            if a.shape != self.engine.shape:
+                raise ValueError(f"restart variable {k!r} has shape {a.shape}, the simulation is {self.engine.shape}")
+            self.engine.set(f, a, member)
+        if d.get("t_seconds") is not None:
+            self.t = float(d["t_seconds"])
+        self._forcing_ahead = None
+        return d
+
     def save_checkpoint(self, path):
         """Every field, mask, counter and the clock as float64 NetCDF-3 (restart.py); resume is bit-exact."""
         from .restart import save_checkpoint

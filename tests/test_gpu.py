@@ -181,3 +181,7 @@ def test_small_tile_gaussian_paths_agree(lib):
     kernels, operator level and through three fused loop steps."""
     qdcheck.check_gauss2d_large(lib, shape=(141, 280))
     qdcheck.check_large_grid_paths_agree(lib, shape=(141, 280))
+
+
+def test_reference_format_restart(lib):
+    qdcheck.check_reference_format_restart(lib)

@@ -143,3 +143,7 @@ def test_checkpoint_resume_is_bit_exact(lib):
 
 def test_checkpoint_resume_with_routing_and_ecology(lib, golden):
     qdcheck.check_checkpoint_resume_config3(lib, golden("routing_golden.npz"))
+
+
+def test_reference_format_restart(lib):
+    qdcheck.check_reference_format_restart(lib)
