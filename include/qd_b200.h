@@ -247,6 +247,10 @@ int  qd_last_nsub(qd_ctx* ctx, int* out_host /* [B] */);      /* sync */
  * for the ocean's data-dependent sub-step loop); 1: stream launches + WHILE-node graph for the ocean
  * loop only; 0: stream launches and a host loop with one scalar read-back per step */
 int  qd_use_graphs(qd_ctx* ctx, int enable);
+/* captured graphs currently cached / captures that failed and fell back to stream mode (a 2x slowdown nobody should
+ * discover by accident: bench.py asserts failed == 0).  Graphs are dropped and re-captured whenever an entry point changes
+ * something they bake in (qd_bind, qd_set_params, qd_set_gauss, qd_route_setup, qd_eco_bind, qd_band_connect). */
+int  qd_graph_status(qd_ctx* ctx, int* live, int* failed);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */

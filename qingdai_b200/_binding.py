@@ -99,6 +99,7 @@ PROTOTYPES = {
     "qd_loop_step": (_I, [_P, C.POINTER(StepCfg), C.POINTER(Forcing), _I]),
     "qd_last_nsub": (_I, [_P, _P]),
     "qd_use_graphs": (_I, [_P, _I]),
+    "qd_graph_status": (_I, [_P, C.POINTER(_I), C.POINTER(_I)]),
     "qd_set_counters": (_I, [_P, _I, _I, _I]),
     "qd_get_counters": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "qd_set_gauss2d": (_I, [_P, _I]),

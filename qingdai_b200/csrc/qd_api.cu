@@ -33,6 +33,8 @@ void qd_emu_launch(dim3 grid, dim3 block, const std::function<void()>& body) {
 
 #define QD_NUSER_ROWS 6
 #define QD_NPART 4
+#define QD_NVB_MAX 1184            // virtual blocks of the sum reductions (8 x 148: one resident wave of 256-thread blocks for one member)
+#define QD_FORCING_CAP 64          // steps per forcing-table upload; longer qd_loop_step calls are chunked
 
 struct qd_route {
   int ready = 0, n_levels = 0, n_lakes = 0;
@@ -66,6 +68,7 @@ struct qd_ctx {
   int last_nsub_max;
   QdGaussW w_sigma1, w_cloud; int w_set;
   int* d_sub_ctr; int use_graphs;
+  int graph_failures = 0;                           // step / ocean graph captures that failed (the step then runs in stream mode)
 #ifndef QD_HOST_EMU
   cudaStream_t cap_stream, cap_stream2;
   cudaGraph_t capture_graph;                        // non-null while a whole loop step is being captured
@@ -174,10 +177,27 @@ static int qd_red_blocks(qd_ctx* c, const void* kern) {
     qd_prof_end((c), pi_); (c)->launches++; } while (0)
 #define QD_K(c, kern, ...) QD_KG(c, kern, dim3((c)->cur_nblk, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 // grid-stride kernels that end in a grid-wide reduction (QD_CELL_LOOP): at most red_blk blocks per member
-#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min(qd_red_blocks((c), (const void*)kern), (c)->cur_nblk), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#ifdef QD_HOST_EMU
+#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3((c)->geo.nvb, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#else
+#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min(std::min(qd_red_blocks((c), (const void*)kern), (c)->cur_nblk), (c)->geo.nvb), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+#endif
 
 struct BIn;
 static void band_release(qd_ctx* c);
+// Captured graphs bake in kernel arguments (pointers, Gaussian taps, switches read from h_prm on the host).  Every entry
+// point that changes one of those drops the cached graphs; the next step captures again.
+static void qd_drop_graphs(qd_ctx* c) {
+#ifndef QD_HOST_EMU
+  if (c->step_graphs.empty() && c->ocean_graphs.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& kv : c->ocean_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : c->step_graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+  c->ocean_graphs.clear(); c->step_graphs.clear();
+#else
+  (void)c;
+#endif
+}
 #ifndef QD_HOST_EMU
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
 static bool qd_prof_on(qd_ctx* c) { return c->prof && qd_prof_of(c)->on; }
@@ -255,6 +275,7 @@ static int qd_upload_rows(qd_ctx* c, int member, const double* rows) {
 extern "C" int qd_version(void) { return 100; }
 extern "C" const char* qd_last_error(const qd_ctx* c) { return c ? c->err : "null context"; }
 
+extern "C" int qd_destroy(qd_ctx* c);
 extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, double dlat, double dlon,
                          double a_sq, double dlon_sq, const double* rows_host, const double* cols_host,
                          const double* params_host, qd_ctx** out) {
@@ -283,7 +304,8 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
 #endif
   const size_t nrows = (size_t)(QD_R_COUNT + 7 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
-#define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { delete c; return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
+  // a failed allocation releases everything allocated so far (qd_destroy frees null pointers harmlessly)
+#define QD_ALLOC(ptr, bytes) do { if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { cudaGetLastError(); qd_destroy(c); return QD_E_CUDA; } cudaMemset((ptr), 0, (bytes)); } while (0)
   QD_ALLOC(c->d_rows, (size_t)batch * nrows * 8);
   QD_ALLOC(c->d_cols, (size_t)QD_C_COUNT * nlon * 8);
   QD_ALLOC(c->d_prm, (size_t)batch * QD_P_COUNT * 8);
@@ -307,7 +329,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
     c->red_blk = std::max(1, std::min(c->nblk, (8 * sms + batch - 1) / batch));     // one resident wave of 256-thread blocks
     const int want = (c->ncell + QD_SEL_THREADS - 1) / QD_SEL_THREADS;
     c->sel_gx = std::max(1, std::min(want, resident / batch));
-    if ((long long)c->sel_gx * batch > resident) { delete c; return QD_E_INVALID; }   // ensemble too large for one cooperative grid
+    if ((long long)c->sel_gx * batch > resident) { qd_destroy(c); return QD_E_INVALID; }   // ensemble too large for one cooperative grid
   }
 #endif
   QD_ALLOC(c->d_diag_part, (size_t)batch * QD_DIAG_COUNT * c->nblk * 8);
@@ -317,6 +339,8 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   if (!c->h_diag) { c->h_diag_dev = nullptr; cudaGetLastError(); }        // no mapped memory: fall back to a device buffer + copy
   QD_ALLOC(c->d_step_idx, sizeof(int));
   QD_ALLOC(c->d_sub_ctr, sizeof(int));
+  c->forcing_cap = QD_FORCING_CAP;                  // fixed: captured step graphs hold this pointer
+  QD_ALLOC(c->d_forcing, (size_t)QD_FORCING_CAP * sizeof(qd_forcing_t));
   QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
   QD_ALLOC(c->d_twid, (size_t)2 * nlon * 8);
   QD_ALLOC(c->d_spec_coef, (size_t)batch * nlat * 2 * (nlon / 2 + 1) * 8);
@@ -341,11 +365,16 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   g.inv_dlat = 1.0 / dlat; g.inv_2dlat = 1.0 / (2.0 * dlat); g.inv_dlon_sq = 1.0 / dlon_sq; g.inv_a_sq = 1.0 / a_sq;
   g.inv_2dlon = 1.0 / (2.0 * dlon); g.inv_a = 1.0 / a; g.inv_dlon = 1.0 / dlon;
   g.own0 = 0; g.own1 = nlat; g.sa0 = 0; g.sa1 = nlat; g.sb0 = 0; g.sb1 = 0; g.ncomp = c->ncell;
+#ifdef QD_HOST_EMU
+  g.nvb = c->red_blk;      // sequential host threads: one virtual block per physical block (QD_KR), still fewer blocks than cells / 256
+#else
+  g.nvb = std::max(1, std::min(c->nblk, QD_NVB_MAX));
+#endif
   g.div_nlon = (1ull << 40) / (unsigned long long)nlon + 1ull;
-  if ((unsigned long long)c->ncell * (unsigned long long)nlon >= (1ull << 40)) { delete c; return QD_E_INVALID; }
+  if ((unsigned long long)c->ncell * (unsigned long long)nlon >= (1ull << 40)) { qd_destroy(c); return QD_E_INVALID; }
   g.rows = c->d_rows; g.row_bstride = (long long)nrows; g.cols = c->d_cols; g.prm = c->d_prm; g.scal = c->d_scal; g.udiv = c->d_udiv;
-  for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { delete c; return QD_E_CUDA; }
-  if (cudaGetLastError() != cudaSuccess) { delete c; return QD_E_CUDA; }
+  for (int b = 0; b < batch; ++b) if (qd_upload_rows(c, b, rows_host) != QD_OK) { qd_destroy(c); return QD_E_CUDA; }
+  if (cudaGetLastError() != cudaSuccess) { qd_destroy(c); return QD_E_CUDA; }
   *out = c;
   return QD_OK;
 }
@@ -372,8 +401,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   free(c->h_prm);
 #ifndef QD_HOST_EMU
   if (c->prof) { qd_prof_harvest(c); delete qd_prof_of(c); }
-  for (auto& kv : c->ocean_graphs) if (kv.second) cudaGraphExecDestroy(kv.second);
-  for (auto& kv : c->step_graphs) if (kv.second.first) cudaGraphExecDestroy(kv.second.first);
+  qd_drop_graphs(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
 #endif
@@ -385,12 +413,14 @@ extern "C" int qd_set_stream(qd_ctx* c, void* s) { if (!c) return QD_E_INVALID; 
 extern "C" int qd_synchronize(qd_ctx* c) { if (!c) return QD_E_INVALID; QD_CUDA(c, cudaStreamSynchronize(c->stream)); return QD_OK; }
 extern "C" int qd_bind(qd_ctx* c, double* fields, uint8_t* masks) {
   if (!c || !fields || !masks) return QD_E_INVALID;
+  qd_drop_graphs(c);
   c->fields = fields; c->masks = masks;
   return QD_OK;
 }
 extern "C" int qd_set_params(qd_ctx* c, const double* p) {
   if (!c || !p) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  qd_drop_graphs(c);                               // host-side branches on h_prm shape the captured launch sequence
   memcpy(c->h_prm, p, (size_t)c->batch * QD_P_COUNT * 8);
   QD_CUDA(c, cudaMemcpy(c->d_prm, p, (size_t)c->batch * QD_P_COUNT * 8, cudaMemcpyHostToDevice));
   c->udiv_valid = 0;
@@ -440,8 +470,8 @@ extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double*
 }
 // test / tuning switch: 0 forces the shared-memory tile kernel for del^4 at every size (default 1: large grids stream)
 // test / tuning switch: 0 forces the two-pass Gaussian kernels at every size (default 1: large grids use the fused tile kernel)
-extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->g2_fused = enable ? 1 : 0; return QD_OK; }
-extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; c->h4_stream = enable ? 1 : 0; return QD_OK; }
+extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->g2_fused = enable ? 1 : 0; return QD_OK; }
+extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->h4_stream = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
 extern "C" int qd_get_counters(qd_ctx* c, int* a, int* o, int* ce) {
@@ -663,6 +693,7 @@ extern "C" int qd_band_connect(qd_ctx* c, const void* handles /* [world][64], ra
     c->band_peer_map[r] = m; B.peer[r] = (char*)m;
 #endif
   }
+  qd_drop_graphs(c);
   c->band_on = 1;
   band_invalidate_dynamic(c);
   band_set_ext(c, 0);
@@ -824,6 +855,7 @@ static QdGaussW mk_gauss_w(int radius, int wrap, const double* weights) {
 }
 extern "C" int qd_set_gauss(qd_ctx* c, int which, int radius, int wrap, const double* weights) {
   if (!c || radius < 0 || radius > QD_GAUSS_MAXR || !weights) return QD_E_INVALID;
+  qd_drop_graphs(c);                               // the taps travel by value in captured kernel arguments
   if (which == 0) c->w_sigma1 = mk_gauss_w(radius, wrap, weights); else c->w_cloud = mk_gauss_w(radius, wrap, weights);
   c->w_set |= (1 << (which ? 1 : 0));
   return QD_OK;
@@ -1114,6 +1146,7 @@ static int eco_policy(qd_ctx* c, double dt) {
 }
 extern "C" int qd_eco_bind(qd_ctx* c, const double* lai, int nl, double k_canopy, double every_hours, double lai_delta, int every_nphys) {
   if (!c || (lai && nl < 1)) return QD_E_INVALID;
+  qd_drop_graphs(c);
   c->d_lai = lai; c->eco_nl = lai ? nl : 0; c->eco_k = k_canopy; c->eco_every_hours = every_hours; c->eco_delta = lai_delta;
   c->eco_every_nphys = every_nphys > 1 ? every_nphys : 1;
   return QD_OK;
@@ -1543,8 +1576,11 @@ static cudaGraphExec_t ocean_while_graph(qd_ctx* c, const qd_step_cfg_t* cfg, in
   c->launches = saved_launches;
   cudaGetLastError();
   if (graph) cudaGraphDestroy(graph);
-  if (!ok) exec = nullptr;
-  c->ocean_graphs[key] = exec;       // nullptr = graphs unavailable -> host loop with one read-back
+  if (!ok) {
+    exec = nullptr; c->graph_failures++;
+    snprintf(c->err, sizeof(c->err), "CUDA-graph capture of the ocean sub-step loop failed: running it as a host loop (stream mode)");
+  }
+  c->ocean_graphs[key] = exec;       // nullptr = graphs unavailable -> host loop with one read-back (reported by qd_graph_status)
   return exec;
 }
 #endif
@@ -1629,6 +1665,18 @@ extern "C" int qd_ocean_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (!c || !cfg) return QD_E_INVALID;
   QD_BOUND(c);
   return ocean_core(c, cfg, 0);
+}
+// live = captured step / ocean-loop graphs in the cache; failed = captures that fell back to stream mode since qd_create
+extern "C" int qd_graph_status(qd_ctx* c, int* live, int* failed) {
+  if (!c) return QD_E_INVALID;
+  int n = 0;
+#ifndef QD_HOST_EMU
+  for (auto& kv : c->step_graphs) if (kv.second.first) ++n;
+  for (auto& kv : c->ocean_graphs) if (kv.second) ++n;
+#endif
+  if (live) *live = n;
+  if (failed) *failed = c->graph_failures;
+  return QD_OK;
 }
 extern "C" int qd_use_graphs(qd_ctx* c, int level) { if (!c) return QD_E_INVALID; c->use_graphs = level < 0 ? 0 : (level > 2 ? 2 : level); return QD_OK; }
 extern "C" int qd_last_nsub(qd_ctx* c, int* out) {
@@ -1811,7 +1859,9 @@ static int loop_step_graph(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (!ok) {
     c->atm_counter = sa; c->oc_counter = so; c->has_cloud_eff = sce; c->launches = sl; c->eco_steps = ses; c->eco_have_alpha = sea;
     c->step_graphs[key] = std::make_pair((cudaGraphExec_t) nullptr, 0ll);
-    return QD_E_STATE;
+    c->graph_failures++;
+    if (rc == QD_OK) snprintf(c->err, sizeof(c->err), "CUDA-graph capture of the loop step failed: this step variant runs in stream mode");
+    return rc != QD_OK ? rc : QD_E_STATE;
   }
   c->step_graphs[key] = std::make_pair(exec, per_step);
   QD_CUDA(c, cudaGraphLaunch(exec, c->stream));     // counters were advanced by the capture pass
@@ -1824,10 +1874,13 @@ extern "C" int qd_loop_step(qd_ctx* c, const qd_step_cfg_t* cfg, const qd_forcin
   QD_BOUND(c);
   { const int rc = qd_derive(c, cfg->dt); if (rc) return rc; }
   if (nsteps > c->forcing_cap) {
-    QD_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_forcing);
-    c->forcing_cap = std::max(nsteps, 64);
-    QD_CUDA(c, cudaMalloc((void**)&c->d_forcing, (size_t)c->forcing_cap * sizeof(qd_forcing_t)));
+    // the forcing table has a fixed capacity (captured graphs hold its address): longer calls run as chunks; the
+    // upload of chunk k+1 is ordered behind the kernels of chunk k on the same stream
+    for (int s0 = 0; s0 < nsteps; s0 += c->forcing_cap) {
+      const int rc = qd_loop_step(c, cfg, forcing + s0, std::min(c->forcing_cap, nsteps - s0));
+      if (rc) return rc;
+    }
+    return QD_OK;
   }
   if (nsteps == 1) {
     // one step per call (the interactive / end-to-end pattern): the 80 bytes of orbital scalars travel as a kernel

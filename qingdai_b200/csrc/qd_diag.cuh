@@ -21,7 +21,7 @@ struct QdDiagArgs {
   const double *ts, *h, *q, *cloud, *hice, *wland, *ssnow, *eflux, *precip, *rland, *albedo, *sst, *isr, *cloud_eff, *lh, *u, *v, *uo, *vo, *eta;
   const uint8_t* land;
   int has_cloud_eff;
-  double* part;          // [B][QD_DIAG_COUNT][gridDim.x]
+  double* part;          // [B][QD_DIAG_COUNT][nvb]
   unsigned* ticket;
   double* out;           // [B][QD_DIAG_COUNT]
 };
@@ -39,10 +39,12 @@ QD_D double qd_diag_identity(int q) {
 
 __global__ void __launch_bounds__(QD_THREADS) k_diag(QdGeo g, QdDiagArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
+  double* part = A.part + ((size_t)blockIdx.y * QD_DIAG_COUNT) * g.nvb;
+  QD_VB_LOOP(g) {
   double acc[QD_DIAG_COUNT];
 #pragma unroll
   for (int q = 0; q < QD_DIAG_COUNT; ++q) acc[q] = qd_diag_identity(q);
-  QD_CELL_LOOP(g) {
+  QD_VB_CELLS(g, g.ncomp) {
     QD_CELL_JI(g)
     if (!qd_owned(g, j)) continue;
     const size_t c = off + idx;
@@ -72,13 +74,12 @@ __global__ void __launch_bounds__(QD_THREADS) k_diag(QdGeo g, QdDiagArgs A) {
     if (ts > acc[QD_D_TS_MAX]) acc[QD_D_TS_MAX] = ts;
   }
   // block reduction of every quantity: warp shuffles, then one value per warp through shared memory
-  double* part = A.part + ((size_t)b * QD_DIAG_COUNT) * gridDim.x;
 #if QD_EMU
   static thread_local double eacc[QD_DIAG_COUNT];
   static thread_local unsigned ecnt = 0;
   if (ecnt == 0) for (int q = 0; q < QD_DIAG_COUNT; ++q) eacc[q] = qd_diag_identity(q);
   for (int q = 0; q < QD_DIAG_COUNT; ++q) eacc[q] = qd_diag_combine(q, eacc[q], acc[q]);
-  if (++ecnt == blockDim.x) { for (int q = 0; q < QD_DIAG_COUNT; ++q) part[(size_t)q * gridDim.x + blockIdx.x] = eacc[q]; ecnt = 0; }
+  if (++ecnt == blockDim.x) { for (int q = 0; q < QD_DIAG_COUNT; ++q) part[(size_t)q * g.nvb + vb_] = eacc[q]; ecnt = 0; }
 #else
   __shared__ double sm[QD_DIAG_COUNT][QD_THREADS / 32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -93,14 +94,16 @@ __global__ void __launch_bounds__(QD_THREADS) k_diag(QdGeo g, QdDiagArgs A) {
     const int q = threadIdx.x;
     double v = sm[q][0];
     for (int k = 1; k < QD_THREADS / 32; ++k) v = qd_diag_combine(q, v, sm[q][k]);
-    part[(size_t)q * gridDim.x + blockIdx.x] = v;
+    part[(size_t)q * g.nvb + vb_] = v;
   }
+  __syncthreads();                         // sm[][] is reused by the next virtual block
 #endif
-  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
+  }
+  if (qd_block_is_last(A.ticket + blockIdx.y, gridDim.x)) {
     QD_BLOCK_LAST_FOR(q, QD_DIAG_COUNT) {
       double v = qd_diag_identity(q);
-      for (unsigned k = 0; k < gridDim.x; ++k) v = qd_diag_combine(q, v, QD_LDCG(part + (size_t)q * gridDim.x + k));
-      A.out[(size_t)b * QD_DIAG_COUNT + q] = v;
+      for (int k = 0; k < g.nvb; ++k) v = qd_diag_combine(q, v, QD_LDCG(part + (size_t)q * g.nvb + k));
+      A.out[(size_t)blockIdx.y * QD_DIAG_COUNT + q] = v;
     }
   }
 }

@@ -31,39 +31,41 @@ QD_D double qd_eco_total(const QdEcoArgs& A, const QdGeo& g, int b, int idx) {
 }
 
 __global__ void __launch_bounds__(QD_THREADS) k_eco_stats(QdGeo g, QdEcoArgs A) {
-  double sd = 0.0, nd = 0.0, sb = 0.0, nb = 0.0;
-  QD_CELL_LOOP(g) {
-    QD_CELL_JI(g)
-    if (!qd_owned(g, j)) continue;
-    const double now = qd_eco_total(A, g, b, idx);
-    const double s = A.snap[off + idx];
-    const double d = fabs(now - s);
-    if (d == d) { sd += d; nd += 1.0; }                     // nanmean skips NaN
-    const double m = qd_max(s, 1e-6);
-    if (m == m) { sb += m; nb += 1.0; }
-  }
   double t;
-  const size_t pb = (size_t)b * gridDim.x;
-  if (qd_block_sum<0>(sd, &t)) A.part[0][pb + blockIdx.x] = t;
-  if (qd_block_sum<1>(nd, &t)) A.part[1][pb + blockIdx.x] = t;
-  if (qd_block_sum<2>(sb, &t)) A.part[2][pb + blockIdx.x] = t;
-  if (qd_block_sum<3>(nb, &t)) A.part[3][pb + blockIdx.x] = t;
+  const size_t pb = (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double sd = 0.0, nd = 0.0, sb = 0.0, nb = 0.0;
+    QD_VB_CELLS(g, g.ncomp) {
+      QD_CELL_JI(g)
+      if (!qd_owned(g, j)) continue;
+      const double now = qd_eco_total(A, g, b, idx);
+      const double s = A.snap[off + idx];
+      const double d = fabs(now - s);
+      if (d == d) { sd += d; nd += 1.0; }                     // nanmean skips NaN
+      const double m = qd_max(s, 1e-6);
+      if (m == m) { sb += m; nb += 1.0; }
+    }
+    if (qd_block_sum<0>(sd, &t)) A.part[0][pb + vb_] = t;
+    if (qd_block_sum<1>(nd, &t)) A.part[1][pb + vb_] = t;
+    if (qd_block_sum<2>(sb, &t)) A.part[2][pb + vb_] = t;
+    if (qd_block_sum<3>(nb, &t)) A.part[3][pb + vb_] = t;
+  }
   if (qd_block_is_last(A.ticket + b, gridDim.x)) {
     double Sd = 0.0, Nd = 0.0, Sb = 0.0, Nb = 0.0;
-    const bool o0 = qd_final_sum<4>(A.part[0] + pb, gridDim.x, &Sd);
+    const bool o0 = qd_final_sum<4>(A.part[0] + pb, g.nvb, &Sd);
 #if !QD_EMU
     __shared__ double keep[4];
     if (o0) keep[0] = Sd;
-    if (qd_final_sum<5>(A.part[1] + pb, gridDim.x, &Nd)) keep[1] = Nd;
-    if (qd_final_sum<6>(A.part[2] + pb, gridDim.x, &Sb)) keep[2] = Sb;
-    if (qd_final_sum<7>(A.part[3] + pb, gridDim.x, &Nb)) keep[3] = Nb;
+    if (qd_final_sum<5>(A.part[1] + pb, g.nvb, &Nd)) keep[1] = Nd;
+    if (qd_final_sum<6>(A.part[2] + pb, g.nvb, &Sb)) keep[2] = Sb;
+    if (qd_final_sum<7>(A.part[3] + pb, g.nvb, &Nb)) keep[3] = Nb;
     __syncthreads();
     Sd = keep[0]; Nd = keep[1]; Sb = keep[2]; Nb = keep[3];
     const bool one = threadIdx.x == 0;
 #else
-    qd_final_sum<5>(A.part[1] + pb, gridDim.x, &Nd);
-    qd_final_sum<6>(A.part[2] + pb, gridDim.x, &Sb);
-    qd_final_sum<7>(A.part[3] + pb, gridDim.x, &Nb);
+    qd_final_sum<5>(A.part[1] + pb, g.nvb, &Nd);
+    qd_final_sum<6>(A.part[2] + pb, g.nvb, &Sb);
+    qd_final_sum<7>(A.part[3] + pb, g.nvb, &Nb);
     const bool one = o0;
 #endif
     if (one) {

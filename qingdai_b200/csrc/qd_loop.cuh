@@ -19,23 +19,25 @@ __global__ void __launch_bounds__(QD_THREADS) k_precip_a(QdGeo g, QdPrecipAArgs 
   if (A.hcos && blockIdx.y == 0) {           // forcing.py:118-131, consumed by k_column later in the step
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nlon; i += gridDim.x * blockDim.x) qd_forcing_col(g, A.forcing, A.step_idx, A.hcos, i);
   }
-  double contrib = 0.0;
-  QD_CELL_LOOP(g) {
-    QD_CELL_JI(g)
-    const size_t c = off + idx;
-    const double div = qd_div_cell(A.u + off, A.v + off, j, i, g);
-    A.pos[c] = qd_max(0.0, -(div - P[QD_P_D_CRIT]));
-    if (qd_owned(g, j)) contrib += qd_max(0.0, A.pcond[c]) * qd_row(g, QD_R_W)[j];
-    if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) {           // physics.py:154-156
-      const double up = qd_max(0.0, A.u[c] * A.nx[c] + A.v[c] * A.ny[c]);
-      A.orog_raw[c] = qd_clip(1.0 + P[QD_P_K_OROG] * up, 1.0, 2.0);
-    }
-  }
   double t;
-  double* part = A.part + (size_t)b * gridDim.x;
-  if (qd_block_sum<0>(contrib, &t)) part[blockIdx.x] = t;
-  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
-    if (qd_final_sum<1>(part, gridDim.x, &t)) g.scal[(size_t)b * QD_S_COUNT + QD_S_SUM_PQW] = t;
+  double* part = A.part + (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double contrib = 0.0;
+    QD_VB_CELLS(g, g.ncomp) {
+      QD_CELL_JI(g)
+      const size_t c = off + idx;
+      const double div = qd_div_cell(A.u + off, A.v + off, j, i, g);
+      A.pos[c] = qd_max(0.0, -(div - P[QD_P_D_CRIT]));
+      if (qd_owned(g, j)) contrib += qd_max(0.0, A.pcond[c]) * qd_row(g, QD_R_W)[j];
+      if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) {           // physics.py:154-156
+        const double up = qd_max(0.0, A.u[c] * A.nx[c] + A.v[c] * A.ny[c]);
+        A.orog_raw[c] = qd_clip(1.0 + P[QD_P_K_OROG] * up, 1.0, 2.0);
+      }
+    }
+    if (qd_block_sum<0>(contrib, &t)) part[vb_] = t;
+  }
+  if (qd_block_is_last(A.ticket + blockIdx.y, gridDim.x)) {
+    if (qd_final_sum<1>(part, g.nvb, &t)) g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUM_PQW] = t;
   }
 }
 
@@ -47,27 +49,29 @@ struct QdPrecipBArgs {
 };
 __global__ void __launch_bounds__(QD_THREADS) k_precip_b(QdGeo g, QdPrecipBArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
-  double contrib = 0.0;
   // the median scale is the same for every cell of a member (one reciprocal per thread, amortised over its cells);
   // pos is zero wherever the flow diverges
   const QdRcp scale = qd_rcp(fmax(qd_scal(g, (int)blockIdx.y, QD_S_MED_POS), 1e-12));
-  QD_CELL_LOOP(g) {
-    QD_CELL_JI(g)
-    const size_t c = off + idx;
-    double F_div = 0.0;
-    if (qd_scal(g, b, QD_S_CNT_POS) > 0.0) F_div = qd_clip(qd_div_u(A.pos[c], scale), 0.0, 5.0);
-    double F_or = 1.0;
-    if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) F_or = qd_clip(A.orog[c], 1.0, 3.0);
-    const double F = (1.0 + P[QD_P_BETA_DIV] * F_div) * F_or;
-    const double praw = qd_max(0.0, A.pcond[c]) * F;
-    A.praw[c] = praw;
-    if (qd_owned(g, j)) contrib += praw * qd_row(g, QD_R_W)[j];
-  }
   double t;
-  double* part = A.part + (size_t)b * gridDim.x;
-  if (qd_block_sum<0>(contrib, &t)) part[blockIdx.x] = t;
-  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
-    if (qd_final_sum<1>(part, gridDim.x, &t)) g.scal[(size_t)b * QD_S_COUNT + QD_S_SUM_PRAWW] = t;
+  double* part = A.part + (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double contrib = 0.0;
+    QD_VB_CELLS(g, g.ncomp) {
+      QD_CELL_JI(g)
+      const size_t c = off + idx;
+      double F_div = 0.0;
+      if (qd_scal(g, b, QD_S_CNT_POS) > 0.0) F_div = qd_clip(qd_div_u(A.pos[c], scale), 0.0, 5.0);
+      double F_or = 1.0;
+      if (P[QD_P_OROG] != 0.0 && P[QD_P_HAS_ELEVATION] != 0.0) F_or = qd_clip(A.orog[c], 1.0, 3.0);
+      const double F = (1.0 + P[QD_P_BETA_DIV] * F_div) * F_or;
+      const double praw = qd_max(0.0, A.pcond[c]) * F;
+      A.praw[c] = praw;
+      if (qd_owned(g, j)) contrib += praw * qd_row(g, QD_R_W)[j];
+    }
+    if (qd_block_sum<0>(contrib, &t)) part[vb_] = t;
+  }
+  if (qd_block_is_last(A.ticket + blockIdx.y, gridDim.x)) {
+    if (qd_final_sum<1>(part, g.nvb, &t)) g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUM_PRAWW] = t;
   }
 }
 

@@ -160,26 +160,28 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
   const double al = P[QD_P_OC_ADV_ALPHA];
-  double contrib = 0.0;
-  QD_CELL_LOOP_N(g, done ? 0 : g.ncomp) {
-    QD_CELL_JI(g)
-    const size_t c = off + idx;
-    const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);
-    double e = A.eta_in[c] + (-sub_dt * P[QD_P_OC_H] * div);
-    const bool land = A.land[c] == 1;
-    if (land) e = 0.0;
-    A.eta[c] = e;
-    if (qd_owned(g, j)) contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
-    double y, x;
-    qd_departure(A.ub[c], A.vb[c], sub_dt, g, qd_row(g, QD_R_COS_ADV_HALF)[j], qd_row(g, QD_R_INV_ACOS_HALF)[j], j, i, &y, &x);
-    const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
-    A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
-  }
   double t;
-  double* part = A.part + (size_t)b * gridDim.x;
-  if (qd_block_sum<0>(contrib, &t)) part[blockIdx.x] = t;
-  if (qd_block_is_last(A.ticket + b, gridDim.x)) {
-    if (qd_final_sum<1>(part, gridDim.x, &t)) { if (!done) g.scal[(size_t)b * QD_S_COUNT + QD_S_ETA_NUM] = t; }
+  double* part = A.part + (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double contrib = 0.0;
+    QD_VB_CELLS(g, done ? 0 : g.ncomp) {
+      QD_CELL_JI(g)
+      const size_t c = off + idx;
+      const double div = qd_div_cell(A.ub + off, A.vb + off, j, i, g);
+      double e = A.eta_in[c] + (-sub_dt * P[QD_P_OC_H] * div);
+      const bool land = A.land[c] == 1;
+      if (land) e = 0.0;
+      A.eta[c] = e;
+      if (qd_owned(g, j)) contrib += e * (qd_row(g, QD_R_W)[j] * (land ? 0.0 : 1.0));
+      double y, x;
+      qd_departure(A.ub[c], A.vb[c], sub_dt, g, qd_row(g, QD_R_COS_ADV_HALF)[j], qd_row(g, QD_R_INV_ACOS_HALF)[j], j, i, &y, &x);
+      const double adv = qd_bilinear_wrap(A.sst + off, g.nlat, g.nlon, y, x);
+      A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
+    }
+    if (qd_block_sum<0>(contrib, &t)) part[vb_] = t;
+  }
+  if (qd_block_is_last(A.ticket + blockIdx.y, gridDim.x)) {
+    if (qd_final_sum<1>(part, g.nvb, &t)) { if (!done) g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_ETA_NUM] = t; }
   }
 }
 

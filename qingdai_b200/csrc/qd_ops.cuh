@@ -60,6 +60,7 @@ struct QdGeo {
   // rows of up to two segments [sa0,sa1) u [sb0,sb1) (its own rows [own0,own1) widened by the halo the
   // inputs allow; the second segment is the part that wraps over a pole).  One rank: sa = own = [0, nlat).
   int own0, own1, sa0, sa1, sb0, sb1, ncomp;
+  int nvb;                       // virtual blocks per member of the sum reductions (QD_VB_LOOP): a function of the grid size only
   unsigned long long div_nlon;   // floor(2^40 / nlon) + 1: t / nlon == (t * div_nlon) >> 40 for t * nlon < 2^40
 };
 QD_HD int qd_div_nlon(const QdGeo& g, int t) { return (int)(((unsigned long long)(unsigned)t * g.div_nlon) >> 40); }
@@ -106,6 +107,19 @@ QD_HD bool qd_owned(const QdGeo& g, int j) { return j >= g.own0 && j < g.own1; }
   (void)off;                                                          \
   _Pragma("unroll 2")                                                 \
   for (int t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < (limit); t_ += gridDim.x * blockDim.x)
+// Sums whose value feeds back into the fields (precipitation renormalisation, the ocean's eta mean, diagnostics) are
+// formed per VIRTUAL block: geo.nvb of them per member, a function of the grid size only.  A physical block takes
+// virtual blocks vb = blockIdx.x, blockIdx.x + gridDim.x, ...; virtual block vb owns cells vb*256 + t + k*nvb*256.
+// Partials are stored per virtual block and combined in that order, so the result does not depend on how many
+// physical blocks the launch has -- i.e. not on how many ensemble members share the GPU (B = 8 gives the bits of B = 1).
+#define QD_VB_LOOP(geo)                                               \
+  const int b = blockIdx.y;                                           \
+  const size_t off = (size_t)b * (geo).ncell;                         \
+  (void)off;                                                          \
+  for (int vb_ = blockIdx.x; vb_ < (geo).nvb; vb_ += gridDim.x)
+#define QD_VB_CELLS(geo, limit)                                       \
+  _Pragma("unroll 2")                                                 \
+  for (int t_ = vb_ * blockDim.x + threadIdx.x; t_ < (limit); t_ += (geo).nvb * blockDim.x)
 #define QD_CELL_JI(geo)                                               \
   const int r_ = qd_div_nlon((geo), t_); const int i = t_ - r_ * (geo).nlon; \
   const int j = qd_seg_row((geo), r_); const int idx = j * (geo).nlon + i; (void)i; (void)j; (void)idx;
@@ -483,12 +497,14 @@ __global__ void __launch_bounds__(QD_THREADS) k_zonal_bandstop(QdGeo g, double* 
 // partials are combined in a fixed order by the last block to finish.
 __global__ void __launch_bounds__(QD_THREADS) k_wsum(QdGeo g, const double* x, const double* wrow,
                                                     double* partial, unsigned* ticket, double* out, int out_stride) {
-  double v = 0.0;
-  QD_CELL_LOOP(g) { QD_CELL_JI(g) if (qd_owned(g, j)) v += x[off + idx] * (wrow ? wrow[j] : 1.0); }
   double tot;
-  double* part = partial + (size_t)b * gridDim.x;
-  if (qd_block_sum<0>(v, &tot)) part[blockIdx.x] = tot;
-  if (qd_block_is_last(ticket + b, gridDim.x)) {
-    if (qd_final_sum<1>(part, gridDim.x, &tot)) out[(size_t)b * out_stride] = tot;
+  double* part = partial + (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double v = 0.0;
+    QD_VB_CELLS(g, g.ncomp) { QD_CELL_JI(g) if (qd_owned(g, j)) v += x[off + idx] * (wrow ? wrow[j] : 1.0); }
+    if (qd_block_sum<0>(v, &tot)) part[vb_] = tot;
+  }
+  if (qd_block_is_last(ticket + blockIdx.y, gridDim.x)) {
+    if (qd_final_sum<1>(part, g.nvb, &tot)) out[(size_t)blockIdx.y * out_stride] = tot;
   }
 }

@@ -63,6 +63,7 @@ extern "C" int qd_route_setup(qd_ctx* c, int n_order, const int64_t* flow_order,
                               int n_lakes, const int64_t* lake_outlet) {
   if (!c || n_order < 0 || !flow_order || !flow_to || !land) return QD_E_INVALID;
   QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  qd_drop_graphs(c);                               // captured steps hold the old network's buffer pointers
   qd_route_free(c->route);
   qd_route& R = c->route;
   const int n = c->ncell;

@@ -234,9 +234,8 @@ class Engine:
             self._connect_band(*band)
         r1, w1 = gaussian_taps(1.0)
         self._chk(self.lib.qd_set_gauss(self.ctx, 0, r1, 0, _ptr(w1)), "qd_set_gauss")
-        sig = self.params[0].cloud_smooth_sigma
-        rc_, wc = gaussian_taps(sig if sig > 0 else 0.2)
-        self._chk(self.lib.qd_set_gauss(self.ctx, 1, rc_, 1, _ptr(wc)), "qd_set_gauss")
+        self._cloud_sigma = None
+        self._upload_cloud_gauss()
         self._finalizer = weakref.finalize(self, self.lib.qd_destroy, self.ctx)
 
     # ---------------------------------------------------------------- latitude bands (SURVEY 8e, configs[4])
@@ -278,11 +277,20 @@ class Engine:
             out[a:b] = rows
         return out
 
+    def _upload_cloud_gauss(self):
+        """Taps of the cloud tracer's wrap Gaussian (run_simulation.py:1931, QD_CLOUD_SMOOTH_SIGMA); re-sent when the sigma changes."""
+        sig = self.params[0].cloud_smooth_sigma
+        if sig == self._cloud_sigma:
+            return
+        rc_, wc = gaussian_taps(sig if sig > 0 else 0.2)
+        self._chk(self.lib.qd_set_gauss(self.ctx, 1, rc_, 1, _ptr(wc)), "qd_set_gauss")
+        self._cloud_sigma = sig
+
     # launch structure (which kernels run, cadences) is shared by the members of one batch; every
     # continuous parameter (P vector, K4 / sponge / polar rows) is per member
     _SWITCHES = ("diff_enable", "filter_type", "diff_every", "k4_nsub", "diff_q", "diff_cloud", "shapiro_every", "shapiro_n",
                  "spec_every", "spec_cutoff", "spec_damp", "oc_diff_every", "oc_k4_nsub", "oc_shapiro_n",
-                 "oc_shapiro_every", "cloud_smooth_sigma", "k4_q", "k4_c")
+                 "oc_shapiro_every", "cloud_smooth_sigma", "k4_q", "k4_c", "cloud_advect", "orog_enabled")
 
     def _check_uniform_switches(self):
         p0 = self.params[0]
@@ -313,6 +321,7 @@ class Engine:
             self._chk(self.lib.qd_set_rows_member(self.ctx, b, _ptr(rows)), "qd_set_rows_member")
         pv = self._param_block()
         self._chk(self.lib.qd_set_params(self.ctx, _ptr(pv)), "qd_set_params")
+        self._upload_cloud_gauss()
         p0 = self.params[0]
         for slot, name in ((2, "oc_k4_u"), (3, "oc_k4_v"), (4, "oc_k4_eta")):    # ocean.py:350-352
             if any((getattr(p, name) is None) != (getattr(p0, name) is None) for p in self.params):
@@ -329,6 +338,12 @@ class Engine:
     def use_graphs(self, enable=True):
         """Ocean sub-step loop as a CUDA-graph WHILE node (default) or as a host loop with a read-back."""
         self._chk(self.lib.qd_use_graphs(self.ctx, int(enable) if not isinstance(enable, bool) else (2 if enable else 0)), "qd_use_graphs")
+
+    def graph_status(self):
+        """{"live": cached CUDA graphs, "failed": captures that fell back to stream mode} (qd_graph_status)."""
+        a, b = C.c_int(), C.c_int()
+        self._chk(self.lib.qd_graph_status(self.ctx, C.byref(a), C.byref(b)), "qd_graph_status")
+        return {"live": a.value, "failed": b.value}
 
     def sync(self):
         self._chk(self.lib.qd_synchronize(self.ctx), "qd_synchronize")
@@ -429,6 +444,7 @@ class Engine:
     # ---------------------------------------------------------------- step configuration
     def step_cfg(self, dt, has_albedo=False, with_ocean=True, with_hydrology=True, with_routing=False,
                  with_eco=False, loop_with_albedo=False, oc_has_q=True, oc_has_ice=True, store_isr_ab=True):
+        self._check_uniform_switches()        # cadences / filter switches come from member 0: a batch that disagrees must not run
         p = self.params[0]
         rows = self._rows
         c = StepCfg()

@@ -1,6 +1,6 @@
 """Fused script loop: the per-step body of scripts/run_simulation.py:1760-2344 on the device.
 
-``Simulation`` is what ``qingdai_b200.run_simulation.main`` drives and what bench.py times: state
+``Simulation`` is what ``qingdai_b200.run_simulation.main`` (the env-driven entry point) drives and what bench.py times: state
 lives in HBM, each step consumes one ``qd_forcing_t`` (10 doubles) and nothing comes back unless
 asked for (diagnostics / plots / autosave pull fields through the C ABI on demand).
 """
@@ -51,7 +51,10 @@ class Simulation:
             e.set("base_albedo", tp["base_albedo"], member=b)
             land = np.asarray(tp["land_mask"])
             e.set("cs_map", np.where(land == 1, plist[b].Cs_land, plist[b].Cs_ocean).astype(float), member=b)
-        if topos[0].get("elevation") is not None:
+        has_elev = [tp.get("elevation") is not None for tp in topos]
+        if any(has_elev) != all(has_elev):
+            raise ValueError("ensemble members of one batch must all come with an elevation map or all without (one launch structure)")
+        if has_elev[0]:
             for b, tp in enumerate(topos):
                 e.set_elevation(tp["elevation"], member=b)
         self.reset_state()

@@ -30,3 +30,21 @@ def make_topography(nlat, nlon, seed=42, land_frac=0.29, scale_m=4500.0):
     base_albedo = np.where(land == 1, 0.30, 0.08).astype(np.float64)
     friction = np.where(land == 1, 1.0e-5, 1.0e-6).astype(np.float64)
     return dict(land_mask=land, elevation=elevation, base_albedo=base_albedo, friction=friction)
+
+
+def load_reference_topography(path, nlat, nlon, roll_columns=0):
+    """QD_TOPO_NC path of the script (run_simulation.py:1198-1203): a topography file written by the reference's
+    ``scripts/generate_topography.py`` read through ``load_topography_from_netcdf`` (bilinear / nearest regrid when the
+    grid differs, as the reference's loader does for a coarser file).  ``roll_columns`` rotates the planet in longitude
+    (the 0/360 seam column stays a duplicate): distinct but equally reference-made masks for ensemble members."""
+    from .grid import SphericalGrid
+    from .restart import load_topography_from_netcdf
+    elev, mask, alb, fric = load_topography_from_netcdf(path, SphericalGrid(nlat, nlon))
+    out = dict(land_mask=np.ascontiguousarray(mask, dtype=np.uint8), elevation=np.ascontiguousarray(elev, dtype=np.float64),
+               base_albedo=np.ascontiguousarray(alb, dtype=np.float64), friction=np.ascontiguousarray(fric, dtype=np.float64))
+    k = int(roll_columns) % max(nlon - 1, 1)
+    if k:
+        for name, a in out.items():
+            r = np.roll(a[:, :-1], k, axis=1)
+            out[name] = np.ascontiguousarray(np.concatenate([r, r[:, :1]], axis=1))
+    return out

@@ -747,6 +747,44 @@ def gen_restart():
     print("restart_golden.npz:", len(out), "arrays")
 
 
+# ------------------------------------------------------------------------------------ reference-generated inputs
+def gen_topo():
+    """The bench / parity inputs SURVEY 8(d) prescribes, produced by the reference's own generators:
+    * ``topography_qingdai_181x360_seed42.nc``: scripts/generate_topography.py defaults (:60-61 -- 181x360, seed 42,
+      land 0.40; elevation parameters :64-75) through pygcm.topography.generate_elevation_map /
+      create_land_sea_mask_from_elevation / generate_base_properties / export_topography_to_netcdf, written through the
+      NetCDF-3 shim (float32 variables, exactly what the reference's exporter stores and what QD_TOPO_NC reads back);
+    * ``default_mask_181x360.npz``: the built-in path of scripts/run_simulation.py:1212-1213 for BASELINE configs[0]
+      (create_land_sea_mask(grid) = land 0.29, seed 42, and generate_base_properties(mask))."""
+    sys.path.insert(0, ROOT)
+    from qingdai_b200 import ncio
+    assert ncio.install_netcdf4_shim(), "a real netCDF4 is installed: record with it instead"
+    set_env()
+    from pygcm.grid import SphericalGrid
+    from pygcm import topography as T
+    grid = SphericalGrid(n_lat=181, n_lon=360)
+    params = {"N_CONTINENTS": 3, "CONTINENT_SIGMA_DEG": 30.0, "CONTINENT_SHAPE_P": 2.0, "CONT_MIN_DIST_DEG": 40.0, "W_VLF": 0.35,
+              "FBM_OCTAVES": 5, "HURST_H": 0.8, "W1": 1.0, "W3": 0.6, "SCALE_M": 4500.0}
+    with quiet():
+        elevation = T.generate_elevation_map(grid, seed=42, params=params)
+        land_mask, sea_level = T.create_land_sea_mask_from_elevation(elevation, grid, target_land_frac=0.40)
+        base_albedo, friction = T.generate_base_properties(land_mask, elevation=elevation, grid=grid)
+        path = os.path.join(OUT, "topography_qingdai_181x360_seed42.nc")
+        T.export_topography_to_netcdf(grid=grid, elevation=elevation, land_mask=land_mask, base_albedo=base_albedo,
+                                      friction=friction, sea_level_m=sea_level, out_path=path)
+        # what the reference's loader returns for it on the same grid: pins qingdai_b200.restart.load_topography_from_netcdf
+        e2, m2, a2, f2 = T.load_topography_from_netcdf(path, grid)
+        mask0 = T.create_land_sea_mask(grid)
+        alb0, fric0 = T.generate_base_properties(mask0)
+    w = np.cos(np.deg2rad(grid.lat_mesh))
+    print("topography_qingdai_181x360_seed42.nc: land fraction", float((w * (land_mask == 1)).sum() / w.sum()), "sea level", float(sea_level),
+          "bytes", os.path.getsize(path))
+    np.savez_compressed(os.path.join(OUT, "default_mask_181x360.npz"), land_mask=mask0.astype(np.uint8), base_albedo=alb0, friction=fric0,
+                        topo_loaded_elev_sum=np.array(float(np.sum(e2))), topo_loaded_mask_sum=np.array(int(np.sum(m2))),
+                        topo_loaded_alb_sum=np.array(float(np.sum(a2))), topo_loaded_fric_sum=np.array(float(np.sum(f2))))
+    print("default_mask_181x360.npz: land fraction", float((w * (mask0 == 1)).sum() / w.sum()))
+
+
 def main():
     _install_stubs()
     which = sys.argv[1:] or ["ops", "cores", "loop"]
@@ -766,6 +804,8 @@ def main():
         gen_indiv()
     if "restart" in which:
         gen_restart()
+    if "topo" in which:
+        gen_topo()
 
 
 if __name__ == "__main__":

@@ -185,3 +185,50 @@ def test_small_tile_gaussian_paths_agree(lib):
 
 def test_reference_format_restart(lib):
     qdcheck.check_reference_format_restart(lib)
+
+
+# ---------------------------------------------------------------------------- full loop at the BASELINE sizes (round 2)
+def test_full_loop_181x360_configs1_vs_oracle(lib):
+    """configs[1]: 181x360 full physics on the reference-generated topography, two teacher-forced steps after a
+    10-step spin-up from a cold banded state (sea ice melting and freezing), every field 1e-12."""
+    qdcheck.check_loop_step_vs_oracle(lib, (181, 360), 300.0, spin=10, nsteps=2, cold=True)
+
+
+def test_full_loop_181x360_configs0_vs_oracle(lib, golden):
+    """configs[0]: the default script path (built-in mask, time_step(Teq, dt) without the albedo argument)."""
+    d = golden("default_mask_181x360.npz")
+    topo = dict(land_mask=d["land_mask"], base_albedo=d["base_albedo"], friction=d["friction"], elevation=None)
+    qdcheck.check_loop_step_vs_oracle(lib, (181, 360), 300.0, spin=8, nsteps=2, with_albedo=False, p=qdcheck.QDParams(), topo=topo)
+
+
+def test_full_loop_181x360_configs2_vs_oracle(lib):
+    """configs[2]: + D8 routing + sub-daily ecology, teacher-forced at 1e-12."""
+    qdcheck.check_config3_teacher_forced(lib, (181, 360), nsteps=2, spin=6, dt=300.0, dt_hydro_hours=0.5)
+
+
+def test_full_loop_1441x2880_vs_oracle(lib):
+    """configs[4]: ONE step at 1441x2880 (dt = 37 s) against the oracle after a 6-step spin-up: the in-situ oracle check of
+    the large-grid kernels (fused Gaussian tile epilogues, warp-streaming del^4, fused ocean sub-steps with n_sub > 1)."""
+    qdcheck.check_loop_step_vs_oracle(lib, (1441, 2880), 37.0, spin=6, nsteps=1, cold=True)
+
+
+def test_batch_members_equal_standalone_runs_bitwise(lib):
+    qdcheck.check_batch_equivalence(lib)
+
+
+def test_batch_with_mismatched_switches_raises(lib):
+    qdcheck.check_switch_mismatch_raises(lib)
+
+
+def test_long_call_and_parameter_change_drop_stale_graphs(lib):
+    qdcheck.check_long_call_and_param_change(lib)
+
+
+def test_graphs_are_live(lib):
+    """A failed graph capture would silently halve the step rate: the status query must report live graphs, none failed."""
+    from qingdai_b200.simulation import Simulation
+    from qingdai_b200.synthetic import make_topography
+    sim = Simulation(46, 90, make_topography(46, 90, seed=1, land_frac=0.4), qdcheck.QDParams(energy_w=1.0), dt=300.0, lib=lib, loop_with_albedo=True)
+    sim.step(8)
+    st = sim.engine.graph_status()
+    assert st["failed"] == 0 and st["live"] >= 1, st

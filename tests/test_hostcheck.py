@@ -147,3 +147,25 @@ def test_checkpoint_resume_with_routing_and_ecology(lib, golden):
 
 def test_reference_format_restart(lib):
     qdcheck.check_reference_format_restart(lib)
+
+
+# ---------------------------------------------------------------------------- round 2 checks at CPU-affordable sizes
+def test_full_loop_teacher_forced_from_device_state(lib):
+    qdcheck.check_loop_step_vs_oracle(lib, (31, 60), 600.0, spin=3, nsteps=2, cold=True)
+    qdcheck.check_loop_step_vs_oracle(lib, (31, 60), 300.0, spin=3, nsteps=2, with_albedo=False, p=qdcheck.QDParams())
+
+
+def test_config3_teacher_forced(lib):
+    qdcheck.check_config3_teacher_forced(lib, (31, 60), nsteps=2, spin=3, dt=600.0, dt_hydro_hours=0.5)
+
+
+def test_batch_members_equal_standalone_runs_bitwise(lib):
+    qdcheck.check_batch_equivalence(lib, (19, 36), B=3, nsteps=3)
+
+
+def test_batch_with_mismatched_switches_raises(lib):
+    qdcheck.check_switch_mismatch_raises(lib)
+
+
+def test_long_call_and_parameter_change(lib):
+    qdcheck.check_long_call_and_param_change(lib)
