@@ -62,7 +62,7 @@ typedef enum {
   /* ecology sub-daily (adapter.py:140-186) */
   QD_F_EDAY, QD_F_FCANOPY, QD_F_ALPHA_ECO, QD_F_LAI_SNAP,
   /* private scratch (ping-pong partners and stencil intermediates) */
-  QD_F_X0, QD_F_X1, QD_F_X2, QD_F_X3, QD_F_X4, QD_F_X5, QD_F_X6, QD_F_X7, QD_F_X8, QD_F_X9,
+  QD_F_X0, QD_F_X1, QD_F_X2, QD_F_X3, QD_F_X4, QD_F_X5, QD_F_X6, QD_F_X7, QD_F_X8, QD_F_X9, QD_F_X10,
   QD_F_COUNT
 } qd_field_id;
 
@@ -146,6 +146,8 @@ typedef enum {
   /* ecology canopy-cache clock (population.py:57-71,272-276): accumulated hours, next recompute,
    * cache present, "recomputed in this step" flag */
   QD_S_ECO_HOURS, QD_S_ECO_NEXT, QD_S_ECO_CACHED, QD_S_ECO_FLAG,
+  /* smallest uo^2 + vo^2 whose rounded square root exceeds QD_OCEAN_MAX_U (the per-cell speed test without a sqrt) */
+  QD_S_OC_SPEED2,
   QD_S_COUNT
 } qd_scalar_id;
 
@@ -256,6 +258,11 @@ int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */
 int  qd_set_gauss2d(qd_ctx* ctx, int enable);                 /* 0: force the two-pass Gaussian kernels (tests); default 1 */
 int  qd_set_h4_stream(qd_ctx* ctx, int enable);               /* 0: force the tile kernel for del^4 (tests); default 1 */
+/* 1: the ocean's CFL sub-steps (ocean.py:305-444) run as two kernels -- a warp-streaming kernel that fuses momentum,
+ * del^4 of (uo, vo, eta), continuity, the SST gather and the current hygiene, plus a closing kernel -- instead of four.
+ * Halves the DRAM traffic of a sub-step; on B200 it is fp64-issue bound and measured ~10 % SLOWER than the four-kernel
+ * form, so it is opt-in.  Default 0. */
+int  qd_set_ocean_fused(qd_ctx* ctx, int enable);
 int  qd_launch_count(qd_ctx* ctx, long long* out);            /* kernels launched so far */
 /* per-kernel device time: CUDA events on the launching stream around every launch while enabled */
 int  qd_profile(qd_ctx* ctx, int enable);

@@ -104,6 +104,7 @@ PROTOTYPES = {
     "qd_get_counters": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "qd_set_gauss2d": (_I, [_P, _I]),
     "qd_set_h4_stream": (_I, [_P, _I]),
+    "qd_set_ocean_fused": (_I, [_P, _I]),
     "qd_launch_count": (_I, [_P, C.POINTER(C.c_longlong)]),
     "qd_profile": (_I, [_P, _I]),
     "qd_profile_report": (_I, [_P, C.c_char_p, _I]),

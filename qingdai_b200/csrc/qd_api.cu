@@ -5,6 +5,7 @@
 // stays on the device in the per-member scalar table and is consumed by later kernels.
 #include "qd_loop.cuh"
 #include "qd_hyper4.cuh"
+#include "qd_ocean_fused.cuh"
 #include "qd_eco.cuh"
 #include "qd_gauss2d.cuh"
 #include "qd_phyto.cuh"
@@ -75,7 +76,10 @@ struct qd_ctx {
   std::map<const void*, int> red_cache;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
+  bool ocean_fused = false;                                // set by ocean_substep_body: the last body took the fused two-kernel path
+  int ocean_fused_enable = 0;                              // qd_set_ocean_fused: opt-in (measured slower than the four-kernel form on B200)
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
+    if (ocean_fused) return 6 + 1;                           // pole pass (momentum, 2 x del^4 tiles, continuity) + k_ocean_fused + k_ocean_close + advance
     const long long tiles_i = (nlon + 63) / 64;                  // launch_hyper4: large grids take the stream + pole-tile pair
     const bool stream = h4_stream && nlat >= 96 && nlon >= 64 && tiles_i * ((nlat + 31) / 32) * batch * 3 >= 2 * 148;
     return 3 + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
@@ -87,6 +91,8 @@ struct qd_ctx {
   // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
   QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
+  double* d_oc_k4 = nullptr;                               // [B][3][nlat] k4 rows of the fused ocean sub-step for the current sub_dt
+  double* d_oc_part = nullptr; int oc_npart = 0;           // eta partial sums of the fused ocean sub-step (pole pass + one per warp)
   QdIndivArgs indiv; int indiv_ready;                     // individual pool (qd_indiv.cuh); device arrays owned here
   double *d_diag_part, *d_diag_out;                       // qd_diag scratch
   double *h_diag = nullptr, *h_diag_dev = nullptr;         // pinned, device-mapped result block: k_diag writes straight to the host
@@ -339,6 +345,13 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   if (!c->h_diag) { c->h_diag_dev = nullptr; cudaGetLastError(); }        // no mapped memory: fall back to a device buffer + copy
   QD_ALLOC(c->d_step_idx, sizeof(int));
   QD_ALLOC(c->d_sub_ctr, sizeof(int));
+#ifndef QD_HOST_EMU
+  // eta partial sums of the fused ocean sub-step: nvb slots of the pole pass + one per strip warp (32-row chunks at most)
+  c->oc_npart = std::max(1, std::min(c->nblk, QD_NVB_MAX)) + (((nlon + QD_OF_COLS - 1) / QD_OF_COLS) * ((nlat + 15) / 16) + 2 * QD_OF_WARPS);
+  QD_ALLOC(c->d_oc_part, (size_t)batch * c->oc_npart * 8);
+  QD_ALLOC(c->d_oc_k4, (size_t)batch * 3 * nlat * 8);
+  cudaFuncSetAttribute(k_ocean_fused, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#endif
   c->forcing_cap = QD_FORCING_CAP;                  // fixed: captured step graphs hold this pointer
   QD_ALLOC(c->d_forcing, (size_t)QD_FORCING_CAP * sizeof(qd_forcing_t));
   QD_ALLOC(c->d_hcos, (size_t)2 * nlon * 8);
@@ -396,6 +409,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
   band_release(c);
+  cudaFree(c->d_oc_part); cudaFree(c->d_oc_k4);
   cudaFree(c->d_phyto_tmp); cudaFree(c->d_diag_part); cudaFree(c->d_diag_out); if (c->h_diag) cudaFreeHost(c->h_diag);
   cudaFree((void*)c->indiv.cell); cudaFree((void*)c->indiv.ab); cudaFree((void*)c->indiv.tol); cudaFree(c->indiv.e_day); cudaFree(c->indiv.stress);
   free(c->h_prm);
@@ -471,6 +485,8 @@ extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double*
 // test / tuning switch: 0 forces the shared-memory tile kernel for del^4 at every size (default 1: large grids stream)
 // test / tuning switch: 0 forces the two-pass Gaussian kernels at every size (default 1: large grids use the fused tile kernel)
 extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->g2_fused = enable ? 1 : 0; return QD_OK; }
+// 1: CFL sub-steps of the ocean run as k_ocean_fused + k_ocean_close (qd_ocean_fused.cuh) where the grid allows it; default 0
+extern "C" int qd_set_ocean_fused(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->ocean_fused_enable = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->h4_stream = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
@@ -1476,10 +1492,119 @@ extern "C" int qd_atmos_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   return atmos_core(c, cfg, 0);
 }
 
+#ifndef QD_HOST_EMU
+// Fused form of one CFL sub-step (qd_ocean_fused.cuh): available on one rank, with the default del^4 cadence (one
+// application per sub-step, no ocean Shapiro), on grids large enough to fill the machine with strip warps.
+// Rows per warp chunk of the fused sub-step, 0 = use the four-kernel form.  A warp streams R output rows after a
+// 10-row warm-up; blocks of 4 warps run 3 per SM.  R is chosen to minimise (waves of blocks) x (R + 10): one full wave
+// where the grid allows it (1441x2880: 14 chunks of 102 rows = 420 blocks on 444 slots).
+static int ocean_fused_rows(qd_ctx* c, const qd_step_cfg_t* cfg, bool do_hyper, bool do_shap) {
+  if (!c->ocean_fused_enable || c->band_on || !c->h4_stream || !do_hyper || do_shap || cfg->oc_k4_nsub > 1) return 0;
+  if (c->nlat < 96 || c->nlon < 64) return 0;
+  const int ntj8 = (c->nlat + 7) / 8, ja = 8, jb = (ntj8 - 2) * 8, rows = jb - ja;
+  const long long strips = (long long)((c->nlon + QD_OF_COLS - 1) / QD_OF_COLS) * c->batch;
+  if (strips * ((rows + 31) / 32) < 2 * 148) return 0;                  // too few strip warps even with 32-row chunks
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+  const long long slots = 3LL * sms;
+  if (const char* ov = getenv("QD_OCEAN_FUSED_ROWS")) { const int r = atoi(ov); if (r >= 16) return std::min(r, rows); }   // tuning override
+  int best = 0; long long best_cost = 1LL << 60;
+  for (int nch = 1; nch <= rows / 16; ++nch) {
+    const int R = (rows + nch - 1) / nch;
+    const long long blocks = (((long long)((c->nlon + QD_OF_COLS - 1) / QD_OF_COLS) * ((rows + R - 1) / R) + QD_OF_WARPS - 1) / QD_OF_WARPS) * c->batch;
+    const long long cost = ((blocks + slots - 1) / slots) * (R + 10);
+    if (cost < best_cost) { best_cost = cost; best = R; }
+  }
+  return best;
+}
+// c->geo restricted to rows [a0, a1) u [b0, b1)
+static QdGeo geo_rows(qd_ctx* c, int a0, int a1, int b0, int b1, int* nblk) {
+  QdGeo g = c->geo;
+  g.sa0 = a0; g.sa1 = a1; g.sb0 = b0; g.sb1 = b1;
+  g.ncomp = ((a1 - a0) + (b1 - b0)) * c->nlon;
+  *nblk = std::max(1, (g.ncomp + QD_THREADS - 1) / QD_THREADS);
+  return g;
+}
+static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, int R) {
+  const double* P = c->h_prm;
+  const int ovu = P[QD_P_OC_K4_U] == P[QD_P_OC_K4_U], ovv = P[QD_P_OC_K4_V] == P[QD_P_OC_K4_V], ove = P[QD_P_OC_K4_ETA] == P[QD_P_OC_K4_ETA];
+  QdSubCtl sc{c->d_sub_ctr};
+  const int nlat = c->nlat, ntj8 = (nlat + 7) / 8, ja = 8, jb = (ntj8 - 2) * 8;
+  const int nstrips = (c->nlon + QD_OF_COLS - 1) / QD_OF_COLS;
+  const int nwarps = nstrips * ((jb - ja + R - 1) / R);
+  const int nblocks = (nwarps + QD_OF_WARPS - 1) / QD_OF_WARPS;
+  const int npart = c->geo.nvb + nblocks * QD_OF_WARPS;
+  if (npart > c->oc_npart) return qd_fail(c, QD_E_STATE, "fused ocean sub-step: partial-sum table too small", cudaSuccess);   // sized in qd_create (no allocation inside a captured step)
+  double* uo2[2] = {F(c, QD_F_UO), F(c, QD_F_X9)};
+  double* vo2[2] = {F(c, QD_F_VO), F(c, QD_F_X10)};
+  int nb;
+  // ---- pole pass: momentum rows [0, 13) u [jb-5, nlat) -> del^4 rows [0, 9) u [jb-1, nlat) -> continuity rows [0, 8) u [jb, nlat)
+  {
+    QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
+    Mo.eta = F(c, QD_F_ETA); Mo.uo = uo2[0]; Mo.vo = vo2[0]; Mo.uo_alt = uo2[1]; Mo.vo_alt = vo2[1];
+    Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1); Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
+    const QdGeo gm = geo_rows(c, 0, 13, jb - 5, nlat, &nb);
+    QD_KG(c, k_ocean_momentum, dim3(nb, c->batch), dim3(QD_THREADS), gm, Mo, sc);
+  }
+  QdHyper4Args H; memset(&H, 0, sizeof(H));
+  H.n = 3; H.cosr = ROW(c, QD_R_COS_ADV_HALF); H.dt = 0.0; H.nsub = 1; H.ocean = 1; H.sc = sc;
+  {
+    const double* src3[3] = {F(c, QD_F_X2), F(c, QD_F_X3), F(c, QD_F_ETA)};
+    double* dst3[3] = {F(c, QD_F_X4), F(c, QD_F_X5), F(c, QD_F_X6)};
+    for (int k = 0; k < 3; ++k) { H.src[k] = src3[k]; H.dst[k] = dst3[k]; H.scale[k] = 1.0; H.k4_bstride[k] = c->geo.row_bstride; }
+    H.k4rows[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[0] = ovu;
+    H.k4rows[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[1] = ovv;
+    H.k4rows[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4); H.raw_k4[2] = ove;
+    if (!ove) H.scale[2] = 0.5;                                       // ocean.py:352
+    H.tj_lo = 1 << 30; H.tj_skip = 0; H.ja = 0; H.jb = 0;
+    const int tiles_i = (c->nlon + QD_H4_TI - 1) / QD_H4_TI;
+    H.row0 = 0; H.row1 = 9;
+    QD_KGN(c, "k_hyper4_tile<8>[3]", k_hyper4_tile<8>, dim3(tiles_i * 2, c->batch, 3), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    H.row0 = jb - 1; H.row1 = nlat;
+    QD_KGN(c, "k_hyper4_tile<8>[3]", k_hyper4_tile<8>, dim3(tiles_i * ((nlat - (jb - 1) + 7) / 8), c->batch, 3), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+  }
+  {
+    QdOcContPoleArgs Cp; memset(&Cp, 0, sizeof(Cp));
+    Cp.ub = F(c, QD_F_X4); Cp.vb = F(c, QD_F_X5); Cp.eta_in = F(c, QD_F_X6); Cp.sst = F(c, QD_F_SST);
+    Cp.uo[0] = uo2[0]; Cp.uo[1] = uo2[1]; Cp.vo[0] = vo2[0]; Cp.vo[1] = vo2[1];
+    Cp.eta_out = F(c, QD_F_X7); Cp.tb = F(c, QD_F_X8); Cp.part = c->d_oc_part; Cp.npart = npart; Cp.land = M(c, QD_M_LAND);
+    const QdGeo gp = geo_rows(c, 0, 8, jb, nlat, &nb);
+    QD_KG(c, k_ocean_cont_pole, dim3(std::min(nb, gp.nvb), c->batch), dim3(QD_THREADS), gp, Cp, sc);
+  }
+  // ---- rows [8, jb): the streaming kernel; its last block totals the eta sum (pole partials included)
+  {
+    QdOcFusedArgs A; memset(&A, 0, sizeof(A));
+    A.uo[0] = uo2[0]; A.uo[1] = uo2[1]; A.vo[0] = vo2[0]; A.vo[1] = vo2[1];
+    A.eta = F(c, QD_F_ETA); A.taux = F(c, QD_F_X0); A.tauy = F(c, QD_F_X1); A.sst = F(c, QD_F_SST);
+    A.eta_out = F(c, QD_F_X7); A.tb = F(c, QD_F_X8); A.land = M(c, QD_M_LAND);
+    A.k4tab = c->d_oc_k4;
+    A.part = c->d_oc_part; A.part_off = c->geo.nvb; A.npart = npart; A.ticket = c->d_ticket + 5 * c->batch;
+    A.ja = ja; A.jb = jb;
+    A.R = R;
+    QD_KG(c, k_ocean_fused, dim3(nblocks, c->batch), dim3(32 * QD_OF_WARPS), c->geo, A, sc);
+  }
+  {
+    QdOcCloseArgs Cl; memset(&Cl, 0, sizeof(Cl));
+    Cl.tb = F(c, QD_F_X8); Cl.eta_mid = F(c, QD_F_X7); Cl.qnet = F(c, QD_F_QNET);
+    Cl.uo[0] = uo2[0]; Cl.uo[1] = uo2[1]; Cl.vo[0] = vo2[0]; Cl.vo[1] = vo2[1];
+    Cl.sst = F(c, QD_F_SST); Cl.ts_atm = F(c, QD_F_TS); Cl.eta = F(c, QD_F_ETA);
+    Cl.land = M(c, QD_M_LAND); Cl.ice = M(c, QD_M_ICE);
+    Cl.has_q = cfg->oc_has_q; Cl.has_ice = cfg->oc_has_ice; Cl.inject = inject;
+    QD_K(c, k_ocean_close, c->geo, Cl, sc);
+  }
+  return QD_OK;
+}
+#endif
+
 // ------------------------------------------------------------------------------ ocean step
 // One CFL sub-step body (ocean.py:305-444).  Launched either from a host loop (stream mode) or captured
 // once as the body of a CUDA-graph WHILE node (graph mode); the sub-step index is read from device memory.
 static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap) {
+#ifndef QD_HOST_EMU
+  const int fused_rows = ocean_fused_rows(c, cfg, do_hyper, do_shap);
+  c->ocean_fused = fused_rows > 0;
+  if (c->ocean_fused) return ocean_substep_fused(c, cfg, inject, fused_rows);
+#endif
   const double* P = c->h_prm;   // K4 overrides are shared by all ensemble members (switch-like)
   const int ovu = P[QD_P_OC_K4_U] == P[QD_P_OC_K4_U], ovv = P[QD_P_OC_K4_V] == P[QD_P_OC_K4_V], ove = P[QD_P_OC_K4_ETA] == P[QD_P_OC_K4_ETA];
   QdSubCtl sc{c->d_sub_ctr};
@@ -1602,6 +1727,20 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
   int rc;
   bool launched = false;
+#ifndef QD_HOST_EMU
+  if (ocean_fused_rows(c, cfg, do_hyper, do_shap) > 0) {      // k4 rows of this step's sub_dt for the fused sub-steps
+    const double* Pp = c->h_prm;
+    const int ovu = Pp[QD_P_OC_K4_U] == Pp[QD_P_OC_K4_U], ovv = Pp[QD_P_OC_K4_V] == Pp[QD_P_OC_K4_V], ove = Pp[QD_P_OC_K4_ETA] == Pp[QD_P_OC_K4_ETA];
+    QdOcK4Args K; memset(&K, 0, sizeof(K));
+    K.k4rows[0] = ovu ? QD_USER_ROW(c, 2) : ROW(c, QD_R_OC_S4DX4); K.raw_k4[0] = ovu;
+    K.k4rows[1] = ovv ? QD_USER_ROW(c, 3) : ROW(c, QD_R_OC_S4DX4); K.raw_k4[1] = ovv;
+    K.k4rows[2] = ove ? QD_USER_ROW(c, 4) : ROW(c, QD_R_OC_S4DX4); K.raw_k4[2] = ove;
+    for (int k = 0; k < 3; ++k) { K.k4_bstride[k] = c->geo.row_bstride; K.scale[k] = 1.0; }
+    if (!ove) K.scale[2] = 0.5;                                 // ocean.py:352
+    K.tab = c->d_oc_k4;
+    QD_KG(c, k_ocean_k4tab, dim3((c->nlat + 127) / 128, 3, c->batch), dim3(128), c->geo, K);
+  }
+#endif
 #ifndef QD_HOST_EMU
   if (c->capture_graph) {
     // whole-step capture: splice a WHILE node into the graph being captured (CUDA programming guide,

@@ -85,7 +85,13 @@ struct QdOcMomArgs {
   const double *eta, *uo, *vo, *taux, *tauy;
   double *ub, *vb;
   const uint8_t* land;
+  const double *uo_alt, *vo_alt;      // fused sub-step path (qd_ocean_fused.cuh): the currents ping-pong, parity decided on the device
 };
+QD_D int qd_oc_src(const QdGeo& g, int b, const QdSubCtl& sc) {      // 0: this sub-step reads the home currents, 1: the alternate pair
+  const int n = (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB], s = *sc.ctr;
+  if ((n & 1) && s == 0) return 0;
+  return ((n - s) & 1) ? 1 : 0;
+}
 __global__ void __launch_bounds__(QD_THREADS) k_ocean_momentum(QdGeo g, QdOcMomArgs A, QdSubCtl sc) {
   QD_CELL_PROLOGUE(g)
   if (!active || qd_sub_done(g, b, sc)) return;
@@ -102,7 +108,8 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_momentum(QdGeo g, QdOcMomA
   const double gx = de_dl * qd_row(g, QD_R_INV_ACOS_HALF)[j];
   const double gy = de_dp * g.inv_a;
   const double f = qd_row(g, QD_R_FCOR)[j];
-  double uo = A.uo[c], vo = A.vo[c];
+  const bool alt = A.uo_alt && qd_oc_src(g, b, sc) == 1;
+  double uo = alt ? A.uo_alt[c] : A.uo[c], vo = alt ? A.vo_alt[c] : A.vo[c];
   const double irH = P[QD_P_OC_INV_RHO_H];
   const double du = (f * vo - P[QD_P_OC_G] * gx + A.taux[c] * irH - P[QD_P_OC_R_BOT] * uo);
   const double dv = (-f * uo - P[QD_P_OC_G] * gy + A.tauy[c] * irH - P[QD_P_OC_R_BOT] * vo);

@@ -232,3 +232,21 @@ def test_graphs_are_live(lib):
     sim.step(8)
     st = sim.engine.graph_status()
     assert st["failed"] == 0 and st["live"] >= 1, st
+
+
+def test_fused_ocean_substep_matches_four_kernel_form(lib):
+    """The opt-in fused ocean sub-step (k_ocean_fused / k_ocean_close) against momentum -> del^4 -> continuity -> finish at
+    401x800 (one member) and for a batch of 32 members of 181x360, with sub-step counts 1, 2 and 3 (both parities of the
+    device-side ping-pong of the currents and the copy-back of the first sub-step of an odd count); one sub-step from
+    identical inputs is bit-exact in the currents and the SST."""
+    qdcheck.check_ocean_fused_one_substep(lib)
+    s1 = qdcheck.check_large_grid_paths_agree(lib, shape=(401, 800), nsteps=4, dt=120.0)
+    s2 = qdcheck.check_large_grid_paths_agree(lib, shape=(401, 800), nsteps=3, dt=320.0)
+    s3 = qdcheck.check_large_grid_paths_agree(lib, shape=(181, 360), nsteps=3, dt=300.0, batch=32)
+    seen = s1 | s2 | s3
+    assert any(n % 2 == 0 for n in seen) and any(n % 2 == 1 and n > 1 for n in seen), seen
+
+
+def test_full_loop_1441x2880_fused_ocean_vs_oracle(lib):
+    """The fused ocean sub-step in situ against the oracle (1441x2880, n_sub = 4)."""
+    qdcheck.check_loop_step_vs_oracle(lib, (1441, 2880), 37.0, spin=4, nsteps=1, cold=True, ocean_fused=True)
