@@ -486,7 +486,15 @@ extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double*
 // test / tuning switch: 0 forces the two-pass Gaussian kernels at every size (default 1: large grids use the fused tile kernel)
 extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->g2_fused = enable ? 1 : 0; return QD_OK; }
 // 1: CFL sub-steps of the ocean run as k_ocean_fused + k_ocean_close (qd_ocean_fused.cuh) where the grid allows it; default 0
-extern "C" int qd_set_ocean_fused(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->ocean_fused_enable = enable ? 1 : 0; return QD_OK; }
+extern "C" int qd_set_ocean_fused(qd_ctx* c, int enable) {
+  if (!c) return QD_E_INVALID;
+#ifndef QD_HOST_EMU
+  qd_drop_graphs(c); c->ocean_fused_enable = enable ? 1 : 0;
+#else
+  (void)enable;                   // GPU-only kernels: the host check build keeps the four-kernel form
+#endif
+  return QD_OK;
+}
 extern "C" int qd_set_h4_stream(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->h4_stream = enable ? 1 : 0; return QD_OK; }
 extern "C" int qd_launch_count(qd_ctx* c, long long* out) { if (!c || !out) return QD_E_INVALID; *out = c->launches; return QD_OK; }
 extern "C" int qd_set_counters(qd_ctx* c, int a, int o, int ce) { if (!c) return QD_E_INVALID; c->atm_counter = a; c->oc_counter = o; c->has_cloud_eff = ce; return QD_OK; }
@@ -598,6 +606,11 @@ static int band_prep_v(qd_ctx* c, const std::vector<BIn>& ins, const std::vector
     }
   }
   if (need) {
+    if (getenv("QD_BAND_TRACE") && c->band.rank == 0) {
+      fprintf(stderr, "[band] prep needs:");
+      for (const BIn& in : ins) { const int id = band_fid(c, in.p); if (id >= 0) fprintf(stderr, " %d(v%d r%d)", id, c->band_valid[id] > 99 ? 99 : c->band_valid[id], in.r); }
+      fprintf(stderr, "\n");
+    }
     int ids[32]; int n = 0;
     for (const BIn& in : ins) {
       const int id = band_fid(c, in.p);
@@ -620,6 +633,16 @@ static int band_prep_v(qd_ctx* c, const std::vector<BIn>& ins, const std::vector
   band_set_ext(c, ext);
   for (const void* o : outs) { const int id = band_fid(c, o); if (id >= 0) c->band_valid[id] = ext; }
   return QD_OK;
+}
+// Refill the halos of the listed fields NOW (one exchange) when they are not fully valid.  band_prep exchanges lazily,
+// right before the first kernel that needs a halo, and only what that kernel reads; fields that a later kernel of the
+// same phase will need anyway ride along here, which halves the number of exchanges per step (each one is a
+// neighbour-to-neighbour round trip that no amount of bandwidth shortens).
+static int band_hint(qd_ctx* c, std::initializer_list<int> fids) {
+  if (!c->band_on) return QD_OK;
+  int ids[QD_BAND_MAXX]; int n = 0;
+  for (int id : fids) if (c->band_valid[id] < c->band.H && n < QD_BAND_MAXX) ids[n++] = id;
+  return n ? band_exchange(c, ids, n) : QD_OK;
 }
 static void band_invalidate_dynamic(qd_ctx* c) {            // start of a step / of a sub-step body: fixed point for graph replay
   if (!c->band_on) return;
@@ -1611,9 +1634,13 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
   Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
   Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
-  if (c->band_on)   // loop-carried fields start every sub-step from "own rows only": the body replays unchanged (WHILE node)
+  if (c->band_on) {   // loop-carried fields start every sub-step from "own rows only": the body replays unchanged (WHILE node)
     for (int id : {(int)QD_F_UO, (int)QD_F_VO, (int)QD_F_ETA, (int)QD_F_SST, (int)QD_F_TS, (int)QD_F_X2, (int)QD_F_X3, (int)QD_F_X4,
                    (int)QD_F_X5, (int)QD_F_X6, (int)QD_F_X7, (int)QD_F_X8, (int)QD_F_X9}) c->band_valid[id] = 0;
+    // ONE exchange per sub-step: everything the body's stencils read with a halo (eta: momentum and del^4; currents: del^4,
+    // divergence; SST: gather and diffusion).  The wind stress was exchanged once in ocean_core.
+    { int rcb = band_hint(c, {QD_F_ETA, QD_F_UO, QD_F_VO, QD_F_SST}); if (rcb) return rcb; }
+  }
   BP(c, BL({Mo.eta, 1}, {Mo.uo, 0}, {Mo.vo, 0}, {Mo.taux, 0}, {Mo.tauy, 0}, {Mo.land, 0}), BL(Mo.ub, Mo.vb));
   QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
   double* ub = F(c, QD_F_X2); double* vb = F(c, QD_F_X3); double* eta_cur = F(c, QD_F_ETA);
@@ -1722,6 +1749,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
   QD_KR(c, k_ocean_prep, c->geo, P0);
   { int rcb = band_allreduce(c, {QD_S_MAX_UOCEAN, QD_S_MAX_VA}, true); if (rcb) return rcb; }
   if (c->band_on) QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
+  { int rcb = band_hint(c, {QD_F_X0, QD_F_X1}); if (rcb) return rcb; }      // wind stress: constant over the sub-steps, exchanged once
   QD_CHECK_LAUNCH(c);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
   const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
@@ -1834,6 +1862,9 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if ((c->w_set & 3) != 3) return qd_fail(c, QD_E_STATE, "qd_set_gauss(0|1) must be called before qd_loop_step", cudaSuccess);
   const QdGaussW w1 = c->w_sigma1;
   int rc;
+  // latitude bands: the halos the whole diagnosis phase reads (winds: divergence, vorticity, advection; T_s: cloud source
+  // gradient; cloud: blend + tracer advection) in one exchange instead of three
+  if ((rc = band_hint(c, {QD_F_U, QD_F_V, QD_F_PCOND, QD_F_TS, QD_F_CLOUD}))) return rc;
   // precipitation (physics.py:253-354)
   QdPrecipAArgs Pa; memset(&Pa, 0, sizeof(Pa));
   Pa.u = F(c, QD_F_U); Pa.v = F(c, QD_F_V); Pa.pcond = F(c, QD_F_PCOND); Pa.nx = F(c, QD_F_OROG_NX); Pa.ny = F(c, QD_F_OROG_NY);
