@@ -135,6 +135,9 @@ typedef enum {
   QD_P_WSUM_ALL, QD_P_OC_WSUM_OCEAN, QD_P_OC_ANY_OCEAN,
   /* host-evaluated reciprocals of parameter-only divisors */
   QD_P_OC_INV_RHO_H, QD_P_OC_INV_RHO_CP_H,
+  /* smallest s2 = uo^2 + vo^2 whose correctly rounded square root exceeds QD_OCEAN_MAX_U: the per-cell test
+   * sqrt(s2) > cap of ocean.py:412 becomes s2 >= threshold with identical outcomes and no square root on the common path */
+  QD_P_OC_SPEED2_CAP,
   QD_P_COUNT
 } qd_param_id;
 
@@ -146,8 +149,6 @@ typedef enum {
   /* ecology canopy-cache clock (population.py:57-71,272-276): accumulated hours, next recompute,
    * cache present, "recomputed in this step" flag */
   QD_S_ECO_HOURS, QD_S_ECO_NEXT, QD_S_ECO_CACHED, QD_S_ECO_FLAG,
-  /* smallest uo^2 + vo^2 whose rounded square root exceeds QD_OCEAN_MAX_U (the per-cell speed test without a sqrt) */
-  QD_S_OC_SPEED2,
   QD_S_COUNT
 } qd_scalar_id;
 
@@ -243,6 +244,9 @@ int  qd_advect_host(qd_ctx* ctx, const double* in, const double* u, const double
 /* ------------------------------------------------------------------ step level (bound fields) */
 int  qd_atmos_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* Teq in QD_F_TEQ, albedo in QD_F_ALBEDO */
 int  qd_ocean_step(qd_ctx* ctx, const qd_step_cfg_t* cfg);   /* winds QD_F_U/V, Q in QD_F_QNET, ice in QD_M_ICE */
+/* WindDrivenSlabOcean.step(dt, u_atm, v_atm, ...) with the winds as caller-owned device arrays [B][nlat][nlon]
+ * (ocean.py:265): the atmosphere's QD_F_U/V are not touched */
+int  qd_ocean_step_winds(qd_ctx* ctx, const qd_step_cfg_t* cfg, const double* u_atm_dev, const double* v_atm_dev);
 int  qd_loop_step(qd_ctx* ctx, const qd_step_cfg_t* cfg, const qd_forcing_t* forcing, int nsteps);
 int  qd_last_nsub(qd_ctx* ctx, int* out_host /* [B] */);      /* sync */
 /* 2 (default): a whole loop step is one CUDA graph (kernels, memsets, cooperative selects, WHILE node

@@ -96,6 +96,7 @@ PROTOTYPES = {
     "qd_advect_host": (_I, [_P, _P, _P, _P, _P, _D, _P]),
     "qd_atmos_step": (_I, [_P, C.POINTER(StepCfg)]),
     "qd_ocean_step": (_I, [_P, C.POINTER(StepCfg)]),
+    "qd_ocean_step_winds": (_I, [_P, C.POINTER(StepCfg), _P, _P]),
     "qd_loop_step": (_I, [_P, C.POINTER(StepCfg), C.POINTER(Forcing), _I]),
     "qd_last_nsub": (_I, [_P, _P]),
     "qd_use_graphs": (_I, [_P, _I]),

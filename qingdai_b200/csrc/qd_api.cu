@@ -1737,11 +1737,12 @@ static cudaGraphExec_t ocean_while_graph(qd_ctx* c, const qd_step_cfg_t* cfg, in
 }
 #endif
 
-static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject) {
+static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const double* wind_u = nullptr, const double* wind_v = nullptr) {
   const double dt = cfg->dt;
   c->oc_counter += 1;                        // ocean.py:281
   QdOcPrepArgs P0; memset(&P0, 0, sizeof(P0));
-  P0.u = F(c, QD_F_U); P0.v = F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
+  // winds: the atmosphere's own fields, or the arrays the caller of the stand-alone step passed (ocean.step(dt, u_atm, v_atm))
+  P0.u = wind_u ? wind_u : F(c, QD_F_U); P0.v = wind_v ? wind_v : F(c, QD_F_V); P0.uo = F(c, QD_F_UO); P0.vo = F(c, QD_F_VO);
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
   P0.dt = dt; P0.sub_ctr = c->band_on ? nullptr : c->d_sub_ctr;      // bands: n_sub needs the all-reduced maxima first
@@ -1832,6 +1833,14 @@ extern "C" int qd_ocean_step(qd_ctx* c, const qd_step_cfg_t* cfg) {
   if (!c || !cfg) return QD_E_INVALID;
   QD_BOUND(c);
   return ocean_core(c, cfg, 0);
+}
+// Same step driven by caller-owned wind arrays [B][nlat][nlon] (device) instead of QD_F_U / QD_F_V: the reference's
+// ocean.step(dt, u_atm, v_atm, ...) takes the winds as arguments, and a caller may pass something else than the
+// atmosphere's current winds without disturbing them.
+extern "C" int qd_ocean_step_winds(qd_ctx* c, const qd_step_cfg_t* cfg, const double* u_dev, const double* v_dev) {
+  if (!c || !cfg || !u_dev || !v_dev) return QD_E_INVALID;
+  QD_BOUND(c);
+  return ocean_core(c, cfg, 0, u_dev, v_dev);
 }
 // live = captured step / ocean-loop graphs in the cache; failed = captures that fell back to stream mode since qd_create
 extern "C" int qd_graph_status(qd_ctx* c, int* live, int* failed) {

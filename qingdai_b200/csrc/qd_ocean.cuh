@@ -243,8 +243,9 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   const double* vb = A.vb + off;
   double uo = qd_nan_to_num(ub[idx]), vo = qd_nan_to_num(vb[idx]);
   const double cap = P[QD_P_OC_MAX_U];
-  const double speed = sqrt(uo * uo + vo * vo);
-  if (speed > cap) {
+  const double s2 = uo * uo + vo * vo;
+  if (s2 >= P[QD_P_OC_SPEED2_CAP]) {           // == sqrt(s2) > cap (host-computed threshold, engine.py:speed2_threshold): no sqrt on the common path
+    const double speed = sqrt(s2);
     // ocean.py:408-434.  Cells at or below the cap (and NaN speeds) fall through unchanged: there the reference
     // multiplies by exactly 1.0, so skipping the second sqrt and the scale is bit-identical.
     if (P[QD_P_OC_MEAN4] != 0.0) {

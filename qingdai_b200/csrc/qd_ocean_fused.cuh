@@ -53,27 +53,10 @@ struct QdOcFusedArgs {
 };
 
 // Once per ocean step, after n_sub is known: k4 = scale * (raw ? row : row / max(1e-12, sub_dt)) per row and field
-// (ocean.py:343-352) -- one thread per (row, field, member) -- and the member's speed-cap threshold: the smallest
-// s2 = uo^2 + vo^2 whose correctly rounded square root exceeds QD_OCEAN_MAX_U, so that the per-cell test
-// sqrt(s2) > cap (ocean.py:412) becomes s2 >= threshold with identical outcomes and no square root on the common path.
+// (ocean.py:343-352) -- one thread per (row, field, member).
 struct QdOcK4Args { const double* k4rows[3]; long long k4_bstride[3]; double scale[3]; int raw_k4[3]; double* tab; };
 __global__ void k_ocean_k4tab(QdGeo g, QdOcK4Args A) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y, b = blockIdx.z;
-  if (j == 0 && k == 0) {
-    const double cap = g.prm[(size_t)b * QD_P_COUNT + QD_P_OC_MAX_U];
-    double t;
-    if (cap != cap) t = INFINITY;                       // sqrt(s2) > NaN is never true
-    else if (cap < 0.0) t = 0.0;                        // every non-NaN speed exceeds a negative cap
-    else if (!(cap < DBL_MAX)) t = INFINITY;
-    else {
-      t = cap * cap;
-      if (!(t < DBL_MAX)) t = DBL_MAX;
-      // neighbouring doubles of a non-negative finite value: +-1 on the bit pattern
-      for (int it = 0; it < 64 && t > 0.0 && sqrt(t) > cap; ++it) t = __longlong_as_double(__double_as_longlong(t) - 1);
-      for (int it = 0; it < 64 && !(sqrt(t) > cap); ++it) t = __longlong_as_double(__double_as_longlong(t) + 1);
-    }
-    g.scal[(size_t)b * QD_S_COUNT + QD_S_OC_SPEED2] = t;
-  }
   if (j >= g.nlat) return;
   const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
   double v = A.k4rows[k][(size_t)b * A.k4_bstride[k] + j];
@@ -155,7 +138,7 @@ __device__ __forceinline__ bool qd_of_chunk(const QdGeo& g, const QdOcFusedArgs&
   const size_t off = (size_t)b * g.ncell;
   const double* __restrict__ P = g.prm + (size_t)b * QD_P_COUNT;
   const double sub_dt = g.scal[(size_t)b * QD_S_COUNT + QD_S_SUB_DT];
-  const double speed2_cap = g.scal[(size_t)b * QD_S_COUNT + QD_S_OC_SPEED2];
+  const double speed2_cap = P[QD_P_OC_SPEED2_CAP];
   const double* __restrict__ uo_in = src ? A.uo[1] : A.uo[0];
   const double* __restrict__ vo_in = src ? A.vo[1] : A.vo[0];
   double* __restrict__ uo_out = src ? A.uo[0] : A.uo[1];
@@ -326,7 +309,7 @@ __device__ __forceinline__ bool qd_of_chunk(const QdGeo& g, const QdOcFusedArgs&
       double ev = E5 + (-sub_dt * pH * div);                                                                      \
       if (ldj) ev = 0.0;                                                                                          \
       const double s2 = U5 * U5 + V5 * V5;                                                                        \
-      const bool over = emit && (s2 >= speed2_cap);      /* == sqrt(s2) > cap, see k_ocean_k4tab */               \
+      const bool over = emit && (s2 >= speed2_cap);      /* == sqrt(s2) > cap, engine.py:speed2_threshold */      \
       /* departure point (ocean.py:380, dynamics.py:104-115 form): exact quotients by reciprocal + residual FMAs */ \
       const double cosj = rc5[QD_RC_COSH];                                                                        \
       const double ddx = qd_div_exact(qd_div_exact(U5 * sub_dt, g.a * cosj, rc5[QD_RC_IACH]), g.dlon, g.inv_dlon); \
@@ -462,8 +445,9 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_cont_pole(QdGeo g, QdOcCon
       A.tb[c] = (1.0 - al) * A.sst[c] + al * adv;
       // currents (ocean.py:408-434)
       double uo = qd_nan_to_num(ub[idx]), vo = qd_nan_to_num(vb[idx]);
-      const double speed = sqrt(uo * uo + vo * vo);
-      if (speed > cap) {
+      const double s2 = uo * uo + vo * vo;
+      if (s2 >= P[QD_P_OC_SPEED2_CAP]) {
+        const double speed = sqrt(s2);
         if (P[QD_P_OC_MEAN4] != 0.0) {
           const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
           const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;

@@ -99,6 +99,23 @@ def row_tables(nlat, nlon, p: QDParams, dt):
 _NAN = float("nan")
 
 
+def speed2_threshold(cap):
+    """Smallest double t with sqrt(t) > cap (IEEE sqrt is correctly rounded and monotone, on the host as on the device):
+    ``sqrt(uo*uo + vo*vo) > cap`` (ocean.py:412) and ``uo*uo + vo*vo >= t`` select exactly the same cells."""
+    import math
+    cap = float(cap)
+    if cap != cap or cap == math.inf:
+        return math.inf                      # nothing exceeds a NaN / infinite cap
+    if cap < 0.0:
+        return 0.0                           # every non-NaN speed exceeds a negative cap
+    t = min(cap * cap, 1.7976931348623157e308)
+    while t > 0.0 and math.sqrt(t) > cap:
+        t = math.nextafter(t, 0.0)
+    while not math.sqrt(t) > cap:
+        t = math.nextafter(t, math.inf)
+    return t
+
+
 def param_vector(p: QDParams, nlat, nlon, land_mask=None, has_elevation=False, eco_alpha_leaf=0.0, eco_enable=False):
     """One [QD_P_COUNT] float64 vector from a QDParams snapshot (+ host-evaluated sums)."""
     a = const.PLANET_RADIUS
@@ -162,6 +179,7 @@ def param_vector(p: QDParams, nlat, nlon, land_mask=None, has_elevation=False, e
         eco_alpha_leaf=float(eco_alpha_leaf),
         wsum_all=wsum_all, oc_wsum_ocean=wsum_ocean, oc_any_ocean=any_ocean,
         oc_inv_rho_h=1.0 / (p.oc_rho_w * p.oc_H), oc_inv_rho_cp_h=1.0 / (p.oc_rho_w * p.oc_cp_w * p.oc_H),
+        oc_speed2_cap=speed2_threshold(p.oc_max_u),
     )
     missing = set(P) - set(vals)
     extra = set(vals) - set(P)
@@ -488,10 +506,15 @@ class Engine:
         cfg = self.step_cfg(dt, has_albedo=has_albedo)
         self._chk(self.lib.qd_atmos_step(self.ctx, C.byref(cfg)), "qd_atmos_step")
 
-    def ocean_step(self, dt, has_q=True, has_ice=True):
+    def ocean_step(self, dt, has_q=True, has_ice=True, winds=None):
+        """One WindDrivenSlabOcean.step; ``winds`` = (u, v) device tensors [B, nlat, nlon] to drive it with instead of the
+        atmosphere's own wind fields."""
         self._dt_guard(dt)
         cfg = self.step_cfg(dt, oc_has_q=has_q, oc_has_ice=has_ice)
-        self._chk(self.lib.qd_ocean_step(self.ctx, C.byref(cfg)), "qd_ocean_step")
+        if winds is None:
+            self._chk(self.lib.qd_ocean_step(self.ctx, C.byref(cfg)), "qd_ocean_step")
+        else:
+            self._chk(self.lib.qd_ocean_step_winds(self.ctx, C.byref(cfg), _ptr(winds[0]), _ptr(winds[1])), "qd_ocean_step_winds")
 
     def loop_steps(self, forcings: Sequence[Forcing], dt, **cfg_kw):
         """Run len(forcings) fused loop steps (run_simulation.py:1760-2344 without plotting/daily ecology)."""

@@ -51,13 +51,17 @@ class WindDrivenSlabOcean:
     def step(self, dt, u_atm, v_atm, Q_net=None, ice_mask=None):
         """ocean.py:265: one ocean step driven by host wind / heat-flux / ice arrays."""
         e = self._engine
-        e.set("u", np.asarray(u_atm, dtype=np.float64))
-        e.set("v", np.asarray(v_atm, dtype=np.float64))
+        # the winds are staged in tensors owned by this object: the atmosphere's u / v on the shared engine stay untouched
+        import torch
+        if getattr(self, "_wind", None) is None:
+            self._wind = torch.empty((2, e.batch, e.nlat, e.nlon), dtype=torch.float64, device=e.device)
+        for k, a in enumerate((u_atm, v_atm)):
+            self._wind[k].copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (e.batch,) + e.shape))))
         if Q_net is not None:
             e.set("qnet", np.asarray(Q_net, dtype=np.float64))
         if ice_mask is not None:
             e.set_mask("ice", np.asarray(ice_mask).astype(np.uint8))
-        e.ocean_step(dt, has_q=Q_net is not None, has_ice=ice_mask is not None)
+        e.ocean_step(dt, has_q=Q_net is not None, has_ice=ice_mask is not None, winds=(self._wind[0], self._wind[1]))
 
     def diagnostics(self):
         """ocean.py:535-561."""

@@ -288,6 +288,17 @@ def load_checkpoint(path, sim):
             raise ValueError("checkpoint was written with a different dt")
         if bool(ds.getncattr("with_routing")) != (sim.routing is not None) or bool(ds.getncattr("with_eco")) != (sim.eco is not None):
             raise ValueError("checkpoint and simulation disagree about routing / ecology")
+        # every check happens BEFORE the first write: a refused checkpoint leaves the simulation untouched
+        land = ds.variables["m_land"][:].data
+        for b in range(e.batch):
+            if not np.array_equal(land[b], e.get_mask("land", b)):
+                raise ValueError("checkpoint land mask differs from the simulation's topography")
+            for static in ("friction", "base_albedo", "elevation"):
+                if not np.array_equal(ds.variables["f_" + static][:].data[b], e.get(static, b)):
+                    raise ValueError(f"checkpoint {static} map differs from the simulation's topography")
+        missing = [n for n in F if "f_" + n not in ds.variables and not n.startswith("x")]
+        if missing:
+            raise ValueError(f"checkpoint lacks the fields {missing}")
         if sim.eco is not None:
             # first the population and its clocks (qd_eco_reset re-snapshots the LAI), then every field on top of it
             pop = sim.eco.pop
@@ -306,6 +317,8 @@ def load_checkpoint(path, sim):
                 rr.lake_volume_kg[:] = ds.variables["routing_lake_volume_kg"][:].data
             rr._diag_cache = None
         for name in sorted(F, key=F.get):
+            if "f_" + name not in ds.variables:
+                continue                                   # a scratch slot added after the checkpoint was written
             data = ds.variables["f_" + name][:].data
             for b in range(e.batch):
                 e.set(name, data[b], b)
@@ -315,10 +328,6 @@ def load_checkpoint(path, sim):
             data = ds.variables["m_" + name][:].data
             for b in range(e.batch):
                 e.set_mask(name, data[b], b)
-        land = ds.variables["m_land"][:].data
-        for b in range(e.batch):
-            if not np.array_equal(land[b], e.get_mask("land", b)):
-                raise ValueError("checkpoint land mask differs from the simulation's topography")
         e.set_counters(int(ds.getncattr("atm_counter")), int(ds.getncattr("oc_counter")), int(ds.getncattr("has_cloud_eff")))
         sim.t = float(ds.variables["clock"][...])
         sim.step_index = int(ds.getncattr("step_index"))

@@ -124,6 +124,10 @@ class Simulation:
             a = np.asarray(a, dtype=np.float64)
             if a.shape != self.engine.shape:
                 raise ValueError(f"restart variable {k!r} has shape {a.shape}, the simulation is {self.engine.shape}")
+            if k == "cloud_cover":
+                a = np.clip(a, 0.0, 1.0)                   # run_simulation.py:1444
+            elif k == "h_ice":
+                a = np.maximum(a, 0.0)                     # run_simulation.py:1446
             self.engine.set(f, a, member)
         if d.get("t_seconds") is not None:
             self.t = float(d["t_seconds"])

@@ -169,3 +169,33 @@ def test_batch_with_mismatched_switches_raises(lib):
 
 def test_long_call_and_parameter_change(lib):
     qdcheck.check_long_call_and_param_change(lib)
+
+
+def test_env_driven_entry_point(lib, tmp_path, golden, monkeypatch):
+    """qingdai_b200.run_simulation.main: QD_N_LAT / QD_N_LON / QD_SIM_DAYS / QD_TOPO_NC / QD_RESTART_OUT -> the same state as
+    driving Simulation directly; QD_RESTART_IN resumes from the file it wrote."""
+    import os
+    from qingdai_b200 import _binding, run_simulation
+    from qingdai_b200.params import QDParams
+    from qingdai_b200.simulation import Simulation, DAY_SECONDS
+    from qingdai_b200.synthetic import load_reference_topography
+    monkeypatch.setattr(_binding, "_default", lib)
+    topo_nc = os.path.join(qdcheck.GOLDEN_DIR, "topography_qingdai_181x360_seed42.nc")
+    nlat, nlon, dt, nsteps = 19, 36, 600, 6
+    r_out = str(tmp_path / "restart.nc")
+    env = {"QD_N_LAT": str(nlat), "QD_N_LON": str(nlon), "QD_DT_SECONDS": str(dt), "QD_SIM_DAYS": repr((nsteps - 0.5) * dt / DAY_SECONDS),
+           "QD_TOPO_NC": topo_nc, "QD_OROG": "1", "QD_ENERGY_W": "1", "QD_LOOP_WITH_ALBEDO": "1", "QD_RESTART_OUT": r_out, "QD_INIT_BANDED": "1"}
+    logs = []
+    sim = run_simulation.main(env, log=logs.append)
+    assert sim.step_index == nsteps and any("<Ts>" in s for s in logs) and os.path.exists(r_out)
+    ref = Simulation(nlat, nlon, load_reference_topography(topo_nc, nlat, nlon), QDParams.from_env(env), dt=dt, lib=lib, loop_with_albedo=True)
+    ts0 = 265.0 + (295.0 - 265.0) * (np.cos(np.deg2rad(ref.grid.lat_mesh)) ** 2)
+    ref.engine.set("ts", ts0)
+    ref.engine.set("sst", np.where(ref.engine.get_mask("land") == 0, ts0, ref.engine.get("sst")))
+    ref.step(nsteps)
+    for k in ("u", "v", "h", "ts", "q", "cloud", "uo", "vo", "eta", "sst", "wland"):
+        assert np.array_equal(sim.engine.get(k), ref.engine.get(k)), k
+    env2 = dict(env, QD_RESTART_IN=r_out, QD_SIM_DAYS=repr(1.5 * dt / DAY_SECONDS))
+    env2.pop("QD_RESTART_OUT"); env2.pop("QD_INIT_BANDED")
+    sim2 = run_simulation.main(env2, log=logs.append)
+    assert sim2.t == (nsteps + 2) * dt and np.all(np.isfinite(sim2.engine.get("ts")))
