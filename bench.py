@@ -196,6 +196,35 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class MultiSim:
+    """The ensemble members of this rank as several batched Simulations on their own CUDA streams
+    (qingdai_b200.ensemble.EnsembleRunner); the few engine calls the bench makes, fanned out / aggregated."""
+
+    def __init__(self, runner):
+        self.r = runner
+        self.sims = runner.sims
+        self.engine = self
+
+    def step(self, n=1):
+        self.r.step(n)
+
+    def sync(self):
+        self.r.synchronize()
+
+    def launches(self):
+        return sum(s.engine.launches() for s in self.sims)
+
+    def graph_status(self):
+        g = [s.engine.graph_status() for s in self.sims]
+        return {"live": sum(x["live"] for x in g), "failed": sum(x["failed"] for x in g), "streams": len(self.sims)}
+
+    def diag(self):
+        return [d for s in self.sims for d in s.engine.diag()]
+
+    def last_nsub(self):
+        return [int(x) for s in self.sims for x in s.engine.last_nsub()]
+
+
 def run_b200(name, args, rank, world, local, short=False, sampler=None):
     """Build the workload, time it, return the JSON record (rank 0) or None."""
     import torch
@@ -203,6 +232,9 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
     from qingdai_b200.simulation import Simulation
 
     spec = workload(name)
+    if spec["members_total"] and args.members:
+        spec["members_total"] = args.members
+        spec["label"] = spec["label"].replace("64-member", f"{args.members}-member")
     nlat, nlon, dt = spec["nlat"], spec["nlon"], spec["dt"]
     ncell = nlat * nlon
     dev = f"cuda:{local}"
@@ -241,6 +273,12 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
         return float(t.item())
 
     def make_sim(b):
+        if spec["members_total"]:
+            from qingdai_b200.ensemble import EnsembleRunner
+            by_id = dict(zip(ids, ins))
+            return MultiSim(EnsembleRunner(nlat, nlon, spec["members_total"], lambda m: by_id[m][0], lambda m: by_id[m][1], dt=dt, rank=rank,
+                                           world=world, device=dev, streams=args.streams or None, with_ocean=True, with_hydrology=True,
+                                           loop_with_albedo=spec["with_albedo"]))
         return Simulation(nlat, nlon, topos, plist, dt=dt, batch=members, with_ocean=True, with_hydrology=True,
                           loop_with_albedo=spec["with_albedo"], device=dev, band=b, **extra)
 
@@ -283,21 +321,33 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
     if sampler:
         sampler.mark("t0")
     barrier()
+    multi = isinstance(sim, MultiSim) and len(sim.sims) > 1
+    cur = torch.cuda.current_stream()
+
+    def fork():          # the member groups' streams start after everything enqueued on the timing stream ...
+        if multi:
+            for st in sim.r._streams:
+                st.wait_stream(cur)
+
+    def join():          # ... and the closing event waits for all of them
+        if multi:
+            for st in sim.r._streams:
+                cur.wait_stream(st)
     if flush_on:
         evs = []
         for _ in range(steps):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); sim.step(1); e1.record()
+            e0.record(); fork(); sim.step(1); join(); e1.record()
             evs.append((e0, e1))
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     else:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(); fork()
         for _ in range(steps):
             sim.step(1)
-        e1.record()
+        join(); e1.record()
         barrier()
         dev_ms = e0.elapsed_time(e1)
     launches = eng.launches() - l0
@@ -325,6 +375,7 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
         sampler.mark("t1")
     e2e_val = total_members * (steps / e2e_s) * dt / DAY
     nsub = [int(x) for x in eng.last_nsub()]
+    prof_eng = sim.sims[0].engine if isinstance(sim, MultiSim) else eng          # per-kernel times: the first member group
     # -------- the reference's object-level operator interface with HOST arrays every step (rank 0, one member):
     # SpectralModel.time_step(Teq, dt, albedo) + WindDrivenSlabOcean.step(dt, u, v, Q_net, ice_mask) + reads of T_s
     dropin = None
@@ -361,13 +412,14 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
     buf = None
     if not args.no_profile and (rank == 0 or band):       # band mode: every rank must run the same (stream-mode) steps
         import ctypes
-        eng.lib.qd_profile(eng.ctx, 1)
+        prof_eng.lib.qd_profile(prof_eng.ctx, 1)
         nprof = min(steps, 20)
+        psim = sim.sims[0] if isinstance(sim, MultiSim) else sim
         for _ in range(nprof):
-            sim.step(1)
+            psim.step(1)
         buf = ctypes.create_string_buffer(1 << 16)
-        eng.lib.qd_profile_report(eng.ctx, buf, len(buf))
-        eng.lib.qd_profile(eng.ctx, 0)
+        prof_eng.lib.qd_profile_report(prof_eng.ctx, buf, len(buf))
+        prof_eng.lib.qd_profile(prof_eng.ctx, 0)
     if rank == 0 and buf is not None:
         rows = [ln.split() for ln in buf.value.decode().strip().splitlines()]
         rows = [(r[0], int(r[1]), float(r[2])) for r in rows if len(r) == 3]
@@ -375,7 +427,8 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
         peak, peak_src = load_peaks()
         kname, cnt, ms = rows[0]
         per_launch_s = ms / cnt * 1e-3
-        alg = alg_bytes_per_cell(kname) * ncell * members
+        pmembers = prof_eng.batch if isinstance(sim, MultiSim) else members
+        alg = alg_bytes_per_cell(kname) * ncell * pmembers
         achieved = alg / per_launch_s / 1e9
         traffic = None
         try:
@@ -390,7 +443,7 @@ def run_b200(name, args, rank, world, local, short=False, sampler=None):
                 "whole_step": {"alg_bytes_per_step": step_alg, "achieved": step_alg / (ms_per_step * 1e-3) / 1e9,
                                "frac": step_alg / (ms_per_step * 1e-3) / 1e9 / peak, "note": "233 B/cell-step (SURVEY 8d) over the whole fused step (graph mode, the timed region)"},
                 "top_kernels": [{"kernel": r[0], "launches_per_step": r[1] / nprof, "us_per_launch": r[2] / r[1] * 1e3, "share": r[2] / tot,
-                                 "frac": alg_bytes_per_cell(r[0]) * ncell * members / (r[2] / r[1] * 1e-3) / 1e9 / peak}
+                                 "frac": alg_bytes_per_cell(r[0]) * ncell * pmembers / (r[2] / r[1] * 1e-3) / 1e9 / peak}
                                 for r in rows[:(40 if (band or args.all_kernels) else 10)]]}
 
     # -------- CPU baseline (oracle port, rank 0, N=1 only)
@@ -455,6 +508,8 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="skip the short sub-records of the other workloads")
     ap.add_argument("--all-kernels", action="store_true", help="list every kernel in roofline.top_kernels")
     ap.add_argument("--halo", type=int, default=16, help="latitude bands: halo rows per exchange")
+    ap.add_argument("--streams", type=int, default=0, help="ensemble workloads: member groups (CUDA streams) per GPU, 0 = automatic")
+    ap.add_argument("--members", type=int, default=0, help="ensemble workloads: total members instead of 64 (tuning runs)")
     ap.add_argument("--replicas", action="store_true", help="hires at N>1: independent replicas instead of latitude bands")
     ap.add_argument("--no-all-cores", action="store_true", help="reference arm: skip the all-cores (independent copies) figure")
     args = ap.parse_args()

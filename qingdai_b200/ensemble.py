@@ -19,28 +19,61 @@ def member_slice(n_members: int, world: int, rank: int) -> range:
 
 
 class EnsembleRunner:
-    """Runs the members of one rank as a single batched Simulation (leading dimension of every kernel)."""
+    """Runs the members of one rank as batched Simulations (leading dimension of every kernel).
+
+    ``streams`` > 1 splits the rank's members into that many groups, each with its own context, CUDA stream and step
+    graph: members are independent, so the groups' graphs run concurrently and the dependency bubbles of one group's
+    step (a chain of ~60 short kernels at 181x360, three grid-wide syncs per exact median) are filled by the others.
+    MEASURED on B200 (profiles/README.md, round 2): it does not pay -- 8 members: 0.51 ms/step on one stream, 0.58 / 0.73 /
+    0.83 on 2 / 4 / 8; 16 members: 0.78 vs 0.84 / 0.99; 64 members: 2.59 vs 2.54.  The cooperative median launches of
+    the groups serialise and the fork / join adds more than the bubbles give back.  Default: one stream."""
 
     def __init__(self, nlat, nlon, n_members, topo_for: Callable[[int], dict], params_for: Callable[[int], QDParams],
-                 dt=300, rank=0, world=1, device=None, lib=None, **sim_kw):
+                 dt=300, rank=0, world=1, device=None, lib=None, streams=None, **sim_kw):
         self.rank, self.world = int(rank), int(world)
         self.members = list(member_slice(n_members, world, rank))
         self.n_members = int(n_members)
+        self.sims, self.groups, self._streams = [], [], []
         if not self.members:
             self.sim = None
             return
-        topos = [topo_for(m) for m in self.members]
-        params = [params_for(m) for m in self.members]
-        self.sim = Simulation(nlat, nlon, topos, params, dt=dt, batch=len(self.members), device=device, lib=lib, **sim_kw)
+        m = len(self.members)
+        if streams is None:
+            streams = 1
+        k = max(1, min(int(streams), m))
+        host_only = lib is not None and getattr(lib, "host_emulation", False)
+        for g in range(k):
+            grp = self.members[g * m // k:(g + 1) * m // k]
+            if not grp:
+                continue
+            topos = [topo_for(i) for i in grp]
+            params = [params_for(i) for i in grp]
+            if k > 1 and not host_only:
+                import torch
+                st = torch.cuda.Stream(device=device)
+                with torch.cuda.stream(st):              # the engine binds the stream that is current at construction
+                    sim = Simulation(nlat, nlon, topos, params, dt=dt, batch=len(grp), device=device, lib=lib, **sim_kw)
+                self._streams.append(st)
+            else:
+                sim = Simulation(nlat, nlon, topos, params, dt=dt, batch=len(grp), device=device, lib=lib, **sim_kw)
+            self.sims.append(sim)
+            self.groups.append(grp)
+        self.sim = self.sims[0]
 
     def step(self, nsteps=1):
-        if self.sim is not None:
-            self.sim.step(nsteps)
+        for sim in self.sims:
+            sim.step(nsteps)
+
+    def synchronize(self):
+        for sim in self.sims:
+            sim.engine.sync()
 
     def local_diagnostics(self) -> Dict[int, dict]:
-        if self.sim is None:
-            return {}
-        return {m: self.sim.diagnostics(member=b) for b, m in enumerate(self.members)}
+        out = {}
+        for sim, grp in zip(self.sims, self.groups):
+            for b, m in enumerate(grp):
+                out[m] = sim.diagnostics(member=b)
+        return out
 
     def gather_diagnostics(self) -> Optional[List[dict]]:
         """All members' diagnostics on rank 0 (None elsewhere); the only communication of an ensemble run."""
