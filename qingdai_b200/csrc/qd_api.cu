@@ -155,21 +155,23 @@ static int qd_fail(qd_ctx* c, int code, const char* what, cudaError_t e) {
 
 // Blocks per member of a grid-stride reduction kernel: exactly ONE resident wave of that kernel (a partial second
 // wave ran k_ocean_continuity at 55 % occupancy and doubled its time, profiles/r01_ncu_full_hires_step_v2.csv).
-static int qd_red_blocks(qd_ctx* c, const void* kern) {
+// one resident wave of `kern` (256-thread blocks) on this device
+static int qd_wave_blocks(qd_ctx* c, const void* kern) {
 #ifdef QD_HOST_EMU
   (void)kern;
-  return c->red_blk;
+  return c->red_blk * c->batch;
 #else
   auto it = c->red_cache.find(kern);
   if (it != c->red_cache.end()) return it->second;
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, QD_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-  const int n = std::max(1, (per_sm * std::max(1, sms)) / c->batch);
+  const int n = std::max(1, per_sm * std::max(1, sms));
   c->red_cache[kern] = n;
   return n;
 #endif
 }
+static int qd_red_blocks(qd_ctx* c, const void* kern) { return std::max(1, qd_wave_blocks(c, kern) / c->batch); }
 
 // Every launch goes through QD_KG so that launches are counted and, in profiling mode, bracketed by
 // CUDA events on the launching stream (per-kernel device time for bench.py's roofline object).
@@ -186,7 +188,19 @@ static int qd_red_blocks(qd_ctx* c, const void* kern) {
 #ifdef QD_HOST_EMU
 #define QD_KR(c, kern, ...) QD_KG(c, kern, dim3((c)->geo.nvb, (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
 #else
-#define QD_KR(c, kern, ...) QD_KG(c, kern, dim3(std::min(std::min(qd_red_blocks((c), (const void*)kern), (c)->cur_nblk), (c)->geo.nvb), (c)->batch), dim3(QD_THREADS), __VA_ARGS__)
+// Virtual blocks of a sum-reduction kernel: ONE resident wave of that kernel for a single member -- a property of the
+// kernel and the device, not of how many members share the GPU (B = 8 gives the bits of B = 1).  With B members the
+// physical grid per member is wave / B blocks and every block takes B virtual blocks (rounded so that the blocks differ by
+// at most one virtual block).
+static inline int qd_nvb_for(qd_ctx* c, const void* kern) { return std::max(1, std::min(c->nblk, qd_wave_blocks(c, kern))); }
+static inline int qd_kr_grid(qd_ctx* c, const void* kern) {
+  const int cap = std::max(1, std::min(qd_red_blocks(c, kern), c->cur_nblk)), nvb = c->geo.nvb;
+  if (cap >= nvb) return nvb;
+  const int k = (nvb + cap - 1) / cap;
+  return (nvb + k - 1) / k;
+}
+#define QD_KR(c, kern, ...) do { (c)->geo.nvb = qd_nvb_for((c), (const void*)kern); \
+    QD_KG(c, kern, dim3(qd_kr_grid((c), (const void*)kern), (c)->batch), dim3(QD_THREADS), __VA_ARGS__); } while (0)
 #endif
 
 struct BIn;
@@ -1556,7 +1570,8 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
   const int nstrips = (c->nlon + QD_OF_COLS - 1) / QD_OF_COLS;
   const int nwarps = nstrips * ((jb - ja + R - 1) / R);
   const int nblocks = (nwarps + QD_OF_WARPS - 1) / QD_OF_WARPS;
-  const int npart = c->geo.nvb + nblocks * QD_OF_WARPS;
+  const int pole_nvb = std::max(1, std::min(c->nblk, QD_NVB_MAX));
+  const int npart = pole_nvb + nblocks * QD_OF_WARPS;
   if (npart > c->oc_npart) return qd_fail(c, QD_E_STATE, "fused ocean sub-step: partial-sum table too small", cudaSuccess);   // sized in qd_create (no allocation inside a captured step)
   double* uo2[2] = {F(c, QD_F_UO), F(c, QD_F_X9)};
   double* vo2[2] = {F(c, QD_F_VO), F(c, QD_F_X10)};
@@ -1591,7 +1606,8 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
     Cp.ub = F(c, QD_F_X4); Cp.vb = F(c, QD_F_X5); Cp.eta_in = F(c, QD_F_X6); Cp.sst = F(c, QD_F_SST);
     Cp.uo[0] = uo2[0]; Cp.uo[1] = uo2[1]; Cp.vo[0] = vo2[0]; Cp.vo[1] = vo2[1];
     Cp.eta_out = F(c, QD_F_X7); Cp.tb = F(c, QD_F_X8); Cp.part = c->d_oc_part; Cp.npart = npart; Cp.land = M(c, QD_M_LAND);
-    const QdGeo gp = geo_rows(c, 0, 8, jb, nlat, &nb);
+    QdGeo gp = geo_rows(c, 0, 8, jb, nlat, &nb);
+    gp.nvb = pole_nvb;
     QD_KG(c, k_ocean_cont_pole, dim3(std::min(nb, gp.nvb), c->batch), dim3(QD_THREADS), gp, Cp, sc);
   }
   // ---- rows [8, jb): the streaming kernel; its last block totals the eta sum (pole partials included)
@@ -1601,7 +1617,7 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
     A.eta = F(c, QD_F_ETA); A.taux = F(c, QD_F_X0); A.tauy = F(c, QD_F_X1); A.sst = F(c, QD_F_SST);
     A.eta_out = F(c, QD_F_X7); A.tb = F(c, QD_F_X8); A.land = M(c, QD_M_LAND);
     A.k4tab = c->d_oc_k4;
-    A.part = c->d_oc_part; A.part_off = c->geo.nvb; A.npart = npart; A.ticket = c->d_ticket + 5 * c->batch;
+    A.part = c->d_oc_part; A.part_off = pole_nvb; A.npart = npart; A.ticket = c->d_ticket + 5 * c->batch;
     A.ja = ja; A.jb = jb;
     A.R = R;
     QD_KG(c, k_ocean_fused, dim3(nblocks, c->batch), dim3(32 * QD_OF_WARPS), c->geo, A, sc);
@@ -1674,14 +1690,16 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
   Co.sst = F(c, QD_F_SST); Co.tb = F(c, QD_F_X7);
   Co.ticket = c->d_ticket + 5 * c->batch;
+  Co.band = c->band; if (!c->band_on) Co.band.world = 1;
   BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}, {Co.sst, 2}), BL(Co.eta, Co.tb));
   QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
-  { int rcb = band_allreduce(c, {QD_S_ETA_NUM}, false); if (rcb) return rcb; }
+  // latitude bands: no all-reduce kernel here -- the partial was published by the last block, k_ocean_sst_finish pulls the world's
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
   Sb.tb = F(c, QD_F_X7); Sb.ub = ub; Sb.vb = vb; Sb.qnet = F(c, QD_F_QNET);
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS); Sb.eta = F(c, QD_F_ETA);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
+  Sb.band = c->band; if (!c->band_on) Sb.band.world = 1;
   BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}, {Sb.eta, 0}),
      BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm, Sb.eta));
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
@@ -1880,8 +1898,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   Pa.pos = F(c, QD_F_X0); Pa.orog_raw = F(c, QD_F_X1); Pa.part = c->d_part[0]; Pa.ticket = c->d_ticket + 6 * c->batch;
   Pa.forcing = c->d_forcing; Pa.step_idx = c->d_step_idx; Pa.hcos = c->d_hcos;      // this step's hour-angle cosines ride along
   BP(c, BL({Pa.u, 1}, {Pa.v, 1}, {Pa.pcond, 0}, {Pa.nx, 0}, {Pa.ny, 0}), BL(Pa.pos, Pa.orog_raw));
-  QD_KR(c, k_precip_a, c->geo, Pa);
-  if ((rc = band_allreduce(c, {QD_S_SUM_PQW}, false))) return rc;
+  QD_KR(c, k_precip_a, c->geo, Pa);          // latitude bands: sum(Pq w) is all-reduced together with sum(P_raw w) below (both are first read by the precipitation Gaussian)
   double* orog_f = F(c, QD_F_X1);
   if (orog) {
     double* fl[1] = {F(c, QD_F_X1)}; double* sx[1] = {F(c, QD_F_X5)}; bool moved = false;
@@ -1894,7 +1911,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
   Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
   BP(c, BL({Pb.pos, 0}, {Pb.pcond, 0}, {Pb.orog, 0}), BL(Pb.praw));
   QD_KR(c, k_precip_b, c->geo, Pb);
-  if ((rc = band_allreduce(c, {QD_S_SUM_PRAWW}, false))) return rc;
+  if ((rc = band_allreduce(c, {QD_S_SUM_PQW, QD_S_SUM_PRAWW}, false))) return rc;
   bool fused = false;
 #ifndef QD_HOST_EMU
   fused = gauss2d_ok(c, w1);

@@ -35,7 +35,8 @@
 
 // flag words inside a rank's buffer (unsigned long long each)
 enum { QD_BF_HALO_S = 0, QD_BF_HALO_N = 1, QD_BF_RED = 8, QD_BF_SEL = 16, QD_BF_ERR = 24, QD_BF_EPOCH_HALO = 32,
-       QD_BF_EPOCH_RED = 33, QD_BF_EPOCH_SEL = 34, QD_BF_TICKET = 40, QD_BF_WORDS = 64 };
+       QD_BF_EPOCH_RED = 33, QD_BF_EPOCH_SEL = 34, QD_BF_EPOCH_PUB = 35, QD_BF_PUB_FLAG = 36, QD_BF_TICKET = 40,
+       QD_BF_PUB_VAL = 48 /* two doubles, by epoch parity */, QD_BF_WORDS = 64 };
 
 struct QdBandCtl {
   int rank, world, H, nlon, nlat;
@@ -186,6 +187,42 @@ __global__ void k_band_allreduce(QdBandCtl B, QdBandRed R, double* scal) {
     scal[R.id[t]] = acc;
   }
 #endif
+}
+
+// ---- one scalar, published and pulled: the producer kernel's last block stores its partial into its OWN buffer and
+// raises a flag; every block of the consumer kernel reads the world's partials over NVLink (peers map the buffer) and
+// adds them in rank order.  No separate all-reduce kernel between producer and consumer (the ocean's eta sum: once per
+// CFL sub-step).  Values are double-buffered by epoch parity: a rank can publish epoch e+2 only after every peer has
+// consumed epoch e (it had to read their e+1 first).
+QD_D void qd_band_publish(const QdBandCtl& B, double v) {
+  unsigned long long* mine = qd_bflags(B, B.rank);
+  const unsigned long long epoch = mine[QD_BF_EPOCH_PUB] + 1ull;
+  ((double*)(mine + QD_BF_PUB_VAL))[epoch & 1ull] = v;
+  qd_fence_sys();
+  mine[QD_BF_EPOCH_PUB] = epoch;
+  qd_st_sys(mine + QD_BF_PUB_FLAG, epoch);
+}
+// called by ONE thread of a block; the rank's own epoch word already counts the publish that precedes this kernel
+QD_D double qd_band_pull_sum(const QdBandCtl& B) {
+#if QD_EMU
+  const unsigned long long epoch = *(volatile unsigned long long*)(qd_bflags(B, B.rank) + QD_BF_EPOCH_PUB);
+#else
+  const unsigned long long epoch = __ldcg(qd_bflags(B, B.rank) + QD_BF_EPOCH_PUB);
+#endif
+  double acc = 0.0;
+  for (int r = 0; r < B.world; ++r) {
+    unsigned long long* fl = qd_bflags(B, r);
+    qd_band_wait(B, fl + QD_BF_PUB_FLAG, epoch);
+#if QD_EMU
+    __sync_synchronize();
+    const double v = ((volatile double*)(fl + QD_BF_PUB_VAL))[epoch & 1ull];
+#else
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"((double*)(fl + QD_BF_PUB_VAL) + (epoch & 1ull)) : "memory");
+#endif
+    acc = r == 0 ? v : acc + v;
+  }
+  return acc;
 }
 
 // ---------------------------------------------------------------------------------------------- selection
