@@ -260,7 +260,7 @@ int  qd_graph_status(qd_ctx* ctx, int* live, int* failed);
 int  qd_set_counters(qd_ctx* ctx, int atm_counter, int ocean_counter, int has_cloud_eff);
 int  qd_get_counters(qd_ctx* ctx, int* atm_counter, int* ocean_counter, int* has_cloud_eff);
 int  qd_minmax(qd_ctx* ctx, const double* in_dev, double* out_host /* [B][2] */);   /* sync */
-int  qd_set_gauss2d(qd_ctx* ctx, int enable);                 /* 0: force the two-pass Gaussian kernels (tests); default 1 */
+int  qd_set_gauss2d(qd_ctx* ctx, int mode);                   /* 0: two one-axis passes; 1 (default): fused tiles, TMA box loads; 2: generic tile kernel; 3: no TMA (A/B runs) */
 int  qd_set_h4_stream(qd_ctx* ctx, int enable);               /* 0: force the tile kernel for del^4 (tests); default 1 */
 /* 1: the ocean's CFL sub-steps (ocean.py:305-444) run as two kernels -- a warp-streaming kernel that fuses momentum,
  * del^4 of (uo, vo, eta), continuity, the SST gather and the current hygiene, plus a closing kernel -- instead of four.

@@ -91,6 +91,9 @@ struct qd_ctx {
   // latitude bands (qd_band.cuh): control block, exchange buffer, per-field valid halo width
   QdBandCtl band; int band_on; size_t band_bytes; char* band_base; void* band_peer_map[QD_BAND_MAXW];
   int band_valid[QD_F_COUNT + QD_M_COUNT]; char band_shm[64]; int band_maxext;
+#ifndef QD_HOST_EMU
+  CUtensorMap tmaps[QD_F_COUNT]; int tma_ok = 0;           // one 2-D tensor map per field slot ([B * n_lat][n_lon] doubles, box 64 x 24): k_gauss2d_r4
+#endif
   double* d_oc_k4 = nullptr;                               // [B][3][nlat] k4 rows of the fused ocean sub-step for the current sub_dt
   double* d_oc_part = nullptr; int oc_npart = 0;           // eta partial sums of the fused ocean sub-step (pole pass + one per warp)
   QdIndivArgs indiv; int indiv_ready;                     // individual pool (qd_indiv.cuh); device arrays owned here
@@ -437,12 +440,39 @@ extern "C" int qd_destroy(qd_ctx* c) {
   return QD_OK;
 }
 
+#ifndef QD_HOST_EMU
+// Tensor maps for the TMA box loads of k_gauss2d_r4: field slot f as a 2-D tensor [B * n_lat][n_lon] of doubles, box
+// QD_G3_CW x QD_G3_RH.  cuTensorMapEncodeTiled is fetched through the runtime (no link against libcuda); without it, or
+// when a row is not a multiple of 16 bytes (odd n_lon), the kernels stage their tiles with ordinary loads.
+static void qd_build_tmaps(qd_ctx* c) {
+  c->tma_ok = 0;
+  if ((c->nlon & 1) || c->nlon < QD_G3_CW || c->nlat < QD_G3_RH) return;
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return; }
+  const cuuint64_t dims[2] = {(cuuint64_t)c->nlon, (cuuint64_t)c->nlat * (cuuint64_t)c->batch};
+  const cuuint64_t strides[1] = {(cuuint64_t)c->nlon * 8};
+  const cuuint32_t box[2] = {QD_G3_CW, QD_G3_RH}, estr[2] = {1, 1};
+  for (int f = 0; f < QD_F_COUNT; ++f) {
+    void* base = (void*)(c->fields + (size_t)f * c->batch * c->ncell);
+    if (((size_t)base & 15) != 0) return;
+    if (((encode_fn)fn)(&c->tmaps[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return;
+  }
+  c->tma_ok = 1;
+}
+#endif
 extern "C" int qd_set_stream(qd_ctx* c, void* s) { if (!c) return QD_E_INVALID; c->stream = (cudaStream_t)s; return QD_OK; }
 extern "C" int qd_synchronize(qd_ctx* c) { if (!c) return QD_E_INVALID; QD_CUDA(c, cudaStreamSynchronize(c->stream)); return QD_OK; }
 extern "C" int qd_bind(qd_ctx* c, double* fields, uint8_t* masks) {
   if (!c || !fields || !masks) return QD_E_INVALID;
   qd_drop_graphs(c);
   c->fields = fields; c->masks = masks;
+#ifndef QD_HOST_EMU
+  qd_build_tmaps(c);
+#endif
   return QD_OK;
 }
 extern "C" int qd_set_params(qd_ctx* c, const double* p) {
@@ -498,7 +528,9 @@ extern "C" int qd_user_row_member(qd_ctx* c, int slot, int member, const double*
 }
 // test / tuning switch: 0 forces the shared-memory tile kernel for del^4 at every size (default 1: large grids stream)
 // test / tuning switch: 0 forces the two-pass Gaussian kernels at every size (default 1: large grids use the fused tile kernel)
-extern "C" int qd_set_gauss2d(qd_ctx* c, int enable) { if (!c) return QD_E_INVALID; qd_drop_graphs(c); c->g2_fused = enable ? 1 : 0; return QD_OK; }
+// 0: two one-axis passes; 1 (default): fused tiles, radius 4 on large grids through k_gauss2d_r4 with TMA box loads; 2: the
+// generic fused tile kernel everywhere; 3: k_gauss2d_r4 without TMA (per-element staging) -- 2 and 3 exist for A/B runs
+extern "C" int qd_set_gauss2d(qd_ctx* c, int mode) { if (!c || mode < 0 || mode > 3) return QD_E_INVALID; qd_drop_graphs(c); c->g2_fused = mode; return QD_OK; }
 // 1: CFL sub-steps of the ocean run as k_ocean_fused + k_ocean_close (qd_ocean_fused.cuh) where the grid allows it; default 0
 extern "C" int qd_set_ocean_fused(qd_ctx* c, int enable) {
   if (!c) return QD_E_INVALID;
@@ -937,10 +969,29 @@ static int launch_gauss2d_t(qd_ctx* c, QdG2Args A, const QdGaussW& w, const char
   }
   return QD_OK;
 }
+// sigma = 1 on large grids: k_gauss2d_r4 (sliding windows; TMA box loads when the tensor maps exist)
+template <int MODE>
+static int launch_gauss2d_r4(qd_ctx* c, QdG2Args A, const QdGaussW& w, const char* name) {
+  const int tiles_i = (c->nlon + QD_G3_TI - 1) / QD_G3_TI;
+  const int f0 = band_fid(c, A.src[0]), f1 = A.n > 1 ? band_fid(c, A.src[1]) : f0;
+  const bool tma = c->g2_fused == 1 && c->tma_ok && f0 >= 0 && f0 < QD_F_COUNT && f1 >= 0 && f1 < QD_F_COUNT;
+  const CUtensorMap& t0 = c->tmaps[tma ? f0 : 0];
+  const CUtensorMap& t1 = c->tmaps[tma ? f1 : 0];
+  const int seg[2][2] = {{c->geo.sa0, c->geo.sa1}, {c->geo.sb0, c->geo.sb1}};
+  for (int q = 0; q < 2; ++q) {
+    if (seg[q][1] <= seg[q][0]) continue;
+    A.row0 = seg[q][0]; A.row1 = seg[q][1];
+    const dim3 grid(tiles_i * ((A.row1 - A.row0 + QD_G3_TJ - 1) / QD_G3_TJ), c->batch), block(256);
+    if (tma) QD_KGN(c, name, (k_gauss2d_r4<MODE, true>), grid, block, c->geo, A, w, t0, t1);
+    else QD_KGN(c, name, (k_gauss2d_r4<MODE, false>), grid, block, c->geo, A, w, t0, t1);
+  }
+  return QD_OK;
+}
 template <int MODE>
 static int launch_gauss2d(qd_ctx* c, QdG2Args A, const QdGaussW& w, const std::vector<BIn>& ins, const std::vector<const void*>& outs, const char* name) {
   BPV(c, ins, outs);
   if (gauss2d_small(c)) return launch_gauss2d_t<MODE, QD_G2S_TJ, QD_G2S_TI>(c, A, w, name);
+  if (w.r == 4 && c->g2_fused != 2 && c->nlon >= QD_G3_CW) return launch_gauss2d_r4<MODE>(c, A, w, name);
   return launch_gauss2d_t<MODE, QD_G2_TJ, QD_G2_TI>(c, A, w, name);
 }
 // Fused two-axis Gaussian or the two one-axis passes?  Default: fused wherever at least 148 tiles (of either size) exist.
@@ -1693,13 +1744,12 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Co.band = c->band; if (!c->band_on) Co.band.world = 1;
   BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}, {Co.sst, 2}), BL(Co.eta, Co.tb));
   QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
-  // latitude bands: no all-reduce kernel here -- the partial was published by the last block, k_ocean_sst_finish pulls the world's
+  // latitude bands: no all-reduce kernel here -- the last block of k_ocean_continuity publishes the rank's partial and pulls the world's
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
   Sb.tb = F(c, QD_F_X7); Sb.ub = ub; Sb.vb = vb; Sb.qnet = F(c, QD_F_QNET);
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS); Sb.eta = F(c, QD_F_ETA);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
-  Sb.band = c->band; if (!c->band_on) Sb.band.world = 1;
   BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}, {Sb.eta, 0}),
      BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm, Sb.eta));
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);

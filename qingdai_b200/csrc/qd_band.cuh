@@ -189,10 +189,9 @@ __global__ void k_band_allreduce(QdBandCtl B, QdBandRed R, double* scal) {
 #endif
 }
 
-// ---- one scalar, published and pulled: the producer kernel's last block stores its partial into its OWN buffer and
-// raises a flag; every block of the consumer kernel reads the world's partials over NVLink (peers map the buffer) and
-// adds them in rank order.  No separate all-reduce kernel between producer and consumer (the ocean's eta sum: once per
-// CFL sub-step).  Values are double-buffered by epoch parity: a rank can publish epoch e+2 only after every peer has
+// ---- one scalar, published and pulled: the producer kernel's last block stores its partial into its OWN buffer, raises
+// a flag, then reads the world's partials over NVLink (peers map the buffer) and adds them in rank order.  No separate
+// all-reduce kernel between producer and consumer (the ocean's eta sum: once per CFL sub-step).  Values are double-buffered by epoch parity: a rank can publish epoch e+2 only after every peer has
 // consumed epoch e (it had to read their e+1 first).
 QD_D void qd_band_publish(const QdBandCtl& B, double v) {
   unsigned long long* mine = qd_bflags(B, B.rank);

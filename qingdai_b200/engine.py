@@ -254,6 +254,9 @@ class Engine:
         self._chk(self.lib.qd_set_gauss(self.ctx, 0, r1, 0, _ptr(w1)), "qd_set_gauss")
         self._cloud_sigma = None
         self._upload_cloud_gauss()
+        import os
+        if os.environ.get("QD_B200_GAUSS2D"):                 # tuning / A-B runs: variant of the fused Gaussian (qd_set_gauss2d)
+            self._chk(self.lib.qd_set_gauss2d(self.ctx, int(os.environ["QD_B200_GAUSS2D"])), "qd_set_gauss2d")
         self._finalizer = weakref.finalize(self, self.lib.qd_destroy, self.ctx)
 
     # ---------------------------------------------------------------- latitude bands (SURVEY 8e, configs[4])
