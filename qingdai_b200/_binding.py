@@ -144,7 +144,7 @@ class Library:
     test scaffolding under tests/hostcheck (device pointers are then host pointers)."""
 
     def __init__(self, path=None, host_emulation=False):
-        path = path or DEFAULT_LIB
+        path = path or os.environ.get("QD_B200_LIB") or DEFAULT_LIB          # QD_B200_LIB: a tuning variant built by build.py --out
         if not os.path.exists(path):
             raise RuntimeError(
                 f"libqd_b200 not found at {path}: build it with `python -m qingdai_b200.build` "

@@ -27,17 +27,20 @@ def _stale():
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force=False, verbose=False):
-    if not (force or _stale()):
+def build(force=False, verbose=False, out=None, defines=()):
+    """out / defines: tuning variants (`--out _lib/x.so -DQD_FOO=1`, loaded with QD_B200_LIB=...); the product is OUT."""
+    if out is None and not (force or _stale()):
         return OUT
+    out = out or OUT
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libqd_b200 cannot be built (and there is no CPU fallback)")
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "qd_api.cu"), "-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + list(defines) + [os.path.join(CSRC, "qd_api.cu"), "-o", out]
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=_out, defines=[a for a in sys.argv if a.startswith("-D")]))

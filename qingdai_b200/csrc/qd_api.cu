@@ -1743,6 +1743,11 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Co.ticket = c->d_ticket + 5 * c->batch;
   Co.band = c->band; if (!c->band_on) Co.band.world = 1;
   BP(c, BL({Co.ub, 1}, {Co.vb, 1}, {Co.eta_in, 0}, {Co.land, 0}, {Co.sst, 2}), BL(Co.eta, Co.tb));
+#ifndef QD_HOST_EMU
+  const bool pairs = (c->nlon & 1) == 0 && !getenv("QD_NO_PAIRS");       // two cells per thread (qd_ocean.cuh)
+  if (pairs) QD_KR(c, k_ocean_continuity2, c->geo, Co, sc);
+  else
+#endif
   QD_KR(c, k_ocean_continuity, c->geo, Co, sc);
   // latitude bands: no all-reduce kernel here -- the last block of k_ocean_continuity publishes the rank's partial and pulls the world's
   QdOcSstBArgs Sb; memset(&Sb, 0, sizeof(Sb));
@@ -1752,6 +1757,12 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
   BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}, {Sb.eta, 0}),
      BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm, Sb.eta));
+#ifndef QD_HOST_EMU
+  if (pairs) {                                                 // two cells per thread, lazy nan_to_num (qd_ocean.cuh)
+    QD_KG(c, k_ocean_sst_finish2, dim3((c->geo.ncomp / 2 + QD_THREADS - 1) / QD_THREADS, c->batch), dim3(QD_THREADS), c->geo, Sb, sc);
+    return QD_OK;
+  }
+#endif
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
   return QD_OK;
 }

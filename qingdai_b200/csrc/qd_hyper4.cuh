@@ -235,20 +235,22 @@ __global__ void __launch_bounds__(QD_H4_NX * QD_H4_NY) k_hyper4_tile(QdGeo g, Qd
 #define QD_H4S_WARPS 4
 // `cr` tables carry, behind the cosine row and its 1/c, 1/c^2 rows, the three centred-stencil coefficient
 // rows ap, am, bl of the tile kernel (filled on the host by qd_cos_companions with the same expressions).
-template <int R>
-__global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
-  static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
-  const int b = blockIdx.y;
-  if (A.ocean && qd_sub_done(g, b, A.sc)) return;
-  const int lane = threadIdx.x & 31;
+// np.nan_to_num is applied LAZILY (the pattern of qd_ocean_fused.cuh): the reference cleans the field, lap(F) and the
+// result; on finite data each of those is the identity.  The FAST instantiation (CLEAN = false) only records whether
+// any value the reference would have cleaned was non-finite (one DSETP per value instead of the ~8-instruction select
+// chain, which was 30 % of this kernel's issue slots: profiles/README.md); a warp that saw one re-runs its chunk with
+// CLEAN = true.  The kernel is out of place, so the re-run reads unmodified inputs and rewrites the outputs:
+// identical bits either way.
+template <bool CLEAN>
+__device__ __forceinline__ double qd_h4s_cl(double x, bool& bad) {
+  if (CLEAN) return qd_clean_sel(x);
+  bad = bad || !(fabs(x) <= DBL_MAX);
+  return x;
+}
+template <int R, bool CLEAN>
+__device__ __forceinline__ bool qd_h4s_chunk(const QdGeo& g, const QdHyper4Args& A, const int b, const int k, const int lane,
+                                             const int strip, const int j0, const int j1) {
   const int nlat = g.nlat, nlon = g.nlon;
-  const int nstrips = (nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
-  const int w = blockIdx.x * QD_H4S_WARPS + (threadIdx.x >> 5);
-  const int chunk = w / nstrips, strip = w - chunk * nstrips;
-  const int j0 = A.ja + chunk * R;
-  if (j0 >= A.jb) return;
-  const int j1 = min(j0 + R, A.jb);
-  const int k = blockIdx.z;
   const size_t off = (size_t)b * g.ncell;
   const double* __restrict__ cap = A.cosr + 3 * (size_t)nlat;
   const double* __restrict__ cam = A.cosr + 4 * (size_t)nlat;
@@ -277,38 +279,60 @@ __global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, Qd
   const bool writer = lane >= 2 && lane < 2 + QD_H4S_COLS && (strip * QD_H4S_COLS + lane - 2) < nlon;
   const double* __restrict__ p = A.src[k] + off + (size_t)(j0 - 4) * nlon + gi;
   double* __restrict__ d = A.dst[k] + off + (size_t)j0 * nlon + gi;
+  bool bad = false;
   auto lap_row = [&](double fm2, double fc, double fp2, double ap, double am, double bl) {
     const double fe = __shfl_down_sync(0xffffffffu, fc, 1), fw = __shfl_up_sync(0xffffffffu, fc, 1);
-    return qd_clean_sel((ap * (fp2 - fc) - am * (fc - fm2)) + bl * ((fe - 2.0 * fc) + fw));
+    return qd_h4s_cl<CLEAN>((ap * (fp2 - fc) - am * (fc - fm2)) + bl * ((fe - 2.0 * fc) + fw), bad);
   };
   // F window f0..f3 = F[j..j+3]; lap window l0..l3 = lap(F)[j-2..j+1]; c?m / c?0 = coefficients of rows j, j+1
-  double f0 = qd_clean_sel(p[0]), f1 = qd_clean_sel(p[nlon]), f2 = qd_clean_sel(p[2 * (size_t)nlon]), f3 = qd_clean_sel(p[3 * (size_t)nlon]);
+  double f0 = qd_h4s_cl<CLEAN>(p[0], bad), f1 = qd_h4s_cl<CLEAN>(p[nlon], bad), f2 = qd_h4s_cl<CLEAN>(p[2 * (size_t)nlon], bad),
+         f3 = qd_h4s_cl<CLEAN>(p[3 * (size_t)nlon], bad);
   p += 4 * (size_t)nlon;
   double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
   double apm = 0.0, amm = 0.0, blm = 0.0, ap0 = 0.0, am0 = 0.0, bl0 = 0.0;
-  // One group = 4 rows: the four loads of new F rows and the twelve coefficient loads are issued together
-  // so that their latency overlaps; unrolling by the window length turns the register shifts into renames.
-  // jr = row of the first new Laplacian value of the group; emit = false for the warm-up group.
-#define QD_H4S_GROUP(jr, emit)                                                                       \
-  {                                                                                                  \
+  // One group = 4 rows.  The four new F rows of group q+1 are loaded BEFORE group q is computed (software pipeline:
+  // the streaming loads of a warp are in flight for a whole group of arithmetic instead of being waited for at the top
+  // of it); the twelve coefficient loads of a group are warp-uniform L1 hits issued next to their use.  Unrolling by
+  // the window length turns the register shifts into renames.  jr = row of the first new Laplacian value of the
+  // group; emit = false for the warm-up group.
+#ifndef QD_H4S_PREFETCH
+#define QD_H4S_PREFETCH 0
+#endif
+#if QD_H4S_PREFETCH
+  double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];
+  p += 4 * (size_t)nlon;
+#define QD_H4S_LOADS(more)                                                                           \
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;                                                   \
+    if (more) { m0 = p[0]; m1 = p[nlon]; m2 = p[2 * (size_t)nlon]; m3 = p[3 * (size_t)nlon]; }       \
+    p += 4 * (size_t)nlon;
+#define QD_H4S_ROTATE n0 = m0; n1 = m1; n2 = m2; n3 = m3;
+#else
+#define QD_H4S_LOADS(more)                                                                           \
     const double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];        \
-    p += 4 * (size_t)nlon;                                                                           \
+    p += 4 * (size_t)nlon;
+#define QD_H4S_ROTATE
+#endif
+#define QD_H4S_GROUP(jr, emit, more)                                                                 \
+  {                                                                                                  \
+    QD_H4S_LOADS(more)                                                                               \
     QD_H4S_STEP(n0, cap[(jr)], cam[(jr)], cbl[(jr)], 0, emit)                                        \
     QD_H4S_STEP(n1, cap[(jr) + 1], cam[(jr) + 1], cbl[(jr) + 1], 1, emit)                            \
     QD_H4S_STEP(n2, cap[(jr) + 2], cam[(jr) + 2], cbl[(jr) + 2], 2, emit)                            \
     QD_H4S_STEP(n3, cap[(jr) + 3], cam[(jr) + 3], cbl[(jr) + 3], 3, emit)                            \
+    QD_H4S_ROTATE                                                                                    \
   }
 #define QD_H4S_STEP(nv, apx, amx, blx, s, emit)                                                      \
   {                                                                                                  \
     const double ap = (apx), am = (amx), bl = (blx);       /* warp-uniform L1 hits, loaded next to their use */ \
-    const double f4 = qd_clean_sel(nv);                                                             \
+    const double f4 = qd_h4s_cl<CLEAN>(nv, bad);                                                     \
     const double l4 = lap_row(f0, f2, f4, ap, am, bl);                                               \
     if (emit) {                                                                                      \
       const int r = j - j0 + (s);                                                                    \
       const double le = __shfl_down_sync(0xffffffffu, l2, 1), lw = __shfl_up_sync(0xffffffffu, l2, 1); \
       const double L2 = (apm * (l4 - l2) - amm * (l2 - l0)) + blm * ((le - 2.0 * l2) + lw);          \
       const double k4 = __shfl_sync(0xffffffffu, (R > 32 && r >= 32) ? kq1 : kq0, r & 31);           \
-      if (writer && j + (s) < j1) d[(size_t)(s) * nlon] = qd_clean_sel(f0 - k4 * L2 * inner);       \
+      const double o = qd_h4s_cl<CLEAN>(f0 - k4 * L2 * inner, bad);                                  \
+      if (writer && j + (s) < j1) d[(size_t)(s) * nlon] = o;                                         \
     }                                                                                                \
     l0 = l1; l1 = l2; l2 = l3; l3 = l4;                                                              \
     apm = ap0; amm = am0; blm = bl0; ap0 = ap; am0 = am; bl0 = bl;                                   \
@@ -316,14 +340,39 @@ __global__ void __launch_bounds__(32 * QD_H4S_WARPS) k_hyper4_stream(QdGeo g, Qd
   }
   {
     const int j = j0;
-    QD_H4S_GROUP(j0 - 2, false)                            // warm-up: lap(F) at rows j0-2 .. j0+1
+    QD_H4S_GROUP(j0 - 2, false, true)                      // warm-up: lap(F) at rows j0-2 .. j0+1
   }
   for (int j = j0; j < j1; j += 4) {
-    QD_H4S_GROUP(j + 2, true)
+    QD_H4S_GROUP(j + 2, true, j + 4 < j1)
     d += 4 * (size_t)nlon;
   }
 #undef QD_H4S_GROUP
 #undef QD_H4S_STEP
+#undef QD_H4S_LOADS
+#undef QD_H4S_ROTATE
+  return bad;
+}
+#ifndef QD_H4S_MINB
+#define QD_H4S_MINB 6
+#endif
+template <int R>
+__global__ void __launch_bounds__(32 * QD_H4S_WARPS, QD_H4S_MINB) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
+  static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
+  const int b = blockIdx.y;
+  if (A.ocean && qd_sub_done(g, b, A.sc)) return;
+  const int lane = threadIdx.x & 31;
+  const int nstrips = (g.nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+  const int w = blockIdx.x * QD_H4S_WARPS + (threadIdx.x >> 5);
+  const int chunk = w / nstrips, strip = w - chunk * nstrips;
+  const int j0 = A.ja + chunk * R;
+  if (j0 >= A.jb) return;
+  const int j1 = min(j0 + R, A.jb);
+  const int k = blockIdx.z;
+  const bool bad = qd_h4s_chunk<R, false>(g, A, b, k, lane, strip, j0, j1);
+  if (__any_sync(0xffffffffu, bad)) {                      // a non-finite value: redo the chunk with np.nan_to_num applied
+    __syncwarp();
+    qd_h4s_chunk<R, true>(g, A, b, k, lane, strip, j0, j1);
+  }
 }
 #else
 // Host check build: the same tile algorithm with cooperative loops written so that one sequential

@@ -202,6 +202,84 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
   }
 }
 
+#if !QD_EMU
+// The same pass with TWO adjacent cells per thread (n_lon even): one row / column index, 16-byte loads of the pair's own
+// values and of its north / south neighbours, shared row constants (the one-cell kernel spends 44 % of its issue slots on
+// index arithmetic: profiles/README.md).  Virtual block vb owns PAIRS vb*256 + t + k*nvb*256; a thread adds its cells in
+// that order, so the eta sum is still a function of the grid and the device only (not of the batch size).
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity2(QdGeo g, QdOcContArgs A, QdSubCtl sc) {
+  const bool done = qd_sub_done(g, blockIdx.y, sc);
+  const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
+  const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
+  const double al = P[QD_P_OC_ADV_ALPHA], mH = -sub_dt * P[QD_P_OC_H];
+  const int nlon = g.nlon, nlat = g.nlat;
+  const double* cosr = qd_row(g, QD_R_COS);
+  const double* iacc = qd_row(g, QD_R_INV_ACOS_CAP);
+  const double* wrow = qd_row(g, QD_R_W);
+  const double* cosh = qd_row(g, QD_R_COS_ADV_HALF);
+  const double* iach = qd_row(g, QD_R_INV_ACOS_HALF);
+  double t;
+  double* part = A.part + (size_t)blockIdx.y * g.nvb;
+  QD_VB_LOOP(g) {
+    double contrib = 0.0;
+    QD_VB_CELLS(g, done ? 0 : g.ncomp / 2) {
+      const int t2 = 2 * t_;
+      const int r_ = qd_div_nlon(g, t2);
+      const int i = t2 - r_ * nlon;
+      const int j = qd_seg_row(g, r_);
+      const int idx = j * nlon + i;
+      const double* ub = A.ub + off;
+      const double* vb = A.vb + off;
+      const double2 u2 = *reinterpret_cast<const double2*>(ub + idx);
+      const double2 v2 = *reinterpret_cast<const double2*>(vb + idx);
+      const double uw = ub[i > 0 ? idx - 1 : idx + nlon - 1];
+      const double ue = ub[i + 2 < nlon ? idx + 2 : idx + 2 - nlon];
+      const double du0 = (u2.y - uw) * g.inv_2dlon, du1 = (ue - u2.x) * g.inv_2dlon;
+      double dv0 = 0.0, dv1 = 0.0;
+      if (j > 0 && j < nlat - 1) {
+        const double2 vn = *reinterpret_cast<const double2*>(vb + idx + nlon);
+        const double2 vs = *reinterpret_cast<const double2*>(vb + idx - nlon);
+        const double cp = cosr[j + 1], cm = cosr[j - 1];
+        dv0 = (vn.x * cp - vs.x * cm) * g.inv_2dlat;
+        dv1 = (vn.y * cp - vs.y * cm) * g.inv_2dlat;
+      }
+      const double ia = iacc[j];
+      const double div0 = ia * (du0 + dv0), div1 = ia * (du1 + dv1);
+      const double2 ein = *reinterpret_cast<const double2*>(A.eta_in + off + idx);
+      const uchar2 l2 = *reinterpret_cast<const uchar2*>(A.land + off + idx);
+      double e0 = ein.x + (mH * div0), e1 = ein.y + (mH * div1);
+      const bool ld0 = l2.x == 1, ld1 = l2.y == 1;
+      if (ld0) e0 = 0.0;
+      if (ld1) e1 = 0.0;
+      *reinterpret_cast<double2*>(A.eta + off + idx) = make_double2(e0, e1);
+      if (qd_owned(g, j)) {
+        const double w = wrow[j];
+        contrib += e0 * (w * (ld0 ? 0.0 : 1.0));
+        contrib += e1 * (w * (ld1 ? 0.0 : 1.0));
+      }
+      const double cj = cosh[j], ij = iach[j];
+      double y0, x0, y1, x1;
+      qd_departure(u2.x, v2.x, sub_dt, g, cj, ij, j, i, &y0, &x0);
+      qd_departure(u2.y, v2.y, sub_dt, g, cj, ij, j, i + 1, &y1, &x1);
+      const double adv0 = qd_bilinear_wrap(A.sst + off, nlat, nlon, y0, x0);
+      const double adv1 = qd_bilinear_wrap(A.sst + off, nlat, nlon, y1, x1);
+      const double2 s2 = *reinterpret_cast<const double2*>(A.sst + off + idx);
+      *reinterpret_cast<double2*>(A.tb + off + idx) = make_double2((1.0 - al) * s2.x + al * adv0, (1.0 - al) * s2.y + al * adv1);
+    }
+    if (qd_block_sum<0>(contrib, &t)) part[vb_] = t;
+  }
+  if (qd_block_is_last(A.ticket + blockIdx.y, gridDim.x)) {
+    if (qd_final_sum<1>(part, g.nvb, &t)) {
+      if (A.band.world > 1) {
+        qd_band_publish(A.band, done ? 0.0 : t);
+        t = qd_band_pull_sum(A.band);
+      }
+      if (!done) g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_ETA_NUM] = t;
+    }
+  }
+}
+#endif
+
 // SST diffusion + Q_net heating (ocean.py:384-406), outlier handling of currents (ocean.py:408-434): B -> A.
 // On the member's last sub-step the non-polar rows also get the final Ts clip (ocean.py:531-533) and,
 // in loop mode, the SST injection into the atmosphere's T_s (run_simulation.py:2252-2253); the two
@@ -212,18 +290,10 @@ struct QdOcSstBArgs {
   const uint8_t *land, *ice;
   int has_q, has_ice, inject;
 };
-__global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
-  QD_CELL_PROLOGUE(g)
-  // the ocean-mean of eta (one true division) once per block instead of once per cell
-  __shared__ double s_eta_mean;
-  if (threadIdx.x == 0) {
-    const double* Pm = g.prm + (size_t)b * QD_P_COUNT;
-    s_eta_mean = g.scal[(size_t)b * QD_S_COUNT + QD_S_ETA_NUM] / (Pm[QD_P_OC_WSUM_OCEAN] + 1e-15);
-  }
-#if !QD_EMU
-  __syncthreads();
-#endif
-  if (!active || qd_sub_done(g, b, sc)) return;
+// One cell of the closing pass, general form (any row: one-sided Laplacian next to the poles, every value cleaned).
+QD_D void qd_sstf_cell_general(const QdGeo& g, const QdOcSstBArgs& A, const QdSubCtl& sc, int b, int j, int i, double eta_mean) {
+  const size_t off = (size_t)b * g.ncell;
+  const int idx = j * g.nlon + i;
   const size_t c = off + idx;
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const double* S = g.scal + (size_t)b * QD_S_COUNT;
@@ -231,7 +301,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   const int nlon = g.nlon, nlat = g.nlat;
   {   // eta: mean removal over the ocean + hygiene (ocean.py:375,436-443); the sum comes from k_ocean_continuity
     double e = A.eta[c];
-    if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - s_eta_mean;
+    if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - eta_mean;
     A.eta[c] = qd_clip(qd_nan_to_num(e), -P[QD_P_OC_ETA_CAP], P[QD_P_OC_ETA_CAP]);
   }
   double T = A.tb[c];
@@ -283,6 +353,164 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSs
   }
   A.sst[c] = T;
 }
+__global__ void __launch_bounds__(QD_THREADS) k_ocean_sst_finish(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
+  QD_CELL_PROLOGUE(g)
+  // the ocean-mean of eta (one true division) once per block instead of once per cell
+  __shared__ double s_eta_mean;
+  if (threadIdx.x == 0) {
+    const double* Pm = g.prm + (size_t)b * QD_P_COUNT;
+    s_eta_mean = g.scal[(size_t)b * QD_S_COUNT + QD_S_ETA_NUM] / (Pm[QD_P_OC_WSUM_OCEAN] + 1e-15);
+  }
+#if !QD_EMU
+  __syncthreads();
+#endif
+  if (!active || qd_sub_done(g, b, sc)) return;
+  qd_sstf_cell_general(g, A, sc, b, j, i, s_eta_mean);
+}
+
+#if !QD_EMU
+// ---- the same pass with TWO adjacent cells per thread (n_lon even) and np.nan_to_num applied lazily.
+// The one-cell kernel spent 38 % of its issue slots on index arithmetic, 25 % on the select chains of nan_to_num
+// and 8 % on parameter loads against 8 % of fp64 arithmetic (profiles/README.md, SASS mix of the r02 capture): here
+// a thread forms one row / column index for two cells, loads them as 16-byte vectors, shares the row constants and
+// parameters, and only tracks whether a value the reference would have cleaned was non-finite (one DSETP per
+// value); a pair that saw one recomputes with the cleaning applied, from the same registers -- identical bits.
+// Rows whose Laplacian is one-sided (j < 2, j > n_lat-3) and cells above the speed cap take the general cell code.
+template <bool CLEAN>
+__device__ __forceinline__ double qd_lz(double x, bool& bad) {
+  if (CLEAN) return qd_nan_to_num(x);
+  bad = bad || !(fabs(x) <= DBL_MAX);
+  return x;
+}
+struct QdSstfK {                       // block-uniform constants of the closing pass
+  double eta_mean, eta_cap, kh, sub_dt, irch, qfac, ts_min, ts_max, speed2_cap;
+  bool any_ocean, use_q, has_ice, ice_q, last, inject;
+};
+struct QdSstfRow { double cp, cm, ic, ic2; };      // cos(j+1), cos(j-1), 1/cos(j), 1/cos(j)^2 of the half-level table
+template <bool CLEAN>
+__device__ __forceinline__ void qd_sstf_fast(const QdGeo& g, const QdSstfK& K, const QdSstfRow& R, double e_in, double t0, double tn, double ts,
+                                             double te, double tw, double qn, double u, double v, bool ocean, bool ice,
+                                             double* eta_o, double* T_o, double* uo_o, double* vo_o, bool* over, bool& bad) {
+  double e = e_in;
+  if (K.any_ocean) e = e - K.eta_mean;
+  *eta_o = qd_clip(qd_lz<CLEAN>(e, bad), -K.eta_cap, K.eta_cap);
+  double T = t0;
+  if (K.kh > 0.0) {
+    // qd_lap_cell's centred form, operand for operand
+    const double f0 = qd_lz<CLEAN>(t0, bad);
+    const double gp = (qd_lz<CLEAN>(tn, bad) - f0) * g.inv_2dlat, gm = (f0 - qd_lz<CLEAN>(ts, bad)) * g.inv_2dlat;
+    const double gphi = (R.cp * gp - R.cm * gm) * g.inv_2dlat;
+    const double term_phi = R.ic * gphi;
+    const double d2 = ((qd_lz<CLEAN>(te, bad) - 2.0 * f0) + qd_lz<CLEAN>(tw, bad)) * g.inv_dlon_sq;
+    const double lap = (term_phi + d2 * R.ic2) * g.inv_a_sq;
+    T = f0 + K.sub_dt * K.kh * lap;
+  }
+  if (K.use_q) {
+    const double tend = qn * K.irch;
+    if (ocean && !ice) T = T + K.sub_dt * tend;
+    else if (ocean && ice && K.ice_q) T = T + K.sub_dt * K.qfac * tend;
+  }
+  T = qd_lz<CLEAN>(T, bad);
+  const double uo = qd_lz<CLEAN>(u, bad), vo = qd_lz<CLEAN>(v, bad);
+  const double s2 = uo * uo + vo * vo;
+  *over = s2 >= K.speed2_cap;
+  if (K.last) T = qd_clip(T, K.ts_min, K.ts_max);
+  *T_o = T; *uo_o = uo; *vo_o = vo;
+}
+// a current above the speed cap (ocean.py:408-434): the general code on that cell's neighbours
+__device__ __forceinline__ void qd_sstf_over(const QdGeo& g, const QdOcSstBArgs& A, int b, int j, int ii, double* uo_io, double* vo_io) {
+  const size_t off = (size_t)b * g.ncell;
+  const int nlon = g.nlon;
+  const double* P = g.prm + (size_t)b * QD_P_COUNT;
+  const double* ub = A.ub + off;
+  const double* vb = A.vb + off;
+  const double cap = P[QD_P_OC_MAX_U];
+  double uo = *uo_io, vo = *vo_io;
+  if (P[QD_P_OC_MEAN4] != 0.0) {
+    const int ip = ii + 1 < nlon ? ii + 1 : 0, im = ii > 0 ? ii - 1 : nlon - 1;
+    const size_t n_ = (size_t)(j + 1) * nlon + ii, s_ = (size_t)(j - 1) * nlon + ii, e_ = (size_t)j * nlon + ip, w_ = (size_t)j * nlon + im;
+    uo = 0.25 * (qd_nan_to_num(ub[n_]) + qd_nan_to_num(ub[s_]) + qd_nan_to_num(ub[e_]) + qd_nan_to_num(ub[w_]));
+    vo = 0.25 * (qd_nan_to_num(vb[n_]) + qd_nan_to_num(vb[s_]) + qd_nan_to_num(vb[e_]) + qd_nan_to_num(vb[w_]));
+    const double sp2 = sqrt(uo * uo + vo * vo);
+    const double sc2 = (sp2 > cap) ? cap / (sp2 + 1e-12) : 1.0;
+    uo = uo * sc2;
+    vo = vo * sc2;
+  } else {
+    const double sc1 = cap / (sqrt(uo * uo + vo * vo) + 1e-12);
+    uo = uo * sc1;
+    vo = vo * sc1;
+  }
+  *uo_io = uo; *vo_io = vo;
+}
+__global__ void __launch_bounds__(QD_THREADS, 3) k_ocean_sst_finish2(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
+  const int b = blockIdx.y;
+  __shared__ QdSstfK sK;
+  if (threadIdx.x == 0) {
+    const double* P = g.prm + (size_t)b * QD_P_COUNT;
+    const double* S = g.scal + (size_t)b * QD_S_COUNT;
+    QdSstfK K;
+    K.eta_mean = S[QD_S_ETA_NUM] / (P[QD_P_OC_WSUM_OCEAN] + 1e-15);
+    K.eta_cap = P[QD_P_OC_ETA_CAP]; K.kh = P[QD_P_OC_K_H]; K.sub_dt = S[QD_S_SUB_DT]; K.irch = P[QD_P_OC_INV_RHO_CP_H];
+    K.qfac = P[QD_P_OC_ICE_QFAC]; K.ts_min = P[QD_P_OC_TS_MIN]; K.ts_max = P[QD_P_OC_TS_MAX]; K.speed2_cap = P[QD_P_OC_SPEED2_CAP];
+    K.any_ocean = P[QD_P_OC_ANY_OCEAN] != 0.0; K.use_q = (P[QD_P_OC_USE_QNET] != 0.0) && A.has_q; K.has_ice = A.has_ice != 0;
+    K.ice_q = A.has_ice && P[QD_P_OC_ICE_QFAC] > 0.0; K.last = (*sc.ctr == (int)S[QD_S_NSUB] - 1); K.inject = A.inject != 0;
+    sK = K;
+  }
+  __syncthreads();
+  const int t2 = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (t2 >= g.ncomp || qd_sub_done(g, b, sc)) return;
+  const int nlon = g.nlon, nlat = g.nlat;
+  const int r_ = qd_div_nlon(g, t2);
+  const int i = t2 - r_ * nlon;                      // even: n_lon is even
+  const int j = qd_seg_row(g, r_);
+  if (j < 2 || j > nlat - 3) {
+    for (int h = 0; h < 2; ++h) qd_sstf_cell_general(g, A, sc, b, j, i + h, sK.eta_mean);
+    return;
+  }
+  const QdSstfK& K = sK;
+  const size_t off = (size_t)b * g.ncell;
+  const int idx = j * nlon + i;
+  const double* __restrict__ tb = A.tb + off;
+  const double* cr = qd_row(g, QD_R_COS_ADV_HALF);
+  const QdSstfRow R{cr[j + 1], cr[j - 1], cr[nlat + j], cr[2 * nlat + j]};
+  const double2 e2 = *reinterpret_cast<const double2*>(A.eta + off + idx);
+  const double2 t2c = *reinterpret_cast<const double2*>(tb + idx);
+  double2 tn2 = t2c, ts2 = t2c;
+  double tw = 0.0, te = 0.0;
+  if (K.kh > 0.0) {
+    tn2 = *reinterpret_cast<const double2*>(tb + idx + 2 * nlon);
+    ts2 = *reinterpret_cast<const double2*>(tb + idx - 2 * nlon);
+    tw = tb[i > 0 ? idx - 1 : idx + nlon - 1];
+    te = tb[i + 2 < nlon ? idx + 2 : idx + 2 - nlon];
+  }
+  double2 q2 = make_double2(0.0, 0.0);
+  if (K.use_q) q2 = *reinterpret_cast<const double2*>(A.qnet + off + idx);
+  const double2 u2 = *reinterpret_cast<const double2*>(A.ub + off + idx);
+  const double2 v2 = *reinterpret_cast<const double2*>(A.vb + off + idx);
+  const uchar2 l2 = *reinterpret_cast<const uchar2*>(A.land + off + idx);
+  uchar2 c2 = make_uchar2(0, 0);
+  if (K.has_ice) c2 = *reinterpret_cast<const uchar2*>(A.ice + off + idx);
+  const bool oc0 = l2.x != 1, oc1 = l2.y != 1, ic0 = c2.x != 0, ic1 = c2.y != 0;
+  double eo0, eo1, T0, T1, uo0, uo1, vo0, vo1;
+  bool ov0, ov1, bad = false;
+  qd_sstf_fast<false>(g, K, R, e2.x, t2c.x, tn2.x, ts2.x, t2c.y, tw, q2.x, u2.x, v2.x, oc0, ic0, &eo0, &T0, &uo0, &vo0, &ov0, bad);
+  qd_sstf_fast<false>(g, K, R, e2.y, t2c.y, tn2.y, ts2.y, te, t2c.x, q2.y, u2.y, v2.y, oc1, ic1, &eo1, &T1, &uo1, &vo1, &ov1, bad);
+  if (bad) {
+    qd_sstf_fast<true>(g, K, R, e2.x, t2c.x, tn2.x, ts2.x, t2c.y, tw, q2.x, u2.x, v2.x, oc0, ic0, &eo0, &T0, &uo0, &vo0, &ov0, bad);
+    qd_sstf_fast<true>(g, K, R, e2.y, t2c.y, tn2.y, ts2.y, te, t2c.x, q2.y, u2.y, v2.y, oc1, ic1, &eo1, &T1, &uo1, &vo1, &ov1, bad);
+  }
+  if (ov0) qd_sstf_over(g, A, b, j, i, &uo0, &vo0);
+  if (ov1) qd_sstf_over(g, A, b, j, i + 1, &uo1, &vo1);
+  *reinterpret_cast<double2*>(A.eta + off + idx) = make_double2(eo0, eo1);
+  *reinterpret_cast<double2*>(A.uo + off + idx) = make_double2(uo0, uo1);
+  *reinterpret_cast<double2*>(A.vo + off + idx) = make_double2(vo0, vo1);
+  *reinterpret_cast<double2*>(A.sst + off + idx) = make_double2(T0, T1);
+  if (K.last && K.inject) {
+    if (oc0 && !ic0) A.ts_atm[off + idx] = T0;
+    if (oc1 && !ic1) A.ts_atm[off + idx + 1] = T1;
+  }
+}
+#endif
 
 // Polar rows: ring means (ocean.py:197-262), final clip, SST injection.  grid = (2 poles, B).
 template <int SLOT, class Fn>
