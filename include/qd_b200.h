@@ -268,6 +268,10 @@ int  qd_set_h4_stream(qd_ctx* ctx, int enable);               /* 0: force the ti
  * form, so it is opt-in.  Default 0. */
 int  qd_set_ocean_fused(qd_ctx* ctx, int enable);
 int  qd_launch_count(qd_ctx* ctx, long long* out);            /* kernels launched so far */
+/* Self-test of the device exp / tanh (csrc/qd_math.cuh: libdevice's algorithms with constant-bank coefficients):
+ * out_host[0..n) = the CUDA library call, out_host[n..2n) = the routine the kernels use, for which = 0 (exp) / 1 (tanh).
+ * The two halves must be bit-identical (tests/test_gpu.py).  Host check build: both halves are libm. */
+int  qd_math_check(qd_ctx* ctx, const double* x_host, long long n, double* out_host /* [2][n] */, int which);   /* sync */
 /* per-kernel device time: CUDA events on the launching stream around every launch while enabled */
 int  qd_profile(qd_ctx* ctx, int enable);
 int  qd_profile_report(qd_ctx* ctx, char* buf, int buflen);   /* "name count total_ms" lines; sync */

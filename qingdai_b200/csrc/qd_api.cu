@@ -1176,6 +1176,24 @@ extern "C" int qd_minmax(qd_ctx* c, const double* in, double* out_host) {
   return QD_OK;
 }
 
+extern "C" int qd_math_check(qd_ctx* c, const double* x_host, long long n, double* out_host, int which) {
+  if (!c || !x_host || !out_host || n <= 0) return QD_E_INVALID;
+#ifdef QD_HOST_EMU
+  for (long long i = 0; i < n; ++i) out_host[i] = out_host[n + i] = which ? tanh(x_host[i]) : exp(x_host[i]);
+#else
+  double *dx = nullptr, *dout = nullptr;
+  QD_CUDA(c, cudaMalloc((void**)&dx, (size_t)n * 8));
+  if (cudaMalloc((void**)&dout, (size_t)n * 16) != cudaSuccess) { cudaFree(dx); return qd_fail(c, QD_E_CUDA, "cudaMalloc", cudaGetLastError()); }
+  cudaMemcpyAsync(dx, x_host, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream);
+  k_math_check<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dx, dout, n, which);
+  cudaMemcpyAsync(out_host, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream);
+  const cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dx); cudaFree(dout);
+  if (e != cudaSuccess) return qd_fail(c, QD_E_CUDA, "qd_math_check", e);
+#endif
+  return QD_OK;
+}
+
 // host-buffer forms of the jax_compat seam (single member, staged through private device buffers)
 static int stage_up(qd_ctx* c, int k, const double* h) { QD_CUDA(c, cudaMemcpyAsync(c->d_stage[k], h, (size_t)c->ncell * 8, cudaMemcpyHostToDevice, c->stream)); return QD_OK; }
 static int stage_down(qd_ctx* c, int k, double* h) {

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_eco_canopy(QdGeo g, QdEcoArgs A)
   QD_CELL_PROLOGUE(g)
   if (!active || g.scal[(size_t)b * QD_S_COUNT + QD_S_ECO_FLAG] == 0.0) return;
   const double tot = qd_eco_total(A, g, b, idx);
-  A.fcanopy[off + idx] = 1.0 - exp(-A.k_canopy * qd_max(tot, 0.0));
+  A.fcanopy[off + idx] = 1.0 - QD_EXP(-A.k_canopy * qd_max(tot, 0.0));
   A.snap[off + idx] = tot;
 }
 

@@ -138,21 +138,21 @@ __global__ void __launch_bounds__(QD_THREADS) k_cloud_a(QdGeo g, QdCloudAArgs A)
     const double ov = P[QD_P_PREF];
     P_ref = (ov == ov) ? ov : qd_scal(g, b, QD_S_PREF);
   }
-  A.craw[c] = P[QD_P_CMAX] * tanh(qd_div_z(A.precip[c], P_ref + 1e-12));      // dry cells have precip == 0
+  A.craw[c] = P[QD_P_CMAX] * QD_TANH(qd_div_z(A.precip[c], P_ref + 1e-12));      // dry cells have precip == 0
   // source
   const double* T = A.ts + off;
   const double Ts = T[idx], u = A.u[c], v = A.v[c];
-  double src = 0.5 * qd_clip(tanh(qd_div_u(Ts - 285.0, D[QD_U_12K])), 0.0, 1.0);
+  double src = 0.5 * qd_clip(QD_TANH(qd_div_u(Ts - 285.0, D[QD_U_12K])), 0.0, 1.0);
   const double vort = qd_vort_cell(A.u + off, A.v + off, j, i, g);
   const double rel = qd_div_z(vort, qd_row(g, QD_R_FCOR)[j] + 1e-12);
-  src = src + 0.4 * qd_clip(tanh((rel - 0.5) / 2.0), 0.0, 1.0);
+  src = src + 0.4 * qd_clip(QD_TANH((rel - 0.5) / 2.0), 0.0, 1.0);
   const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
   const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;
   const double dx = g.dlon * g.a * qd_row(g, QD_R_COS_ADV_ATM)[j];
   const double gx = qd_div_z(T[(size_t)j * nlon + ip] - T[(size_t)j * nlon + im], 2 * dx);
   const double gy = qd_div_u(T[(size_t)jp * nlon + i] - T[(size_t)jm * nlon + i], D[QD_U_2DY]);
   const double adv = -(u * gx + v * gy);
-  src = src + 0.3 * qd_clip(tanh(qd_div_u(fabs(adv), D[QD_U_ADV_REF])), 0.0, 1.0);
+  src = src + 0.3 * qd_clip(QD_TANH(qd_div_u(fabs(adv), D[QD_U_ADV_REF])), 0.0, 1.0);
   A.sraw[c] = src;
 }
 // ---- cloud phase B: Gaussian along longitude of both fields, then the blend

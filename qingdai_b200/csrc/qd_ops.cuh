@@ -7,6 +7,7 @@
 // expressions exactly (compile with -fmad=false) so fields agree to the last few ulp.
 #pragma once
 #include "qd_rt.h"
+#include "qd_math.cuh"
 #include "../../include/qd_b200.h"
 
 #define QD_THREADS 256

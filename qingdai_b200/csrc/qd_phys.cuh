@@ -11,7 +11,7 @@
 // ------------------------------------------------------------------------------ humidity (humidity.py)
 QD_HD double qd_qsat(double T, double p0) {                       // humidity.py:85-101
   const double Tc = qd_clip(T - 273.15, -80.0, 60.0);
-  const double es = 610.94 * exp(17.625 * Tc / (Tc + 243.04));
+  const double es = 610.94 * QD_EXP(17.625 * Tc / (Tc + 243.04));
   const double den = qd_max(p0 - (1.0 - 0.622) * es, 1.0);
   return qd_clip(0.622 * es / den, 0.0, 0.5);
 }
@@ -45,7 +45,7 @@ QD_HD QdLW qd_longwave(double Ts, double Ta, double cloud, int land, double ice_
     const double Ts4 = qd_pow4(Tsc), Ta4 = qd_pow4(Tac);
     const double eps_clear = qd_clip(P[QD_P_LW_EPS0], 0.0, 1.0);
     const double ce = qd_clip(cloud, 0.0, 1.0);
-    const double eps_cloud = qd_clip(1.0 - exp(-P[QD_P_LW_KTAU] * (P[QD_P_LW_TAU0] * ce)), 0.0, 1.0);
+    const double eps_cloud = qd_clip(1.0 - QD_EXP(-P[QD_P_LW_KTAU] * (P[QD_P_LW_TAU0] * ce)), 0.0, 1.0);
     const double eps_eff = 1.0 - (1.0 - eps_clear) * (1.0 - eps_cloud);
     double es;
     if (land) es = P[QD_P_EPS_LAND];
@@ -75,10 +75,10 @@ QD_HD QdLW qd_longwave(double Ts, double Ta, double cloud, int land, double ice_
   return o;
 }
 QD_HD double qd_ice_frac(double h_ice, double href) {              // dynamics.py:362, run_simulation.py:2065
-  return 1.0 - exp(-qd_max(h_ice, 0.0) / qd_max(1e-6, href));
+  return 1.0 - QD_EXP(-qd_max(h_ice, 0.0) / qd_max(1e-6, href));
 }
 QD_HD double qd_ice_frac_u(double h_ice, const QdRcp& href) {      // same, href = RN-reciprocal pair of max(1e-6, H_ice_ref)
-  return 1.0 - exp(qd_div_u(-qd_max(h_ice, 0.0), href));
+  return 1.0 - QD_EXP(qd_div_u(-qd_max(h_ice, 0.0), href));
 }
 QD_HD double qd_sensible(double Ts, double Ta, double u, double v, const double* P) {   // energy.py:439-442
   const double V = sqrt(u * u + v * v);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
     const double hs_eff = (qd_mrow(g, QD_R_POLAR, b)[j] != 0.0) ? qd_min(hs_geom, P[QD_P_POLAR_ICE_THICK_MAX]) : hs_geom;
     const double H_eff = qd_min(Hb + hs_eff, P[QD_P_LAND_ELEV_MAX]);
     const double T_hat = (P[QD_P_LAPSE_ENABLE] != 0.0) ? Ta_proxy - P[QD_P_LAPSE_KPM] * qd_div_u(H_eff, D[QD_U_1000]) : Ta_proxy;
-    const double f_snow = qd_clip(1.0 / (1.0 + exp(qd_div_u(T_hat - P[QD_P_SNOW_THRESH], D[QD_U_SNOW_BAND]))), 0.0, 1.0);
+    const double f_snow = qd_clip(1.0 / (1.0 + QD_EXP(qd_div_u(T_hat - P[QD_P_SNOW_THRESH], D[QD_U_SNOW_BAND]))), 0.0, 1.0);
     const double P_snow = qd_nan_to_num(f_snow * precip);
     const double P_rain = qd_nan_to_num((1.0 - f_snow) * precip);
     double C_snow = 0.0, S_next = S0, melt = 0.0;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
       if (P[QD_P_SWE_MAX] > 0.0) S_next = qd_min(S_next, P[QD_P_SWE_MAX]);
       S_next = qd_max(0.0, S_next);
       melt = qd_nan_to_num(qd_div_u(amt, D[QD_U_DT]));
-      C_snow = qd_clip(1.0 - exp(qd_div_u(-qd_max(S_next, 0.0), D[QD_U_SWE_REF])), 0.0, 1.0);
+      C_snow = qd_clip(1.0 - QD_EXP(qd_div_u(-qd_max(S_next, 0.0), D[QD_U_SWE_REF])), 0.0, 1.0);
       S_next = qd_nan_to_num(S_next);
       glacier = land && ((C_snow >= P[QD_P_GLACIER_FRAC]) || (S_next >= P[QD_P_GLACIER_SWE]));
       const double rain_gl = (P_rain * (land ? 1.0 : 0.0)) * (glacier ? 1.0 : 0.0);
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_energy(QdGeo g, QdEnergyArgs A) 
     const double Pc = A.pcond[c];
     const double pref_over = P[QD_P_PCOND_REF];
     const double P_ref = (pref_over == pref_over) ? pref_over : g.scal[(size_t)b * QD_S_COUNT + QD_S_PREF_ATM];
-    const double p_term = tanh((P_ref > 0) ? qd_div_z(Pc, P_ref) : 0.0);          // Pc is zero wherever nothing condenses
+    const double p_term = QD_TANH((P_ref > 0) ? qd_div_z(Pc, P_ref) : 0.0);          // Pc is zero wherever nothing condenses
     cloud_eff = qd_clip(cloud_eff + P[QD_P_K_Q] * rh_ex + P[QD_P_K_P] * p_term, 0.0, 1.0);
   }
   A.cloud_eff[c] = cloud_eff;

@@ -106,21 +106,16 @@ QD_HD double qd_nan_to_num(double x) {
   return x;
 #endif
 }
-QD_HD double qd_clip(double x, double lo, double hi) {   // np.clip = minimum(maximum(x, lo), hi), NaN propagates
-  if (x != x) return x;
-  double y = x < lo ? lo : x;
+// np.clip = minimum(maximum(x, lo), hi) for non-NaN bounds; a NaN x fails both comparisons and comes out unchanged, so
+// no separate NaN test is needed (it was 7-14 % of the issue slots of the column / energy / tail kernels)
+QD_HD double qd_clip(double x, double lo, double hi) {
+  const double y = x < lo ? lo : x;
   return y > hi ? hi : y;
 }
-QD_HD double qd_max(double a, double b) {                // np.maximum: NaN propagates
-  if (a != a) return a;
-  if (b != b) return b;
-  return a > b ? a : b;
-}
-QD_HD double qd_min(double a, double b) {
-  if (a != a) return a;
-  if (b != b) return b;
-  return a < b ? a : b;
-}
+// np.maximum / np.minimum: NaN propagates from either argument.  (a > b || a != a) ? a : b -- a NaN b fails the
+// comparison and is returned by the else branch.
+QD_HD double qd_max(double a, double b) { return (a > b || a != a) ? a : b; }
+QD_HD double qd_min(double a, double b) { return (a < b || a != a) ? a : b; }
 
 // ------------------------------------------------------------------------------ block reductions
 // Each returns true in exactly ONE thread of the block, with *total = reduction over the block.

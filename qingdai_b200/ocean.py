@@ -56,7 +56,7 @@ class WindDrivenSlabOcean:
         if getattr(self, "_wind", None) is None:
             self._wind = torch.empty((2, e.batch, e.nlat, e.nlon), dtype=torch.float64, device=e.device)
         for k, a in enumerate((u_atm, v_atm)):
-            self._wind[k].copy_(torch.from_numpy(np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (e.batch,) + e.shape))))
+            self._wind[k].copy_(torch.from_numpy(np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), (e.batch,) + e.shape))))
         if Q_net is not None:
             e.set("qnet", np.asarray(Q_net, dtype=np.float64))
         if ice_mask is not None:

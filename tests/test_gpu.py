@@ -116,6 +116,10 @@ def test_hyper4_streaming_kernel(lib):
     qdcheck.check_hyper4_stream(lib)
 
 
+def test_math_matches_libdevice(lib):
+    qdcheck.check_math_matches_libdevice(lib)
+
+
 @pytest.mark.parametrize("tag", ["p1", "p2"])
 def test_phyto_transport(lib, golden, tag):
     qdcheck.check_phyto(lib, golden("phyto_golden.npz"), tag)
