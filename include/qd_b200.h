@@ -289,6 +289,10 @@ int  qd_band_init(qd_ctx* ctx, int rank, int world, int halo_rows);
 int  qd_band_export(qd_ctx* ctx, void* handle64);
 int  qd_band_connect(qd_ctx* ctx, const void* handles /* [world][64] in rank order */);
 int  qd_band_info(qd_ctx* ctx, int* own0, int* own1, int* halo_rows, int* error_word /* != 0: a bounded wait expired */);
+/* Tuning aid: `iters` back-to-back halo exchanges of the first `nfields` field slots (values are exchanged as they
+ * are: the halo rows of those fields are overwritten with the neighbours' current rows); *ms_out = device time of the
+ * loop on this rank.  Every rank of the band group must call it with the same arguments. */
+int  qd_band_exchange_bench(qd_ctx* ctx, int nfields, int iters, float* ms_out);                /* sync */
 
 /* ------------------------------------------------------------------ ecology sub-daily
  * Replaces EcologyAdapter.step_subdaily (adapter.py:140-186) + PopulationManager.step_subdaily /

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "qd_wsum": (_I, [_P, _P, _P]),
     "qd_minmax": (_I, [_P, _P, _P]),
     "qd_math_check": (_I, [_P, _P, C.c_longlong, _P, _I]),
+    "qd_band_exchange_bench": (_I, [_P, _I, _I, _P]),
     "qd_row_dev": (_P, [_P, _I]),
     "qd_user_row": (_P, [_P, _I, _P]),
     "qd_user_row_member": (_I, [_P, _I, _I, _P]),

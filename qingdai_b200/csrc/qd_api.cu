@@ -73,6 +73,12 @@ struct qd_ctx {
 #ifndef QD_HOST_EMU
   cudaStream_t cap_stream, cap_stream2;
   cudaGraph_t capture_graph;                        // non-null while a whole loop step is being captured
+  // side streams: small kernels that only touch rows nobody else writes (the del^4 pole tiles) run NEXT TO the main
+  // kernel of their phase instead of after it (fork / join by events; inside a capture they become parallel graph
+  // branches).  One per capture level: a stream that joined the step capture cannot join the capture of the ocean's
+  // WHILE body (level 1) as well.
+  cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  int side_level = 0, side_enable = 1;
   std::map<const void*, int> red_cache;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
@@ -225,6 +231,31 @@ static void qd_drop_graphs(qd_ctx* c) {
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
 static bool qd_prof_on(qd_ctx* c) { return c->prof && qd_prof_of(c)->on; }
 #endif
+#ifndef QD_HOST_EMU
+// fork: the side stream of the current capture level starts after everything enqueued on the main stream so far and
+// becomes the launch stream; qd_side_end returns to the main stream; qd_side_join makes the main stream wait for it.
+static bool qd_side_begin(qd_ctx* c, cudaStream_t* saved) {
+  if (!c->side_enable) return false;
+  const int L = c->side_level;
+  if (!c->side[L]) {
+    if (cudaStreamCreateWithFlags(&c->side[L], cudaStreamNonBlocking) != cudaSuccess) { c->side[L] = nullptr; c->side_enable = 0; cudaGetLastError(); return false; }
+    cudaEventCreateWithFlags(&c->ev_fork[L], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join[L], cudaEventDisableTiming);
+  }
+  if (cudaEventRecord(c->ev_fork[L], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->side[L], c->ev_fork[L], 0) != cudaSuccess) { cudaGetLastError(); return false; }
+  *saved = c->stream;
+  c->stream = c->side[L];
+  return true;
+}
+static void qd_side_end(qd_ctx* c, cudaStream_t saved) { c->stream = saved; }
+static void qd_side_join(qd_ctx* c) {
+  const int L = c->side_level;
+  cudaEventRecord(c->ev_join[L], c->side[L]);
+  cudaStreamWaitEvent(c->stream, c->ev_join[L], 0);
+}
+struct QdSideLevel { qd_ctx* c; int saved; QdSideLevel(qd_ctx* c_, int l) : c(c_), saved(c_->side_level) { c->side_level = l; } ~QdSideLevel() { c->side_level = saved; } };
+#endif
+
 extern "C" int qd_profile(qd_ctx* c, int enable) {
   if (!c) return QD_E_INVALID;
 #ifndef QD_HOST_EMU
@@ -325,6 +356,7 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
+  c->side_enable = getenv("QD_NO_SIDE") ? 0 : 1;                 // tuning / A-B switch
 #endif
   const size_t nrows = (size_t)(QD_R_COUNT + 7 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
   // a failed allocation releases everything allocated so far (qd_destroy frees null pointers harmlessly)
@@ -435,6 +467,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   qd_drop_graphs(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
+  for (int L = 0; L < 2; ++L) if (c->side[L]) { cudaStreamDestroy(c->side[L]); cudaEventDestroy(c->ev_fork[L]); cudaEventDestroy(c->ev_join[L]); }
 #endif
   delete c;
   return QD_OK;
@@ -612,8 +645,8 @@ static int band_exchange(qd_ctx* c, const int* ids, int n) {
     QdBandList L; memset(&L, 0, sizeof(L));
     L.n = std::min(QD_BAND_MAXX, n - k0);
     for (int k = 0; k < L.n; ++k) { L.f[k] = F(c, ids[k0 + k]); c->band_valid[ids[k0 + k]] = c->band.H; }
-    // every block waits on a peer: the whole grid must be resident (gx * fields * 2 <= 480 blocks of 256 threads)
-    const int gx = std::max(1, std::min(QD_BAND_GX, (c->band.H * c->nlon / 2 + 4 * QD_THREADS - 1) / (4 * QD_THREADS)));
+    // every block waits on a peer: the whole grid must be resident (gx * fields * 2 <= 960 blocks of 256 threads; 148 SMs hold 1184)
+    const int gx = std::max(1, std::min(QD_BAND_GX, (c->band.H * c->nlon + 2 * QD_THREADS - 1) / (2 * QD_THREADS)));   // ~2 lines per thread
 #ifdef QD_HOST_EMU
     QD_KG(c, k_band_exchange, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1, 1);
     QD_KG(c, k_band_exchange, dim3(gx, L.n, 2), dim3(QD_THREADS), c->band, L, c->geo.own0, c->geo.own1, 2);
@@ -698,7 +731,7 @@ static int band_allreduce(qd_ctx* c, std::initializer_list<int> ids, bool is_max
   if (!c->band_on) return QD_OK;
   QdBandRed R; memset(&R, 0, sizeof(R));
   for (int id : ids) { R.id[R.n] = id; R.is_max[R.n] = is_max ? 1 : 0; R.n++; }
-  QD_KG(c, k_band_allreduce, dim3(1), dim3(32), c->band, R, c->d_scal);
+  QD_KG(c, k_band_allreduce, dim3(1), dim3(QD_BAND_MAXR * QD_BAND_MAXW), c->band, R, c->d_scal);
   return QD_OK;
 }
 
@@ -714,9 +747,9 @@ extern "C" int qd_band_init(qd_ctx* c, int rank, int world, int halo_rows) {
   B.rank = rank; B.world = world; B.H = H; B.nlon = c->nlon; B.nlat = c->nlat;
   size_t off = QD_BF_WORDS * 8;
   auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-  B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * 8);
+  B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * sizeof(QdLine));      // flagged lines, 16 bytes per element
   B.off_sflag = take((size_t)2 * QD_BAND_MAXX * QD_BAND_GX * 8);
-  B.off_red = take((size_t)2 * QD_BAND_MAXW * QD_BAND_MAXR * 8);
+  B.off_red = take((size_t)2 * 2 * QD_BAND_MAXW * QD_BAND_MAXR * sizeof(QdLine));     // flagged lines: [set][parity][src][slot]
   B.off_hist = take((size_t)2 * QD_BAND_MAXW * QD_SEL_MAXBINS * 4);
   B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * 8);
 #ifdef QD_HOST_EMU
@@ -804,6 +837,26 @@ extern "C" int qd_band_info(qd_ctx* c, int* own0, int* own1, int* halo, int* err
   }
   return QD_OK;
 }
+extern "C" int qd_band_exchange_bench(qd_ctx* c, int nfields, int iters, float* ms_out) {
+  if (!c || !ms_out || nfields < 1 || nfields > QD_BAND_MAXX || iters < 1) return QD_E_INVALID;
+  if (!c->band_on) return qd_fail(c, QD_E_STATE, "qd_band_exchange_bench needs latitude bands", cudaSuccess);
+  *ms_out = 0.f;
+#ifndef QD_HOST_EMU
+  int ids[QD_BAND_MAXX];
+  for (int k = 0; k < nfields; ++k) ids[k] = k;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int w = 0; w < 3; ++w) { int rc = band_exchange(c, ids, nfields); if (rc) return rc; }
+  cudaEventRecord(a, c->stream);
+  for (int k = 0; k < iters; ++k) { int rc = band_exchange(c, ids, nfields); if (rc) return rc; }
+  cudaEventRecord(b, c->stream);
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(ms_out, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  band_invalidate_dynamic(c);
+#endif
+  return QD_OK;
+}
 static void band_release(qd_ctx* c) {
   if (!c->band_base) return;
 #ifdef QD_HOST_EMU
@@ -859,9 +912,15 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
         H.ja = ja; H.jb = jb;
         const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
         const int nwarps = nstrips * ((jb - ja + R - 1) / R);
-        QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        // the rows next to a pole (tile kernel) on the side stream, next to the streaming kernel
+        cudaStream_t saved = nullptr;
+        const bool pole = s0 < ja || jb < s1;
+        const bool side = pole && qd_side_begin(c, &saved);
         if (s0 < ja) { H.row0 = s0; H.row1 = ja; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((ja - s0 + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
         if (jb < s1) { H.row0 = jb; H.row1 = s1; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((s1 - jb + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
+        if (side) qd_side_end(c, saved);
+        QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        if (side) qd_side_join(c);
         continue;
       }
 #endif
@@ -879,9 +938,14 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
     H.ja = 8; H.jb = (ntj8 - 2) * 8;
     const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
     const int nwarps = nstrips * ((H.jb - H.ja + R - 1) / R);
-    QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
     H.tj_lo = 1; H.tj_skip = ntj8 - 3;
+    // the three tile rows that touch a pole on the side stream, next to the streaming kernel (disjoint output rows)
+    cudaStream_t saved = nullptr;
+    const bool side = qd_side_begin(c, &saved);
     QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * 3, c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
+    if (side) qd_side_end(c, saved);
+    QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+    if (side) qd_side_join(c);
     return QD_OK;
   }
 #endif
@@ -1709,6 +1773,7 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
 // once as the body of a CUDA-graph WHILE node (graph mode); the sub-step index is read from device memory.
 static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap) {
 #ifndef QD_HOST_EMU
+  QdSideLevel side_level(c, 1);
   const int fused_rows = ocean_fused_rows(c, cfg, do_hyper, do_shap);
   c->ocean_fused = fused_rows > 0;
   if (c->ocean_fused) return ocean_substep_fused(c, cfg, inject, fused_rows);

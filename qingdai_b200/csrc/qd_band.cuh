@@ -44,9 +44,6 @@ struct QdBandCtl {
   unsigned long long off_inbox, off_red, off_hist, off_list, off_emu, off_sflag;   // byte offsets, identical on every rank
 };
 QD_HD unsigned long long* qd_bflags(const QdBandCtl& B, int r) { return (unsigned long long*)B.peer[r]; }
-QD_HD double* qd_binbox(const QdBandCtl& B, int r, int parity, int dir, int slot) {
-  return (double*)(B.peer[r] + B.off_inbox) + (((size_t)parity * 2 + dir) * QD_BAND_MAXX + slot) * (size_t)B.H * B.nlon;
-}
 QD_HD double* qd_bred(const QdBandCtl& B, int r, int parity, int src) {
   return (double*)(B.peer[r] + B.off_red) + ((size_t)parity * QD_BAND_MAXW + src) * QD_BAND_MAXR;
 }
@@ -85,17 +82,74 @@ QD_D bool qd_band_wait(const QdBandCtl& B, const unsigned long long* flag, unsig
   return false;
 }
 
+// ---- flagged lines ("LL" protocol, the low-latency form NCCL uses): one double travels as a 16-byte line
+// {lo32, flag32, hi32, flag32}; each 8-byte half is written atomically, so a reader that sees the expected flag in
+// BOTH halves has the whole value.  Data and "it has arrived" are ONE posted store: no fence, no separate flag
+// store, no second NVLink round trip; the receiver polls its OWN memory.  Lines are double-buffered by epoch parity
+// and the flag is the (never zero) low word of the epoch, so a stale line can never be mistaken for a fresh one.
+struct QdLine { unsigned long long w[2]; };
+#if QD_EMU
+static inline void qd_ll_store(QdLine* l, double v, unsigned flag) {
+  unsigned long long u; memcpy(&u, &v, 8);
+  const unsigned long long a = (u & 0xffffffffull) | ((unsigned long long)flag << 32), b = (u >> 32) | ((unsigned long long)flag << 32);
+  __sync_synchronize();
+  *(volatile unsigned long long*)&l->w[0] = a; *(volatile unsigned long long*)&l->w[1] = b;
+  __sync_synchronize();
+}
+static inline bool qd_ll_load(const QdLine* l, unsigned flag, double* v) {
+  __sync_synchronize();
+  const unsigned long long a = *(volatile const unsigned long long*)&l->w[0], b = *(volatile const unsigned long long*)&l->w[1];
+  if ((unsigned)(a >> 32) != flag || (unsigned)(b >> 32) != flag) return false;
+  const unsigned long long u = (a & 0xffffffffull) | (b << 32);
+  memcpy(v, &u, 8);
+  return true;
+}
+#else
+__device__ __forceinline__ void qd_ll_store(QdLine* l, double v, unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(l), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool qd_ll_load(const QdLine* l, unsigned flag, double* v) {
+  unsigned a, fa, b, fb;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(l) : "memory");
+  if (fa != flag || fb != flag) return false;
+  *v = __hiloint2double((int)b, (int)a);
+  return true;
+}
+#endif
+// spin until the line carries `flag`; false (and the error word) when the bound is hit
+QD_D bool qd_ll_wait(const QdBandCtl& B, const QdLine* l, unsigned flag, double* v) {
+  if (qd_bflags(B, B.rank)[QD_BF_ERR] != 0ull) { *v = 0.0; return false; }
+  for (unsigned n = 0; n < QD_BAND_SPIN; ++n) {
+    if (qd_ll_load(l, flag, v)) return true;
+#if QD_EMU
+    if ((n & 1023u) == 1023u) sched_yield();
+#endif
+  }
+  qd_bflags(B, B.rank)[QD_BF_ERR] = 1ull;
+  *v = 0.0;
+  return false;
+}
+QD_HD unsigned qd_ll_flag(unsigned long long epoch) { const unsigned f = (unsigned)epoch; return f ? f : 0x80000000u; }
+// scalar mailboxes: line [set][parity][src][slot]; set 0 = k_band_allreduce, set 1 = publish / pull
+QD_HD QdLine* qd_bline(const QdBandCtl& B, int r, int set, int parity, int src, int slot) {
+  return (QdLine*)(B.peer[r] + B.off_red) + (((size_t)set * 2 + parity) * QD_BAND_MAXW + src) * QD_BAND_MAXR + slot;
+}
+
 // ---------------------------------------------------------------------------------------------- halo rows
 struct QdBandList { int n; double* f[QD_BAND_MAXX]; };     // member-0 base pointers of the fields to exchange
 
 // ONE kernel per exchange, grid (gx slices, n fields, 2 directions), every block resident (gx * n * 2 <= one wave).
-// Block (x, k, dir) stores slice x of field k's boundary rows into the neighbour on side `dir` (dir 0: my lowest H
-// rows to my SOUTH neighbour, dir 1: my top H rows to my NORTH neighbour), publishes the slice's own epoch flag
-// there, then waits for the matching slice from the opposite neighbour and copies it next to my own rows (mod
-// n_lat: the ring is closed over the poles).  No grid-wide dependency: a slice is unpacked as soon as it arrived.
-#define QD_BAND_GX 24
-QD_HD unsigned long long* qd_bslice_flag(const QdBandCtl& B, int r, int dir, int k, int x) {
-  return (unsigned long long*)(B.peer[r] + B.off_sflag) + ((size_t)dir * QD_BAND_MAXX + k) * QD_BAND_GX + x;
+// Block (x, k, dir) sends slice x of field k's boundary rows to the neighbour on side `dir` (dir 0: my lowest H rows to
+// my SOUTH neighbour, dir 1: my top H rows to my NORTH neighbour) as flagged lines -- value and arrival flag in one
+// 16-byte posted store per element, straight into the neighbour's inbox over NVLink: no block barrier, no fence, no
+// separate flag store on the sender -- then collects the matching slice from the opposite neighbour out of its OWN
+// inbox, element by element as the lines land, and writes it next to my own rows (mod n_lat: the ring is closed over
+// the poles).  Measured on 2 B200s (tools/band_micro.py, profiles/README.md) against the earlier copy + fence + slice
+// flag + unpack form.  No grid-wide dependency; inboxes are double-buffered by epoch parity.
+#define QD_BAND_GX 48
+QD_HD QdLine* qd_binbox(const QdBandCtl& B, int r, int parity, int dir, int slot) {
+  return (QdLine*)(B.peer[r] + B.off_inbox) + (((size_t)parity * 2 + dir) * QD_BAND_MAXX + slot) * (size_t)B.H * B.nlon;
 }
 // phase: 1 = push, 2 = receive, 3 = both (GPU; the sequential host check build launches 1 then 2: its blocks do not overlap)
 __global__ void __launch_bounds__(QD_THREADS) k_band_exchange(QdBandCtl B, QdBandList L, int own0, int own1, int phase) {
@@ -103,51 +157,26 @@ __global__ void __launch_bounds__(QD_THREADS) k_band_exchange(QdBandCtl B, QdBan
   unsigned long long* mine = qd_bflags(B, B.rank);
   const unsigned long long epoch = mine[QD_BF_EPOCH_HALO] + 1ull;      // bumped by the last block to FINISH: all are resident, all read it first
   const int parity = (int)(epoch & 1ull);
+  const unsigned flag = qd_ll_flag(epoch);
   const int south = (B.rank + B.world - 1) % B.world, north = (B.rank + 1) % B.world;
   const int n = B.H * B.nlon;
-  const int per = ((n + gridDim.x - 1) / gridDim.x + 1) & ~1;           // slice length, even (16-byte stores)
+  const int per = (n + gridDim.x - 1) / gridDim.x;
   const int e0 = x * per, e1 = (e0 + per < n) ? e0 + per : n;
   // ---- push: (dir 0) rows [own0, own0+H) -> south neighbour's "from north" inbox; (dir 1) rows [own1-H, own1) -> north's "from south"
   if (phase & 1) {
     const int nbr = dir == 0 ? south : north, rdir = dir == 0 ? 1 : 0;
     const double* src = L.f[k] + (size_t)(dir == 0 ? own0 : own1 - B.H) * B.nlon;
-    double* dst = qd_binbox(B, nbr, parity, rdir, k);
-#if !QD_EMU
-    if ((((size_t)src | (size_t)dst) & 15) == 0 && (e1 & 1) == 0) {
-      const double2* s2 = reinterpret_cast<const double2*>(src);
-      double2* d2 = reinterpret_cast<double2*>(dst);
-      for (int e = e0 / 2 + threadIdx.x; e < e1 / 2; e += blockDim.x) d2[e] = s2[e];
-    } else
-#endif
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = src[e];
-#if !QD_EMU
-    __syncthreads();
-#endif
-    QD_BLOCK_LAST_ONE { qd_fence_sys(); qd_st_sys(qd_bslice_flag(B, nbr, rdir, k, x), epoch); }
+    QdLine* dst = qd_binbox(B, nbr, parity, rdir, k);
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) qd_ll_store(dst + e, src[e], flag);
   }
   // ---- receive: slice x of field k arriving on side `dir` (dir 0: from the south neighbour -> rows below mine)
   if (phase & 2) {
-#if QD_EMU
-    if (threadIdx.x == 0) qd_band_wait(B, qd_bslice_flag(B, B.rank, dir, k, x), epoch);
-#else
-    if (threadIdx.x == 0) qd_band_wait(B, qd_bslice_flag(B, B.rank, dir, k, x), epoch);
-    __syncthreads();
-#endif
     int first = dir == 0 ? own0 - B.H : own1;               // H <= rows of any rank: the block never straddles the wrap
     if (first < 0) first += B.nlat;
     if (first >= B.nlat) first -= B.nlat;
-    const double* src = qd_binbox(B, B.rank, parity, dir, k);
+    const QdLine* src = qd_binbox(B, B.rank, parity, dir, k);
     double* dst = L.f[k] + (size_t)first * B.nlon;
-#if !QD_EMU
-    if ((((size_t)src | (size_t)dst) & 15) == 0 && (e1 & 1) == 0) {
-      const double2* s2 = reinterpret_cast<const double2*>(src);
-      double2* d2 = reinterpret_cast<double2*>(dst);
-      for (int e = e0 / 2 + threadIdx.x; e < e1 / 2; e += blockDim.x) d2[e] = __ldcg(s2 + e);
-    } else
-      for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = __ldcg(src + e);
-#else
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) dst[e] = src[e];
-#endif
+    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) { double v; qd_ll_wait(B, src + e, flag, &v); dst[e] = v; }
   }
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
   if ((phase & 2) && qd_block_is_last((unsigned*)(mine + QD_BF_TICKET), nblocks)) { QD_BLOCK_LAST_ONE { mine[QD_BF_EPOCH_HALO] = epoch; } }
@@ -161,64 +190,56 @@ __global__ void k_band_allreduce(QdBandCtl B, QdBandRed R, double* scal) {
   unsigned long long* mine = qd_bflags(B, B.rank);
   const unsigned long long epoch = mine[QD_BF_EPOCH_RED] + 1ull;
   const int parity = (int)(epoch & 1ull);
-  const int t = threadIdx.x;
+  const unsigned flag = qd_ll_flag(epoch);
+  // thread (q, r): scalar q to / from rank r -- one flagged line each way, combined in rank order by thread (q, 0)
 #if QD_EMU
-  if (t != 0) return;
-  for (int q = 0; q < R.n; ++q) for (int r = 0; r < B.world; ++r) qd_bred(B, r, parity, B.rank)[q] = scal[R.id[q]];
-  qd_fence_sys();
+  for (int q = 0; q < R.n; ++q) for (int r = 0; r < B.world; ++r) qd_ll_store(qd_bline(B, r, 0, parity, B.rank, q), scal[R.id[q]], flag);
   mine[QD_BF_EPOCH_RED] = epoch;
-  for (int r = 0; r < B.world; ++r) qd_st_sys(qd_bflags(B, r) + QD_BF_RED + B.rank, epoch);
-  for (int r = 0; r < B.world; ++r) qd_band_wait(B, mine + QD_BF_RED + r, epoch);
   for (int q = 0; q < R.n; ++q) {
-    double acc = qd_bred(B, B.rank, parity, 0)[q];
-    for (int r = 1; r < B.world; ++r) { const double v = qd_bred(B, B.rank, parity, r)[q]; acc = R.is_max[q] ? (v > acc ? v : acc) : acc + v; }
+    double acc = 0.0;
+    for (int r = 0; r < B.world; ++r) {
+      double v; qd_ll_wait(B, qd_bline(B, B.rank, 0, parity, r, q), flag, &v);
+      acc = r == 0 ? v : (R.is_max[q] ? (v > acc ? v : acc) : acc + v);
+    }
     scal[R.id[q]] = acc;
   }
 #else
-  if (t < R.n) { const double v = scal[R.id[t]]; for (int r = 0; r < B.world; ++r) qd_bred(B, r, parity, B.rank)[t] = v; }
-  qd_fence_sys();
+  __shared__ double got[QD_BAND_MAXR][QD_BAND_MAXW];
+  const int q = threadIdx.x / QD_BAND_MAXW, r = threadIdx.x % QD_BAND_MAXW;
+  __syncthreads();                                                      // every thread has read the epoch word
+  if (q < R.n && r < B.world) qd_ll_store(qd_bline(B, r, 0, parity, B.rank, q), scal[R.id[q]], flag);
+  if (threadIdx.x == 0) mine[QD_BF_EPOCH_RED] = epoch;
+  if (q < R.n && r < B.world) { double v; qd_ll_wait(B, qd_bline(B, B.rank, 0, parity, r, q), flag, &v); got[q][r] = v; }
   __syncthreads();
-  if (t == 0) mine[QD_BF_EPOCH_RED] = epoch;
-  if (t < B.world) { qd_st_sys(qd_bflags(B, t) + QD_BF_RED + B.rank, epoch); qd_band_wait(B, mine + QD_BF_RED + t, epoch); }
-  __syncthreads();
-  if (t < R.n) {
-    double acc = __ldcg(qd_bred(B, B.rank, parity, 0) + t);
-    for (int r = 1; r < B.world; ++r) { const double v = __ldcg(qd_bred(B, B.rank, parity, r) + t); acc = R.is_max[t] ? (v > acc ? v : acc) : acc + v; }
-    scal[R.id[t]] = acc;
+  if (q < R.n && r == 0) {
+    double acc = got[q][0];
+    for (int k = 1; k < B.world; ++k) { const double v = got[q][k]; acc = R.is_max[q] ? (v > acc ? v : acc) : acc + v; }
+    scal[R.id[q]] = acc;
   }
 #endif
 }
 
-// ---- one scalar, published and pulled: the producer kernel's last block stores its partial into its OWN buffer, raises
-// a flag, then reads the world's partials over NVLink (peers map the buffer) and adds them in rank order.  No separate
-// all-reduce kernel between producer and consumer (the ocean's eta sum: once per CFL sub-step).  Values are double-buffered by epoch parity: a rank can publish epoch e+2 only after every peer has
-// consumed epoch e (it had to read their e+1 first).
+// ---- one scalar all-reduced in the tail of its producer kernel (the ocean's eta sum, once per CFL sub-step): the one
+// thread that holds the rank's partial PUSHES it as a flagged line into every rank's mailbox (posted stores, all in
+// flight together) and then collects the world's lines from its OWN mailbox, adding them in rank order (identical bits
+// on every rank).  One NVLink one-way flight instead of the earlier publish-locally / poll-remotely scheme, whose
+// remote polls were a round trip per rank.  Lines are double-buffered by epoch parity: a rank can publish epoch e+2
+// only after it has collected every peer's e+1, which those peers sent after collecting its e.
 QD_D void qd_band_publish(const QdBandCtl& B, double v) {
   unsigned long long* mine = qd_bflags(B, B.rank);
   const unsigned long long epoch = mine[QD_BF_EPOCH_PUB] + 1ull;
-  ((double*)(mine + QD_BF_PUB_VAL))[epoch & 1ull] = v;
-  qd_fence_sys();
+  const unsigned flag = qd_ll_flag(epoch);
+  for (int r = 0; r < B.world; ++r) qd_ll_store(qd_bline(B, r, 1, (int)(epoch & 1ull), B.rank, 0), v, flag);
   mine[QD_BF_EPOCH_PUB] = epoch;
-  qd_st_sys(mine + QD_BF_PUB_FLAG, epoch);
 }
-// called by ONE thread of a block; the rank's own epoch word already counts the publish that precedes this kernel
+// called by the SAME thread right after qd_band_publish
 QD_D double qd_band_pull_sum(const QdBandCtl& B) {
-#if QD_EMU
-  const unsigned long long epoch = *(volatile unsigned long long*)(qd_bflags(B, B.rank) + QD_BF_EPOCH_PUB);
-#else
-  const unsigned long long epoch = __ldcg(qd_bflags(B, B.rank) + QD_BF_EPOCH_PUB);
-#endif
+  const unsigned long long epoch = qd_bflags(B, B.rank)[QD_BF_EPOCH_PUB];
+  const unsigned flag = qd_ll_flag(epoch);
   double acc = 0.0;
   for (int r = 0; r < B.world; ++r) {
-    unsigned long long* fl = qd_bflags(B, r);
-    qd_band_wait(B, fl + QD_BF_PUB_FLAG, epoch);
-#if QD_EMU
-    __sync_synchronize();
-    const double v = ((volatile double*)(fl + QD_BF_PUB_VAL))[epoch & 1ull];
-#else
     double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"((double*)(fl + QD_BF_PUB_VAL) + (epoch & 1ull)) : "memory");
-#endif
+    qd_ll_wait(B, qd_bline(B, B.rank, 1, (int)(epoch & 1ull), r, 0), flag, &v);
     acc = r == 0 ? v : acc + v;
   }
   return acc;
