@@ -73,12 +73,7 @@ struct qd_ctx {
 #ifndef QD_HOST_EMU
   cudaStream_t cap_stream, cap_stream2;
   cudaGraph_t capture_graph;                        // non-null while a whole loop step is being captured
-  // side streams: small kernels that only touch rows nobody else writes (the del^4 pole tiles) run NEXT TO the main
-  // kernel of their phase instead of after it (fork / join by events; inside a capture they become parallel graph
-  // branches).  One per capture level: a stream that joined the step capture cannot join the capture of the ocean's
-  // WHILE body (level 1) as well.
-  cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-  int side_level = 0, side_enable = 1;
+
   std::map<const void*, int> red_cache;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
@@ -231,31 +226,6 @@ static void qd_drop_graphs(qd_ctx* c) {
 static qd_prof* qd_prof_of(qd_ctx* c) { return (qd_prof*)c->prof; }
 static bool qd_prof_on(qd_ctx* c) { return c->prof && qd_prof_of(c)->on; }
 #endif
-#ifndef QD_HOST_EMU
-// fork: the side stream of the current capture level starts after everything enqueued on the main stream so far and
-// becomes the launch stream; qd_side_end returns to the main stream; qd_side_join makes the main stream wait for it.
-static bool qd_side_begin(qd_ctx* c, cudaStream_t* saved) {
-  if (!c->side_enable) return false;
-  const int L = c->side_level;
-  if (!c->side[L]) {
-    if (cudaStreamCreateWithFlags(&c->side[L], cudaStreamNonBlocking) != cudaSuccess) { c->side[L] = nullptr; c->side_enable = 0; cudaGetLastError(); return false; }
-    cudaEventCreateWithFlags(&c->ev_fork[L], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_join[L], cudaEventDisableTiming);
-  }
-  if (cudaEventRecord(c->ev_fork[L], c->stream) != cudaSuccess || cudaStreamWaitEvent(c->side[L], c->ev_fork[L], 0) != cudaSuccess) { cudaGetLastError(); return false; }
-  *saved = c->stream;
-  c->stream = c->side[L];
-  return true;
-}
-static void qd_side_end(qd_ctx* c, cudaStream_t saved) { c->stream = saved; }
-static void qd_side_join(qd_ctx* c) {
-  const int L = c->side_level;
-  cudaEventRecord(c->ev_join[L], c->side[L]);
-  cudaStreamWaitEvent(c->stream, c->ev_join[L], 0);
-}
-struct QdSideLevel { qd_ctx* c; int saved; QdSideLevel(qd_ctx* c_, int l) : c(c_), saved(c_->side_level) { c->side_level = l; } ~QdSideLevel() { c->side_level = saved; } };
-#endif
-
 extern "C" int qd_profile(qd_ctx* c, int enable) {
   if (!c) return QD_E_INVALID;
 #ifndef QD_HOST_EMU
@@ -356,7 +326,6 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   c->forcing_cap = 0; c->d_forcing = nullptr; c->w_set = 0; c->prof = nullptr; c->use_graphs = 2;
 #ifndef QD_HOST_EMU
   c->cap_stream = nullptr; c->cap_stream2 = nullptr; c->capture_graph = nullptr;
-  c->side_enable = getenv("QD_NO_SIDE") ? 0 : 1;                 // tuning / A-B switch
 #endif
   const size_t nrows = (size_t)(QD_R_COUNT + 7 * QD_NUSER_ROWS) * nlat;   // one table PER MEMBER (K4, sponge, polar rows follow the member's parameters)
   // a failed allocation releases everything allocated so far (qd_destroy frees null pointers harmlessly)
@@ -467,7 +436,6 @@ extern "C" int qd_destroy(qd_ctx* c) {
   qd_drop_graphs(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   if (c->cap_stream2) cudaStreamDestroy(c->cap_stream2);
-  for (int L = 0; L < 2; ++L) if (c->side[L]) { cudaStreamDestroy(c->side[L]); cudaEventDestroy(c->ev_fork[L]); cudaEventDestroy(c->ev_join[L]); }
 #endif
   delete c;
   return QD_OK;
@@ -708,6 +676,11 @@ static int band_prep_v(qd_ctx* c, const std::vector<BIn>& ins, const std::vector
     if (in.r > H) return qd_fail(c, QD_E_STATE, "latitude bands: halo width smaller than a stencil radius", cudaSuccess);
     ext = std::min(ext, c->band_valid[id] - in.r);
   }
+  if (c->band.rank == 0) if (const char* tr = getenv("QD_BAND_TRACE")) if (atoi(tr) >= 2) {
+    fprintf(stderr, "[band] prep ext %d:", ext);
+    for (const BIn& in : ins) { const int id = band_fid(c, in.p); if (id >= 0) fprintf(stderr, " %d(v%d r%d)", id, c->band_valid[id] > 99 ? 99 : c->band_valid[id], in.r); }
+    fprintf(stderr, "\n");
+  }
   if (ext < 0) return qd_fail(c, QD_E_STATE, "latitude bands: negative compute extent", cudaSuccess);
   band_set_ext(c, ext);
   for (const void* o : outs) { const int id = band_fid(c, o); if (id >= 0) c->band_valid[id] = ext; }
@@ -750,8 +723,8 @@ extern "C" int qd_band_init(qd_ctx* c, int rank, int world, int halo_rows) {
   B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * sizeof(QdLine));      // flagged lines, 16 bytes per element
   B.off_sflag = take((size_t)2 * QD_BAND_MAXX * QD_BAND_GX * 8);
   B.off_red = take((size_t)2 * 2 * QD_BAND_MAXW * QD_BAND_MAXR * sizeof(QdLine));     // flagged lines: [set][parity][src][slot]
-  B.off_hist = take((size_t)2 * QD_BAND_MAXW * QD_SEL_MAXBINS * 4);
-  B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * 8);
+  B.off_hist = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_MAXBINS / 2) * sizeof(QdLine));
+  B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * sizeof(QdLine));
 #ifdef QD_HOST_EMU
   B.off_emu = take((size_t)QD_BAND_MAXW * ((size_t)c->ncell + 1) * 8);
 #else
@@ -912,15 +885,9 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
         H.ja = ja; H.jb = jb;
         const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
         const int nwarps = nstrips * ((jb - ja + R - 1) / R);
-        // the rows next to a pole (tile kernel) on the side stream, next to the streaming kernel
-        cudaStream_t saved = nullptr;
-        const bool pole = s0 < ja || jb < s1;
-        const bool side = pole && qd_side_begin(c, &saved);
         if (s0 < ja) { H.row0 = s0; H.row1 = ja; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((ja - s0 + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
         if (jb < s1) { H.row0 = jb; H.row1 = s1; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((s1 - jb + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
-        if (side) qd_side_end(c, saved);
         QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
-        if (side) qd_side_join(c);
         continue;
       }
 #endif
@@ -939,13 +906,8 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
     const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
     const int nwarps = nstrips * ((H.jb - H.ja + R - 1) / R);
     H.tj_lo = 1; H.tj_skip = ntj8 - 3;
-    // the three tile rows that touch a pole on the side stream, next to the streaming kernel (disjoint output rows)
-    cudaStream_t saved = nullptr;
-    const bool side = qd_side_begin(c, &saved);
     QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * 3, c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
-    if (side) qd_side_end(c, saved);
     QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
-    if (side) qd_side_join(c);
     return QD_OK;
   }
 #endif
@@ -1771,9 +1733,8 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
 // ------------------------------------------------------------------------------ ocean step
 // One CFL sub-step body (ocean.py:305-444).  Launched either from a host loop (stream mode) or captured
 // once as the body of a CUDA-graph WHILE node (graph mode); the sub-step index is read from device memory.
-static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap) {
+static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap, bool first_in_group = true) {
 #ifndef QD_HOST_EMU
-  QdSideLevel side_level(c, 1);
   const int fused_rows = ocean_fused_rows(c, cfg, do_hyper, do_shap);
   c->ocean_fused = fused_rows > 0;
   if (c->ocean_fused) return ocean_substep_fused(c, cfg, inject, fused_rows);
@@ -1784,7 +1745,7 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
   Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
   Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
-  if (c->band_on) {   // loop-carried fields start every sub-step from "own rows only": the body replays unchanged (WHILE node)
+  if (c->band_on && first_in_group) {   // loop-carried fields start every GROUP of sub-steps from "own rows only": the body replays unchanged (WHILE node)
     for (int id : {(int)QD_F_UO, (int)QD_F_VO, (int)QD_F_ETA, (int)QD_F_SST, (int)QD_F_TS, (int)QD_F_X2, (int)QD_F_X3, (int)QD_F_X4,
                    (int)QD_F_X5, (int)QD_F_X6, (int)QD_F_X7, (int)QD_F_X8, (int)QD_F_X9}) c->band_valid[id] = 0;
     // ONE exchange per sub-step: everything the body's stencils read with a halo (eta: momentum and del^4; currents: del^4,
@@ -1838,8 +1799,11 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS); Sb.eta = F(c, QD_F_ETA);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
-  BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.ts_atm, 0}, {Sb.eta, 0}),
-     BL(Sb.sst, Sb.uo, Sb.vo, Sb.ts_atm, Sb.eta));
+  // T_s is only WRITTEN here (SST injection on a member's last sub-step, also on whatever halo rows the launch covers --
+  // the neighbour computes the same values for them); nothing inside the loop reads it, and ocean_core resets its valid
+  // width after the loop, so it constrains neither the compute region nor is it marked valid
+  BP(c, BL({Sb.tb, 2}, {Sb.ub, 1}, {Sb.vb, 1}, {Sb.qnet, 0}, {Sb.land, 0}, {Sb.ice, 0}, {Sb.sst, 0}, {Sb.eta, 0}),
+     BL(Sb.sst, Sb.uo, Sb.vo, Sb.eta));
 #ifndef QD_HOST_EMU
   if (pairs) {                                                 // two cells per thread, lazy nan_to_num (qd_ocean.cuh)
     QD_KG(c, k_ocean_sst_finish2, dim3((c->geo.ncomp / 2 + QD_THREADS - 1) / QD_THREADS, c->batch), dim3(QD_THREADS), c->geo, Sb, sc);
@@ -1847,6 +1811,37 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   }
 #endif
   QD_K(c, k_ocean_sst_finish, c->geo, Sb, sc);
+  return QD_OK;
+}
+
+// Latitude bands: a sub-step consumes 8 halo rows (eta gradient 1 + del^4 4 + divergence 1 + SST Laplacian 2), so ONE
+// exchange of H rows serves H / 8 consecutive sub-steps (the first one computes on its own rows widened by H - 8 rows,
+// redundantly on both sides of a cut): half as many neighbour round trips per ocean step at H = 16.  The body of the
+// WHILE node is then a GROUP of sub-steps; members whose n_sub is not a multiple of the group size find qd_sub_done()
+// true in the trailing sub-steps of their last group (the kernels exit at once).  The valid-halo tracker (band_prep)
+// keeps this correct whatever the group size: a kernel whose inputs are no longer valid triggers an exchange itself.
+static int ocean_group_size(qd_ctx* c, bool do_shap) {
+  if (!c->band_on || do_shap) return 1;
+  // Measured on 2 B200s (profiles/README.md): 6.0 instead of 7.85 exchanges per step, but the step is 1 % SLOWER (inside
+  // the step graph an exchange costs less than the extra halo rows, the ice-mask kernel and the no-op tail of a group),
+  // so the default group is ONE sub-step; QD_OCEAN_GROUP=2..4 opts in.
+  if (const char* ov = getenv("QD_OCEAN_GROUP")) return std::max(1, std::min(std::min(4, c->band.H / 8), atoi(ov)));
+  return 1;
+}
+#ifdef QD_HOST_EMU
+typedef unsigned long long qd_cond_handle_t;
+#else
+typedef cudaGraphConditionalHandle qd_cond_handle_t;
+#endif
+// one group: K x (body, advance).  raw: inside a capture of the WHILE body (launch not counted / profiled, handle live)
+static int ocean_substep_group(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap, bool raw, qd_cond_handle_t handle) {
+  const int K = ocean_group_size(c, do_shap);
+  for (int q = 0; q < K; ++q) {
+    int rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap, q == 0);
+    if (rc) return rc;
+    if (raw) QD_LAUNCH(k_ocean_sub_advance, dim3(1), dim3(32), c->stream, c->geo, c->d_sub_ctr, handle, 1);
+    else QD_KG(c, k_ocean_sub_advance, dim3(1), dim3(32), c->geo, c->d_sub_ctr, handle, 0);
+  }
   return QD_OK;
 }
 
@@ -1878,8 +1873,7 @@ static cudaGraphExec_t ocean_while_graph(qd_ctx* c, const qd_step_cfg_t* cfg, in
     cudaGraph_t body = np.conditional.phGraph_out[0];
     if (cudaStreamBeginCaptureToGraph(c->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) != cudaSuccess) break;
     c->stream = c->cap_stream;
-    int rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap);
-    QD_LAUNCH(k_ocean_sub_advance, dim3(1), dim3(32), c->stream, c->geo, c->d_sub_ctr, handle, 1);
+    int rc = ocean_substep_group(c, cfg, inject, do_hyper, do_shap, true, handle);
     c->stream = saved;
     cudaGraph_t dummy = nullptr;
     if (cudaStreamEndCapture(c->cap_stream, &dummy) != cudaSuccess || rc != QD_OK) break;
@@ -1912,10 +1906,20 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
   QD_KR(c, k_ocean_prep, c->geo, P0);
   { int rcb = band_allreduce(c, {QD_S_MAX_UOCEAN, QD_S_MAX_VA}, true); if (rcb) return rcb; }
   if (c->band_on) QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
-  { int rcb = band_hint(c, {QD_F_X0, QD_F_X1}); if (rcb) return rcb; }      // wind stress: constant over the sub-steps, exchanged once
-  QD_CHECK_LAUNCH(c);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);
   const bool do_shap = (cfg->oc_shapiro_n > 0) && (cfg->oc_shapiro_every > 0) && (c->oc_counter % cfg->oc_shapiro_every == 0);
+  if (c->band_on && inject && ocean_group_size(c, do_shap) > 1) {
+    // groups of sub-steps per exchange: the closing kernel of a group's first sub-steps also runs on halo rows, so
+    // everything it reads there must be valid -- the wind stress, Q_net (constant over the sub-steps: ONE
+    // exchange per step) and the ice mask, rebuilt on the halo rows from the exchanged ice thickness exactly as
+    // k_tail built it on the rank's own rows (run_simulation.py:2201: ice = h_ice > 0)
+    { int rcb = band_hint(c, {QD_F_X0, QD_F_X1, QD_F_QNET, QD_F_HICE}); if (rcb) return rcb; }
+    BP(c, BL({F(c, QD_F_HICE), 0}), BL(M(c, QD_M_ICE)));
+    QD_K(c, k_ice_mask, c->geo, F(c, QD_F_HICE), M(c, QD_M_ICE));
+  } else {
+    int rcb = band_hint(c, {QD_F_X0, QD_F_X1}); if (rcb) return rcb;      // wind stress: constant over the sub-steps, exchanged once
+  }
+  QD_CHECK_LAUNCH(c);
   int rc;
   bool launched = false;
 #ifndef QD_HOST_EMU
@@ -1950,8 +1954,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
     QD_CUDA(c, cudaStreamBeginCaptureToGraph(c->cap_stream2, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
     cudaStream_t outer = c->stream;
     c->stream = c->cap_stream2;
-    rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap);
-    QD_LAUNCH(k_ocean_sub_advance, dim3(1), dim3(32), c->stream, c->geo, c->d_sub_ctr, handle, 1);
+    rc = ocean_substep_group(c, cfg, inject, do_hyper, do_shap, true, handle);
     c->stream = outer;
     cudaGraph_t dummy = nullptr;
     cudaError_t ee = cudaStreamEndCapture(c->cap_stream2, &dummy);
@@ -1976,9 +1979,8 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
     int nmax = 1;
     for (int b = 0; b < c->batch; ++b) nmax = std::max(nmax, (int)s[(size_t)b * QD_S_COUNT + QD_S_NSUB]);
     c->last_nsub_max = nmax;
-    for (int sub = 0; sub < nmax; ++sub) {
-      rc = ocean_substep_body(c, cfg, inject, do_hyper, do_shap); if (rc) return rc;
-      QD_KG(c, k_ocean_sub_advance, dim3(1), dim3(32), c->geo, c->d_sub_ctr, 0, 0);
+    for (int sub = 0; sub < nmax; sub += ocean_group_size(c, do_shap)) {
+      rc = ocean_substep_group(c, cfg, inject, do_hyper, do_shap, false, 0); if (rc) return rc;
     }
   }
   QdOcPolarArgs Po; memset(&Po, 0, sizeof(Po));

@@ -47,12 +47,9 @@ QD_HD unsigned long long* qd_bflags(const QdBandCtl& B, int r) { return (unsigne
 QD_HD double* qd_bred(const QdBandCtl& B, int r, int parity, int src) {
   return (double*)(B.peer[r] + B.off_red) + ((size_t)parity * QD_BAND_MAXW + src) * QD_BAND_MAXR;
 }
-QD_HD unsigned* qd_bhist(const QdBandCtl& B, int r, int parity, int src) {
-  return (unsigned*)(B.peer[r] + B.off_hist) + ((size_t)parity * QD_BAND_MAXW + src) * QD_SEL_MAXBINS;
-}
-QD_HD unsigned long long* qd_blist(const QdBandCtl& B, int r, int parity, int src) {   // [0] count, [1] mingt, [2..] keys
-  return (unsigned long long*)(B.peer[r] + B.off_list) + ((size_t)parity * QD_BAND_MAXW + src) * (QD_SEL_CAP + 2);
-}
+struct QdLine;
+QD_HD QdLine* qd_bhist(const QdBandCtl& B, int r, int parity, int src);      // QD_SEL_MAXBINS / 2 lines (two bins each)
+QD_HD QdLine* qd_blist(const QdBandCtl& B, int r, int parity, int src);      // [0] count, [1] mingt, [2..] keys: one line each
 
 #if QD_EMU
 static inline void qd_fence_sys() { __sync_synchronize(); }
@@ -117,6 +114,17 @@ __device__ __forceinline__ bool qd_ll_load(const QdLine* l, unsigned flag, doubl
   return true;
 }
 #endif
+#if !QD_EMU
+// the same line carrying two 32-bit words (histogram bins) or one 64-bit key
+__device__ __forceinline__ void qd_ll_store2(QdLine* l, unsigned a, unsigned b, unsigned flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(l), "r"(a), "r"(flag), "r"(b), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool qd_ll_load2(const QdLine* l, unsigned flag, unsigned* a, unsigned* b) {
+  unsigned fa, fb;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(*a), "=r"(fa), "=r"(*b), "=r"(fb) : "l"(l) : "memory");
+  return fa == flag && fb == flag;
+}
+#endif
 // spin until the line carries `flag`; false (and the error word) when the bound is hit
 QD_D bool qd_ll_wait(const QdBandCtl& B, const QdLine* l, unsigned flag, double* v) {
   if (qd_bflags(B, B.rank)[QD_BF_ERR] != 0ull) { *v = 0.0; return false; }
@@ -131,6 +139,21 @@ QD_D bool qd_ll_wait(const QdBandCtl& B, const QdLine* l, unsigned flag, double*
   return false;
 }
 QD_HD unsigned qd_ll_flag(unsigned long long epoch) { const unsigned f = (unsigned)epoch; return f ? f : 0x80000000u; }
+#if !QD_EMU
+__device__ __forceinline__ bool qd_ll_wait2(const QdBandCtl& B, const QdLine* l, unsigned flag, unsigned* a, unsigned* b) {
+  if (qd_bflags(B, B.rank)[QD_BF_ERR] != 0ull) { *a = *b = 0u; return false; }
+  for (unsigned n = 0; n < QD_BAND_SPIN; ++n) if (qd_ll_load2(l, flag, a, b)) return true;
+  qd_bflags(B, B.rank)[QD_BF_ERR] = 1ull;
+  *a = *b = 0u;
+  return false;
+}
+#endif
+QD_HD QdLine* qd_bhist(const QdBandCtl& B, int r, int parity, int src) {
+  return (QdLine*)(B.peer[r] + B.off_hist) + ((size_t)parity * QD_BAND_MAXW + src) * (QD_SEL_MAXBINS / 2);
+}
+QD_HD QdLine* qd_blist(const QdBandCtl& B, int r, int parity, int src) {
+  return (QdLine*)(B.peer[r] + B.off_list) + ((size_t)parity * QD_BAND_MAXW + src) * (QD_SEL_CAP + 2);
+}
 // scalar mailboxes: line [set][parity][src][slot]; set 0 = k_band_allreduce, set 1 = publish / pull
 QD_HD QdLine* qd_bline(const QdBandCtl& B, int r, int set, int parity, int src, int slot) {
   return (QdLine*)(B.peer[r] + B.off_red) + (((size_t)set * 2 + parity) * QD_BAND_MAXW + src) * QD_BAND_MAXR + slot;
@@ -253,27 +276,26 @@ QD_D double qd_band_pull_sum(const QdBandCtl& B) {
 // back when the kernel ends.  Blocks 0..world-1 each serve one peer, block 0 combines.
 //
 // gh[0..nb) <- sum over ranks of their gh (element-wise, exact integers).  Call after a grid.sync (gh complete);
-// the caller grid.syncs afterwards.
+// the caller grid.syncs afterwards.  Flagged lines of two bins each: block 0 posts this rank's histogram into every
+// peer's mailbox, then adds the world's lines out of its own mailbox as they land.
 __device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsigned* gh, int nb, unsigned long long epoch) {
-  unsigned long long* mine = qd_bflags(B, B.rank);
   const int parity = (int)(epoch & 1ull);
-  for (int r = blockIdx.x; r < B.world; r += gridDim.x) {               // nb is a multiple of 4, boxes are 256-byte aligned
-    uint4* dst = reinterpret_cast<uint4*>(qd_bhist(B, r, parity, B.rank));
-    const uint4* src = reinterpret_cast<const uint4*>(gh);
-    for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) dst[k] = __ldcg(src + k);
-    __syncthreads();
-    if (threadIdx.x == 0) { qd_fence_sys(); qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, epoch); }
+  const unsigned flag = qd_ll_flag(epoch);
+  if (blockIdx.x != 0) return;                                          // block 0 posts to every peer and combines: gh is only overwritten
+  for (int r = 0; r < B.world; ++r) {                                   // after this block has read it for all of them (nb is even)
+    QdLine* dst = qd_bhist(B, r, parity, B.rank);
+    const uint2* src = reinterpret_cast<const uint2*>(gh);
+    for (int k = threadIdx.x; k < nb / 2; k += blockDim.x) { const uint2 v = __ldcg(src + k); qd_ll_store2(dst + k, v.x, v.y, flag); }
   }
-  if (blockIdx.x != 0) return;
-  if (threadIdx.x < B.world) qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch);
   __syncthreads();
-  for (int k = threadIdx.x; k < nb / 4; k += blockDim.x) {
-    uint4 s = make_uint4(0u, 0u, 0u, 0u);
+  for (int k = threadIdx.x; k < nb / 2; k += blockDim.x) {
+    unsigned sx = 0u, sy = 0u;
     for (int r = 0; r < B.world; ++r) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(qd_bhist(B, B.rank, parity, r)) + k);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      unsigned a, c;
+      qd_ll_wait2(B, qd_bhist(B, B.rank, parity, r) + k, flag, &a, &c);
+      sx += a; sy += c;
     }
-    reinterpret_cast<uint4*>(gh)[k] = s;
+    reinterpret_cast<uint2*>(gh)[k] = make_uint2(sx, sy);
   }
   __threadfence();
 }
@@ -282,28 +304,30 @@ __device__ __forceinline__ void qd_band_hist_allreduce(const QdBandCtl& B, unsig
 // skeys[0..m) (shared memory, unsorted) and the global mingt; other blocks return -1.
 __device__ __forceinline__ int qd_band_list_allgather(const QdBandCtl& B, const unsigned long long* lst, unsigned cnt, unsigned long long mingt_local,
                                                       unsigned long long* skeys, unsigned long long* mingt_out, unsigned long long epoch) {
-  unsigned long long* mine = qd_bflags(B, B.rank);
   const int parity = (int)(epoch & 1ull);
+  const unsigned flag = qd_ll_flag(epoch);
   if (cnt > QD_SEL_CAP) cnt = QD_SEL_CAP;
   for (int r = blockIdx.x; r < B.world; r += gridDim.x) {
-    unsigned long long* dst = qd_blist(B, r, parity, B.rank);
-    if (threadIdx.x == 0) { dst[0] = cnt; dst[1] = mingt_local; }
-    for (int k = threadIdx.x; k < (int)cnt; k += blockDim.x) dst[2 + k] = __ldcg(lst + k);
-    __syncthreads();
-    if (threadIdx.x == 0) { qd_fence_sys(); qd_st_sys(qd_bflags(B, r) + QD_BF_SEL + B.rank, epoch); }
+    QdLine* dst = qd_blist(B, r, parity, B.rank);
+    if (threadIdx.x == 0) { qd_ll_store2(dst, cnt, 0u, flag); qd_ll_store2(dst + 1, (unsigned)mingt_local, (unsigned)(mingt_local >> 32), flag); }
+    for (int k = threadIdx.x; k < (int)cnt; k += blockDim.x) { const unsigned long long key = __ldcg(lst + k); qd_ll_store2(dst + 2 + k, (unsigned)key, (unsigned)(key >> 32), flag); }
   }
   if (blockIdx.x != 0) return -1;
-  if (threadIdx.x < B.world) qd_band_wait(B, mine + QD_BF_SEL + threadIdx.x, epoch);
-  __syncthreads();
   int m = 0;
   unsigned long long mg = ~0ull;
   for (int r = 0; r < B.world; ++r) {
-    const unsigned long long* src = qd_blist(B, B.rank, parity, r);
-    const int n = (int)__ldcg(src);
-    const unsigned long long g2 = __ldcg(src + 1);
+    const QdLine* src = qd_blist(B, B.rank, parity, r);
+    unsigned n, z, glo, ghi;
+    qd_ll_wait2(B, src, flag, &n, &z);
+    qd_ll_wait2(B, src + 1, flag, &glo, &ghi);
+    const unsigned long long g2 = ((unsigned long long)ghi << 32) | glo;
     if (g2 < mg) mg = g2;
-    for (int k = threadIdx.x; k < n && m + k < QD_SEL_CAP; k += blockDim.x) skeys[m + k] = __ldcg(src + 2 + k);
-    m += n;
+    for (int k = threadIdx.x; k < (int)n && m + k < QD_SEL_CAP; k += blockDim.x) {
+      unsigned lo, hi;
+      qd_ll_wait2(B, src + 2 + k, flag, &lo, &hi);
+      skeys[m + k] = ((unsigned long long)hi << 32) | lo;
+    }
+    m += (int)n;
   }
   __syncthreads();
   *mingt_out = mg;

@@ -80,6 +80,14 @@ __global__ void k_ocean_nsub(QdGeo g, double dt, int* sub_ctr) {
   qd_ocean_nsub_member(g, b, dt);
 }
 
+// ice mask from the ice thickness (run_simulation.py:2201) on the rows of the launch geometry: latitude bands rebuild it
+// on their halo rows after exchanging h_ice (masks themselves are never exchanged)
+__global__ void __launch_bounds__(QD_THREADS) k_ice_mask(QdGeo g, const double* hice, uint8_t* ice) {
+  QD_CELL_PROLOGUE(g)
+  if (!active) return;
+  ice[off + idx] = (uint8_t)(hice[off + idx] > 0.0);
+}
+
 // Momentum + land zeroing + polar sponge (ocean.py:306-336): A -> B.
 struct QdOcMomArgs {
   const double *eta, *uo, *vo, *taux, *tauy;
@@ -597,16 +605,18 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarAr
 #if !QD_EMU
 __global__ void k_ocean_sub_advance(QdGeo g, int* sub_ctr, cudaGraphConditionalHandle handle, int use_handle) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  const int s = *sub_ctr + 1;
-  *sub_ctr = s;
   int nmax = 1;
   for (int b = 0; b < g.batch; ++b) { const int n = (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB]; if (n > nmax) nmax = n; }
+  const int s = min(*sub_ctr + 1, nmax);                      // saturates: a group of sub-steps may run past the last one (no-ops)
+  *sub_ctr = s;
   if (use_handle) cudaGraphSetConditional(handle, s < nmax ? 1u : 0u);
 }
 #else
 __global__ void k_ocean_sub_advance(QdGeo g, int* sub_ctr, unsigned long long handle, int use_handle) {
-  (void)g; (void)handle; (void)use_handle;
+  (void)handle; (void)use_handle;
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  *sub_ctr = *sub_ctr + 1;
+  int nmax = 1;
+  for (int b = 0; b < g.batch; ++b) { const int n = (int)g.scal[(size_t)b * QD_S_COUNT + QD_S_NSUB]; if (n > nmax) nmax = n; }
+  *sub_ctr = *sub_ctr + 1 < nmax ? *sub_ctr + 1 : nmax;
 }
 #endif

@@ -13,6 +13,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NLAT, NLON, NSTEPS, DT = 49, 72, 7, 600
+HALO = 8
 FIELDS = ("u", "v", "h", "ts", "q", "cloud", "hice", "uo", "vo", "eta", "sst", "precip", "albedo", "wland", "ssnow")
 
 
@@ -25,7 +26,14 @@ def _sim(lib, band=None):
     return Simulation(NLAT, NLON, topo, p, dt=DT, lib=lib, loop_with_albedo=True, band=band)
 
 
-def _run(rank, world, port, out):
+def _run(rank, world, port, out, shape=None, halo=None, dt=None):
+    global NLAT, NLON, HALO, DT
+    if dt is not None:
+        DT = dt
+    if shape is not None:
+        NLAT, NLON = shape
+    if halo is not None:
+        HALO = halo
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from hostcheck import library
@@ -34,14 +42,14 @@ def _run(rank, world, port, out):
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
         dist.init_process_group("gloo", rank=rank, world_size=world)
-        band = (rank, world, 8)
+        band = (rank, world, HALO)
     sim = _sim(library(), band)
     sim.step(NSTEPS)
     full = {k: sim.engine.gather_rows(k) for k in FIELDS}
     nsub = sim.engine.scalars()[0]
     err = sim.engine.band_info()[3]
     if rank == 0:
-        np.savez(out, err=np.array(err), **full)
+        np.savez(out, err=np.array(err), nsub=np.array(float(sim.engine.last_nsub()[0])), **full)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -55,6 +63,30 @@ def test_latitude_bands_match_single_process(tmp_path, world):
     mp.spawn(_run, args=(world, port, many), nprocs=world, join=True)
     a, b = np.load(one), np.load(many)
     assert int(b["err"]) == 0
+    for k in FIELDS:
+        scale = max(float(np.max(np.abs(a[k]))), 1e-300)
+        err = float(np.max(np.abs(a[k] - b[k]))) / scale
+        assert err < 1e-10, (k, err)
+
+
+def test_latitude_bands_two_substeps_per_exchange(tmp_path):
+    """Halo of 16 rows: one exchange serves a GROUP of two ocean sub-steps (8 halo rows each; qd_api.cu:
+    ocean_group_size); dt chosen so that n_sub > 1 and odd / even counts both occur over the run."""
+    global NLAT, NLON, HALO, DT
+    one, many = str(tmp_path / "one.npz"), str(tmp_path / "w2.npz")
+    saved = (NLAT, NLON, HALO, DT)
+    shape = (97, 96)
+    os.environ["QD_OCEAN_GROUP"] = "2"                    # opt-in (the default is one sub-step per exchange); inherited by the spawned ranks
+    try:
+        _run(0, 1, 0, one, shape, 16, 1500)
+        port = 29700 + (os.getpid() % 1500) + 7
+        mp.spawn(_run, args=(2, port, many, shape, 16, 1500), nprocs=2, join=True)
+    finally:
+        NLAT, NLON, HALO, DT = saved
+        os.environ.pop("QD_OCEAN_GROUP", None)
+    a, b = np.load(one), np.load(many)
+    assert int(b["err"]) == 0
+    assert float(a["nsub"]) >= 2.0, a["nsub"]
     for k in FIELDS:
         scale = max(float(np.max(np.abs(a[k]))), 1e-300)
         err = float(np.max(np.abs(a[k] - b[k]))) / scale
