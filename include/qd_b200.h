@@ -225,6 +225,10 @@ int  qd_divergence(qd_ctx* ctx, const double* u_dev, const double* v_dev, double
 int  qd_vorticity(qd_ctx* ctx, const double* u_dev, const double* v_dev, double* out_dev);
 int  qd_median_pos(qd_ctx* ctx, const double* in_dev, double empty_value, double* out_host /* [B] */); /* sync */
 int  qd_wsum(qd_ctx* ctx, const double* in_dev, double* out_host /* [B] sum(x*w) */);                    /* sync */
+/* Exact-median kernel launches and first-digit speculation hits (csrc/qd_select.cuh) per call site since qd_create:
+ * out[site][0] = launches (x members), out[site][1] = hits; sites: 0 positive precipitation part, 1 precipitation,
+ * 2 P_cond, 3 qd_median_pos. */
+int  qd_median_stats(qd_ctx* ctx, long long* out /* [4][2] */);                                            /* sync */
 /* device row tables for the operator calls above */
 const double* qd_row_dev(qd_ctx* ctx, int row_id);
 /* upload an arbitrary [nlat] row table into one of 6 user row slots (0/1 are used by the *_host operator

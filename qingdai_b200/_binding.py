@@ -87,6 +87,7 @@ PROTOTYPES = {
     "qd_vorticity": (_I, [_P, _P, _P, _P]),
     "qd_median_pos": (_I, [_P, _P, _D, _P]),
     "qd_wsum": (_I, [_P, _P, _P]),
+    "qd_median_stats": (_I, [_P, _P]),
     "qd_minmax": (_I, [_P, _P, _P]),
     "qd_math_check": (_I, [_P, _P, C.c_longlong, _P, _I]),
     "qd_band_exchange_bench": (_I, [_P, _I, _I, _P]),

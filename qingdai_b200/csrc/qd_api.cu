@@ -51,6 +51,7 @@ struct qd_route {
   double *d_buffer = nullptr, *d_mass = nullptr, *d_after = nullptr, *d_out = nullptr;
 };
 
+#define QD_SEL_SITES 4          // call sites of the exact median that remember their last first digit (op_median)
 struct qd_ctx {
   int nlat, nlon, ncell, batch, device, nblk, cur_nblk, red_blk, h4_stream, polar_advances_step, spec_attr_set, g2_fused;
   cudaStream_t stream;
@@ -60,7 +61,7 @@ struct qd_ctx {
   double* fields; uint8_t* masks;
   double* d_part[QD_NPART]; unsigned* d_ticket;
   unsigned* d_hist; unsigned long long* d_mingt; int sel_gx;
-  unsigned long long* d_sel_list; unsigned* d_sel_cnt; int* d_sel_more;
+  unsigned long long* d_sel_list; unsigned* d_sel_cnt; int* d_sel_more; unsigned* d_sel_spec = nullptr;
   qd_forcing_t* d_forcing; int forcing_cap; int* d_step_idx; double* d_hcos;
   double *d_twid, *d_spec_coef, *d_spec_out;
   double* d_stage[5];
@@ -337,7 +338,10 @@ extern "C" int qd_create(int nlat, int nlon, int batch, int device, double a, do
   QD_ALLOC(c->d_udiv, (size_t)batch * QD_U_COUNT * sizeof(QdRcp));
   for (int k = 0; k < QD_NPART; ++k) QD_ALLOC(c->d_part[k], (size_t)batch * c->nblk * 8);
   QD_ALLOC(c->d_ticket, (size_t)batch * 8 * sizeof(unsigned));
-  QD_ALLOC(c->d_hist, (size_t)QD_SEL_PASSES * batch * QD_SEL_MAXBINS * sizeof(unsigned));
+  QD_ALLOC(c->d_hist, (size_t)(QD_SEL_PASSES + 1) * batch * QD_SEL_MAXBINS * sizeof(unsigned));      // + the speculative second-digit slot (qd_select.cuh)
+  QD_ALLOC(c->d_sel_spec, ((size_t)QD_SEL_SITES * batch + 2 * QD_SEL_SITES) * sizeof(unsigned));    // remembered digits, then (calls, hits) per site
+  cudaMemset(c->d_sel_spec, 0xff, (size_t)QD_SEL_SITES * batch * sizeof(unsigned));                 // no remembered digit yet
+  cudaMemset(c->d_sel_spec + (size_t)QD_SEL_SITES * batch, 0, 2 * QD_SEL_SITES * sizeof(unsigned));
   QD_ALLOC(c->d_mingt, (size_t)batch * sizeof(unsigned long long));
   cudaMemset(c->d_mingt, 0xff, (size_t)batch * sizeof(unsigned long long));
   QD_ALLOC(c->d_sel_list, (size_t)batch * QD_SEL_CAP * sizeof(unsigned long long));
@@ -422,7 +426,7 @@ extern "C" int qd_destroy(qd_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rows); cudaFree(c->d_cols); cudaFree(c->d_prm); cudaFree(c->d_scal); cudaFree(c->d_udiv);
   for (int k = 0; k < QD_NPART; ++k) cudaFree(c->d_part[k]);
-  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_sel_list); cudaFree(c->d_sel_cnt); cudaFree(c->d_sel_more); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
+  cudaFree(c->d_ticket); cudaFree(c->d_hist); cudaFree(c->d_mingt); cudaFree(c->d_sel_list); cudaFree(c->d_sel_cnt); cudaFree(c->d_sel_more); cudaFree(c->d_sel_spec); cudaFree(c->d_step_idx); cudaFree(c->d_sub_ctr); cudaFree(c->d_hcos);
   cudaFree(c->d_twid); cudaFree(c->d_spec_coef); cudaFree(c->d_spec_out); cudaFree(c->d_forcing);
   for (int k = 0; k < 5; ++k) cudaFree(c->d_stage[k]);
   qd_route_free(c->route);
@@ -723,7 +727,7 @@ extern "C" int qd_band_init(qd_ctx* c, int rank, int world, int halo_rows) {
   B.off_inbox = take((size_t)2 * 2 * QD_BAND_MAXX * H * c->nlon * sizeof(QdLine));      // flagged lines, 16 bytes per element
   B.off_sflag = take((size_t)2 * QD_BAND_MAXX * QD_BAND_GX * 8);
   B.off_red = take((size_t)2 * 2 * QD_BAND_MAXW * QD_BAND_MAXR * sizeof(QdLine));     // flagged lines: [set][parity][src][slot]
-  B.off_hist = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_MAXBINS / 2) * sizeof(QdLine));
+  B.off_hist = take((size_t)2 * QD_BAND_MAXW * QD_SEL_MAXBINS * sizeof(QdLine));       // two histograms (first digit + speculative second) of two bins per line
   B.off_list = take((size_t)2 * QD_BAND_MAXW * (QD_SEL_CAP + 2) * sizeof(QdLine));
 #ifdef QD_HOST_EMU
   B.off_emu = take((size_t)QD_BAND_MAXW * ((size_t)c->ncell + 1) * 8);
@@ -1090,7 +1094,9 @@ static int op_bandstop(qd_ctx* c, double* fld, double cutoff, double damp) {
   return QD_OK;
 }
 // exact median of positives of x -> dst[b*stride] (and count -> cnt[b*stride])
-static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst, double* cnt, int stride) {
+// site: which of the loop's medians this is (0 positive part of the diagnosed precipitation, 1 precipitation, 2 P_cond,
+// 3 the operator API) -- every site remembers the first digit of its last result for the kernel's speculation
+static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst, double* cnt, int stride, int site) {
   QdSelOut out; out.value = dst; out.count = cnt; out.stride = stride; out.empty_value = empty_value;
 #ifdef QD_HOST_EMU
   qd_select_host(c->geo, x, out, c->band);
@@ -1098,7 +1104,9 @@ static int op_median(qd_ctx* c, const double* x, double empty_value, double* dst
 #else
   // the kernel leaves hist / list counter / mingt reset for the next launch (no memset nodes in the step graph)
   QdGeo geo = c->geo;
-  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_sel_list, (void*)&c->d_sel_cnt, (void*)&c->d_mingt, (void*)&c->d_sel_more, (void*)&out, (void*)&c->band};
+  unsigned* spec = (c->d_sel_spec && !getenv("QD_NO_SELSPEC")) ? c->d_sel_spec + (size_t)site * c->batch : nullptr;
+  unsigned* spec_stat = c->d_sel_spec ? c->d_sel_spec + (size_t)QD_SEL_SITES * c->batch + 2 * site : nullptr;
+  void* args[] = {(void*)&geo, (void*)&x, (void*)&c->d_hist, (void*)&c->d_sel_list, (void*)&c->d_sel_cnt, (void*)&c->d_mingt, (void*)&c->d_sel_more, (void*)&out, (void*)&c->band, (void*)&spec, (void*)&spec_stat};
   const int pi = qd_prof_begin(c, "k_select_coop");
   QD_CUDA(c, cudaLaunchCooperativeKernel((const void*)k_select_coop, dim3(c->sel_gx, c->batch), dim3(QD_SEL_THREADS), args, 0, c->stream));
   qd_prof_end(c, pi);
@@ -1170,12 +1178,23 @@ extern "C" int qd_vorticity(qd_ctx* c, const double* u, const double* v, double*
 }
 extern "C" int qd_median_pos(qd_ctx* c, const double* in, double empty_value, double* out_host) {
   if (!c || !in || !out_host) return QD_E_INVALID;
-  int rc = op_median(c, in, empty_value, c->d_scal + QD_S_TMP0, c->d_scal + QD_S_TMP1, QD_S_COUNT);
+  int rc = op_median(c, in, empty_value, c->d_scal + QD_S_TMP0, c->d_scal + QD_S_TMP1, QD_S_COUNT, 3);
   if (rc) return rc;
   std::vector<double> s((size_t)c->batch * QD_S_COUNT);
   rc = qd_get_scalars(c, s.data());
   if (rc) return rc;
   for (int b = 0; b < c->batch; ++b) out_host[b] = s[(size_t)b * QD_S_COUNT + QD_S_TMP0];
+  return QD_OK;
+}
+extern "C" int qd_median_stats(qd_ctx* c, long long* out /* [4][2] */) {
+  if (!c || !out) return QD_E_INVALID;
+  for (int k = 0; k < 2 * QD_SEL_SITES; ++k) out[k] = 0;
+#ifndef QD_HOST_EMU
+  unsigned h[2 * QD_SEL_SITES];
+  QD_CUDA(c, cudaStreamSynchronize(c->stream));
+  QD_CUDA(c, cudaMemcpy(h, c->d_sel_spec + (size_t)QD_SEL_SITES * c->batch, sizeof(h), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 2 * QD_SEL_SITES; ++k) out[k] = h[k];
+#endif
   return QD_OK;
 }
 extern "C" int qd_wsum(qd_ctx* c, const double* in, double* out_host) {
@@ -1526,7 +1545,7 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
       const double* P = c->h_prm + (size_t)b * QD_P_COUNT;
       if (P[QD_P_CLOUD_COUPLE] != 0.0 && P[QD_P_PCOND_REF] != P[QD_P_PCOND_REF]) need_median = true;
     }
-    if (need_median) { int rc = op_median(c, F(c, QD_F_PCOND), 1e-6, c->d_scal + QD_S_PREF_ATM, c->d_scal + QD_S_CNT_PCOND, QD_S_COUNT); if (rc) return rc; }
+    if (need_median) { int rc = op_median(c, F(c, QD_F_PCOND), 1e-6, c->d_scal + QD_S_PREF_ATM, c->d_scal + QD_S_CNT_PCOND, QD_S_COUNT, 2); if (rc) return rc; }
     QdEnergyArgs E; memset(&E, 0, sizeof(E));
     E.h = F(c, QD_F_H); E.hice = F(c, QD_F_HICE); E.ts_pre = F(c, QD_F_X2); E.olr = F(c, QD_F_OLR); E.cloud_eff = F(c, QD_F_CLOUD_EFF);
     E.ts = F(c, QD_F_TS); E.q_pre = F(c, QD_F_X3); E.cloud = F(c, QD_F_CLOUD); E.pcond = F(c, QD_F_PCOND); E.isr = F(c, QD_F_ISR);
@@ -2051,7 +2070,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
     if ((rc = op_gauss(c, 1, fl, sx, w1, &moved))) return rc;
     if (moved) orog_f = sx[0];
   }
-  if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT))) return rc;
+  if ((rc = op_median(c, F(c, QD_F_X0), 0.0, c->d_scal + QD_S_MED_POS, c->d_scal + QD_S_CNT_POS, QD_S_COUNT, 0))) return rc;
   QdPrecipBArgs Pb; memset(&Pb, 0, sizeof(Pb));
   Pb.pos = F(c, QD_F_X0); Pb.pcond = F(c, QD_F_PCOND); Pb.orog = orog_f; Pb.praw = F(c, QD_F_X2);
   Pb.part = c->d_part[0]; Pb.ticket = c->d_ticket + 6 * c->batch;
@@ -2076,7 +2095,7 @@ static int loop_physics(qd_ctx* c, const qd_step_cfg_t* cfg) {
     QD_K(c, k_precip_d, c->geo, Pd, w1);
   }
   // clouds (run_simulation.py:1866-1934)
-  if ((rc = op_median(c, F(c, QD_F_PRECIP), 1e-6, c->d_scal + QD_S_PREF, c->d_scal + QD_S_CNT_PRECIP, QD_S_COUNT))) return rc;
+  if ((rc = op_median(c, F(c, QD_F_PRECIP), 1e-6, c->d_scal + QD_S_PREF, c->d_scal + QD_S_CNT_PRECIP, QD_S_COUNT, 1))) return rc;
   QdCloudAArgs Ca; Ca.precip = F(c, QD_F_PRECIP); Ca.ts = F(c, QD_F_TS); Ca.u = F(c, QD_F_U); Ca.v = F(c, QD_F_V);
   Ca.craw = F(c, QD_F_X0); Ca.sraw = F(c, QD_F_X1);
   BP(c, BL({Ca.precip, 0}, {Ca.ts, 1}, {Ca.u, 1}, {Ca.v, 1}), BL(Ca.craw, Ca.sraw));

@@ -48,7 +48,7 @@ QD_HD double* qd_bred(const QdBandCtl& B, int r, int parity, int src) {
   return (double*)(B.peer[r] + B.off_red) + ((size_t)parity * QD_BAND_MAXW + src) * QD_BAND_MAXR;
 }
 struct QdLine;
-QD_HD QdLine* qd_bhist(const QdBandCtl& B, int r, int parity, int src);      // QD_SEL_MAXBINS / 2 lines (two bins each)
+QD_HD QdLine* qd_bhist(const QdBandCtl& B, int r, int parity, int src);      // QD_SEL_MAXBINS lines of two bins each (two histograms)
 QD_HD QdLine* qd_blist(const QdBandCtl& B, int r, int parity, int src);      // [0] count, [1] mingt, [2..] keys: one line each
 
 #if QD_EMU
@@ -149,7 +149,7 @@ __device__ __forceinline__ bool qd_ll_wait2(const QdBandCtl& B, const QdLine* l,
 }
 #endif
 QD_HD QdLine* qd_bhist(const QdBandCtl& B, int r, int parity, int src) {
-  return (QdLine*)(B.peer[r] + B.off_hist) + ((size_t)parity * QD_BAND_MAXW + src) * (QD_SEL_MAXBINS / 2);
+  return (QdLine*)(B.peer[r] + B.off_hist) + ((size_t)parity * QD_BAND_MAXW + src) * QD_SEL_MAXBINS;
 }
 QD_HD QdLine* qd_blist(const QdBandCtl& B, int r, int parity, int src) {
   return (QdLine*)(B.peer[r] + B.off_list) + ((size_t)parity * QD_BAND_MAXW + src) * (QD_SEL_CAP + 2);

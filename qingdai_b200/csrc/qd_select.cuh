@@ -8,6 +8,13 @@
 // host round trip).  As soon as <= QD_SEL_CAP candidates remain they are gathered and sorted by one block,
 // which also yields the upper middle element for even counts (np.median = mean of the two middle values).
 // The whole selection is ONE persistent cooperative launch.
+//
+// Speculation on the first digit: the median of a field moves slowly from step to step, and its first digit (sign +
+// exponent of the double) practically never changes.  Every call site remembers the first-digit bucket of its last
+// call (`spec`, device memory, per member); the FIRST sweep then also builds the second-digit histogram restricted to
+// that bucket.  If the located first digit equals the remembered one (checked exactly, every time), the second sweep
+// -- and, with latitude bands, its cross-rank round -- is skipped: 2 sweeps + 2 grid syncs (+ 2 rounds) instead of
+// 3 + 3 (+ 3).  A miss costs nothing but the wasted shared-memory atomics: the normal second pass runs.
 #pragma once
 #include "qd_band.cuh"           // QD_SEL_* sizes, QdBandCtl and the cross-rank pieces used when the field is split over ranks
 
@@ -70,9 +77,15 @@ __device__ __forceinline__ int qd_sel_locate(const unsigned* __restrict__ hist, 
 // radix passes down to bit 0.  3 sweeps + 3 grid syncs in the common case instead of 6 + 6.
 // The histograms are left zeroed for the next launch and the list counter / mingt are reset at the start: no
 // memset nodes in the step graph.
+// hist slots: [0] first digit, [1] speculative second digit, [p + 1] digit p >= 1 -- slots 0 and 1 are adjacent for one
+// member, so latitude bands all-reduce both in one round
+#define QD_SEL_SLOTS (QD_SEL_PASSES + 1)
+#define QD_SEL_NOSPEC 0xffffffffu
 __global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, const double* __restrict__ x, unsigned* hist,
                                                                unsigned long long* list, unsigned* lcount,
-                                                               unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B) {
+                                                               unsigned long long* mingt, int* more_flag, QdSelOut out, QdBandCtl B,
+                                                               unsigned* spec /* [B] remembered first digit, or null */,
+                                                               unsigned* spec_stat /* [2] calls, speculation hits of this site */) {
   cg::grid_group grid = cg::this_grid();
   __shared__ __align__(16) unsigned sh[QD_SEL_MAXBINS > 2 * QD_SEL_CAP ? QD_SEL_MAXBINS : 2 * QD_SEL_CAP];   // histogram, later the candidate keys
   __shared__ unsigned long long part[QD_SEL_THREADS];
@@ -89,17 +102,26 @@ __global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, cons
   int npass = 0, lo_shift = 63;
   // latitude bands: epoch of the k-th cross-rank collective of this launch = word at launch + k (same in every block)
   unsigned long long sel_epoch = B.world > 1 ? qd_bflags(B, B.rank)[QD_BF_EPOCH_SEL] : 0ull;
+  const unsigned spec1 = spec ? __ldcg(spec + b) : QD_SEL_NOSPEC;          // first digit of this call site's last median (block-uniform)
+  const bool spec_on = spec1 != QD_SEL_NOSPEC;
+  unsigned* ghs = hist + ((size_t)1 * g.batch + b) * QD_SEL_MAXBINS;
   // One radix pass.  Every block of the GRID takes part in the sync; members whose candidates already fit
   // the list (work == false) skip the sweep.
   auto radix_pass = [&](int pass, bool work) {
     const int shift = shifts[pass], nb = 1 << nbits[pass];
-    unsigned* gh = hist + ((size_t)pass * g.batch + b) * QD_SEL_MAXBINS;
+    unsigned* gh = hist + ((size_t)(pass ? pass + 1 : 0) * g.batch + b) * QD_SEL_MAXBINS;
+    const bool spec_pass = pass == 0 && spec_on;
     if (work) {
-      for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) sh[k] = 0;
+      for (int k = threadIdx.x; k < (spec_pass ? 2 * nb : nb); k += QD_SEL_THREADS) sh[k] = 0;
       __syncthreads();
       const int hi = shift + nbits[pass];
       // four independent loads per trip: with one load in flight per thread the sweep is bound by HBM latency
       // (27 dependent trips of ~1 us at 1441x2880), not by bandwidth
+      // First digit: nearly every key of a field shares ONE exponent, so the plain histogram serialises a warp's 32
+      // atomics on one shared-memory word -- that contention, not the loads, is the cost of this sweep.  Keys with the
+      // remembered digit are therefore counted in a register (one atomic per warp at the end); their second digit
+      // spreads over 2048 bins.
+      unsigned nspec = 0u;
       for (int idx = c0 + t0; idx < c1; idx += QD_SEL_UNROLL * stride) {
         double v[QD_SEL_UNROLL];
 #pragma unroll
@@ -108,16 +130,25 @@ __global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, cons
         for (int u = 0; u < QD_SEL_UNROLL; ++u)
           if (v[u] > 0.0) {
             const unsigned long long key = (unsigned long long)__double_as_longlong(v[u]);
-            if (pass == 0 || (key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
+            if (pass == 0) {
+              const unsigned d1 = (unsigned)(key >> 52);
+              if (spec_pass && d1 == spec1) { ++nspec; atomicAdd(&sh[QD_SEL_MAXBINS + (unsigned)((key >> 41) & 2047ull)], 1u); }
+              else atomicAdd(&sh[d1], 1u);
+            } else if ((key >> hi) == (prefix >> hi)) atomicAdd(&sh[(key >> shift) & (unsigned long long)(nb - 1)], 1u);
           }
+      }
+      if (spec_pass) {
+        for (int o = 16; o > 0; o >>= 1) nspec += __shfl_down_sync(0xffffffffu, nspec, o);
+        if ((threadIdx.x & 31) == 0 && nspec) atomicAdd(&sh[spec1 & (QD_SEL_MAXBINS - 1)], nspec);
       }
       __syncthreads();
       for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) { const unsigned c = sh[k]; if (c) atomicAdd(gh + k, c); }
+      if (spec_pass) for (int k = threadIdx.x; k < nb; k += QD_SEL_THREADS) { const unsigned c = sh[QD_SEL_MAXBINS + k]; if (c) atomicAdd(ghs + k, c); }
       __threadfence();
     }
     grid.sync();
     if (B.world > 1 && work) {                             // latitude bands (one member): histogram of the whole domain
-      qd_band_hist_allreduce(B, gh, nb, ++sel_epoch);
+      qd_band_hist_allreduce(B, gh, spec_pass ? 2 * nb : nb, ++sel_epoch);      // slots 0 and 1 are adjacent (batch = 1)
       grid.sync();
     }
     if (work) {
@@ -160,7 +191,21 @@ __global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, cons
   // list counter / "next above" key: reset here (they are first touched in the gather pass, two grid syncs later)
   if (blockIdx.x == 0 && threadIdx.x == 0) { lcount[b] = 0u; mingt[b] = ~0ull; }
   radix_pass(0, true);
-  radix_pass(1, inbin > QD_SEL_CAP);
+  // speculation check (exact): the located first digit is the remembered one -> its second-digit histogram is already
+  // complete in slot 1; locate there instead of sweeping again
+  const bool spec_hit = spec_on && (unsigned)(prefix >> 52) == spec1 && count > 0;
+  if (spec_hit && inbin > QD_SEL_CAP) {
+    unsigned long long below, total;
+    const int bin = qd_sel_locate(ghs, 1 << nbits[1], &rank, 0, sh, part, &below, &inbin, &total);
+    prefix |= ((unsigned long long)bin) << shifts[1];
+    rank -= below;
+    lo_shift = shifts[1];
+  }
+  {
+    // every block of the grid passes through radix_pass(1)'s sync; members that hit (or already fit) do no work in it
+    const bool work1 = !spec_hit && inbin > QD_SEL_CAP;
+    radix_pass(1, work1);
+  }
   const bool more = inbin > QD_SEL_CAP;                    // heavily duplicated data: keep narrowing
   if (more && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(more_flag, 1);
   gather_pass(!more);
@@ -174,8 +219,13 @@ __global__ void __launch_bounds__(QD_SEL_THREADS, 2) k_select_coop(QdGeo g, cons
   }
   // leave the histograms of the passes that ran zeroed for the next launch (every block is past its reads)
   for (int p = 0; p < npass; ++p) {
-    unsigned* gh = hist + ((size_t)p * g.batch + b) * QD_SEL_MAXBINS;
+    unsigned* gh = hist + ((size_t)(p ? p + 1 : 0) * g.batch + b) * QD_SEL_MAXBINS;
     for (int k = t0; k < (1 << nbits[p]); k += stride) gh[k] = 0u;
+  }
+  if (spec_on) for (int k = t0; k < QD_SEL_MAXBINS; k += stride) ghs[k] = 0u;
+  if (spec && blockIdx.x == 0 && threadIdx.x == 0) {
+    spec[b] = count > 0 ? (unsigned)(prefix >> 52) : QD_SEL_NOSPEC;
+    if (spec_stat) { atomicAdd(spec_stat, 1u); if (spec_hit) atomicAdd(spec_stat + 1, 1u); }       // calls, hits (qd_median_stats)
   }
   const bool fits = inbin <= QD_SEL_CAP;                   // false only when one VALUE fills the last bucket
   unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sh);      // QD_SEL_CAP x u64

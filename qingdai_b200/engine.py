@@ -457,6 +457,13 @@ class Engine:
         raw[:, 1:21] /= (raw[:, :1] + 1e-15)                 # x / (sum(w) + 1e-15), element by element as before
         return [dict(zip(self.DIAG, row)) for row in raw.tolist()]
 
+    def median_stats(self):
+        """[[launches, first-digit speculation hits]] of the exact-median kernel per call site (positive precipitation
+        part, precipitation, P_cond, qd_median_pos)."""
+        out = np.zeros((4, 2), dtype=np.int64)
+        self._chk(self.lib.qd_median_stats(self.ctx, _ptr(out)), "qd_median_stats")
+        return out
+
     def scalars(self):
         out = np.empty((self.batch, NS), dtype=np.float64)
         self._chk(self.lib.qd_get_scalars(self.ctx, _ptr(out)), "qd_get_scalars")

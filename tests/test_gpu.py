@@ -45,6 +45,10 @@ def test_median_large_duplicates_and_batch(lib):
     qdcheck.check_median_large(lib)
 
 
+def test_median_first_digit_speculation(lib):
+    qdcheck.check_median_speculation(lib)
+
+
 @pytest.mark.parametrize("shape", [(37, 72), (181, 360)])
 def test_ops_random(lib, shape):
     qdcheck.check_ops_random(lib, shape)
