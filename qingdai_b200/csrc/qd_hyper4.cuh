@@ -290,28 +290,16 @@ __device__ __forceinline__ bool qd_h4s_chunk(const QdGeo& g, const QdHyper4Args&
   p += 4 * (size_t)nlon;
   double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
   double apm = 0.0, amm = 0.0, blm = 0.0, ap0 = 0.0, am0 = 0.0, bl0 = 0.0;
-  // One group = 4 rows.  The four new F rows of group q+1 are loaded BEFORE group q is computed (software pipeline:
-  // the streaming loads of a warp are in flight for a whole group of arithmetic instead of being waited for at the top
-  // of it); the twelve coefficient loads of a group are warp-uniform L1 hits issued next to their use.  Unrolling by
-  // the window length turns the register shifts into renames.  jr = row of the first new Laplacian value of the
-  // group; emit = false for the warm-up group.
-#ifndef QD_H4S_PREFETCH
-#define QD_H4S_PREFETCH 0
-#endif
-#if QD_H4S_PREFETCH
-  double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];
-  p += 4 * (size_t)nlon;
-#define QD_H4S_LOADS(more)                                                                           \
-    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;                                                   \
-    if (more) { m0 = p[0]; m1 = p[nlon]; m2 = p[2 * (size_t)nlon]; m3 = p[3 * (size_t)nlon]; }       \
-    p += 4 * (size_t)nlon;
-#define QD_H4S_ROTATE n0 = m0; n1 = m1; n2 = m2; n3 = m3;
-#else
+  // One group = 4 rows: the four loads of new F rows are issued together at the top of the group so that their
+  // latency overlaps; the twelve coefficient loads of a group are warp-uniform L1 hits issued next to their use.
+  // Unrolling by the window length turns the register shifts into renames.  jr = row of the first new Laplacian value
+  // of the group; emit = false for the warm-up group.  Measured and dropped (profiles/README.md): loading group q+1
+  // before computing group q (96 registers, 5 blocks per SM: slower), and staging rows 8 / 12 ahead in a per-warp
+  // cp.async shared-memory ring (64 -> 74 us for the ocean's three fields).
 #define QD_H4S_LOADS(more)                                                                           \
     const double n0 = p[0], n1 = p[nlon], n2 = p[2 * (size_t)nlon], n3 = p[3 * (size_t)nlon];        \
     p += 4 * (size_t)nlon;
 #define QD_H4S_ROTATE
-#endif
 #define QD_H4S_GROUP(jr, emit, more)                                                                 \
   {                                                                                                  \
     QD_H4S_LOADS(more)                                                                               \
