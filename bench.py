@@ -58,7 +58,7 @@ ALG_BYTES = {
     "k_precip_a": (5 + 2) * 8, "k_precip_b": 4 * 8, "k_precip_c": 3 * 8, "k_precip_d": 2 * 8,
     "k_cloud_a": (4 + 2) * 8, "k_cloud_b": 4 * 8, "k_cloud_c": 3 * 8, "k_select_coop": 8, "k_select_cluster": 8,
     "k_ocean_prep": 6 * 8, "k_ocean_momentum": 7 * 8 + 1, "k_ocean_lap": 3 * 16, "k_ocean_hyper": 3 * 24,
-    "k_ocean_continuity": 6 * 8 + 1, "k_ocean_continuity2": 6 * 8 + 1, "k_ocean_sst_finish": 9 * 8 + 2, "k_ocean_sst_finish2": 9 * 8 + 2,
+    "k_ocean_continuity": 6 * 8 + 1, "k_ocean_continuity2": 6 * 8 + 1, "k_ocean_sst_finish": 9 * 8 + 2, "k_ocean_sst_finish2": 11 * 8 + 2,
     "k_ocean_fused": (6 + 4) * 8 + 1, "k_ocean_close": (4 + 2) * 8 + 2,
     "k_gauss2d_tile<plain>": 16, "k_gauss2d_tile<precip>": 3 * 8, "k_gauss2d_tile<cloud_b>": 4 * 8, "k_gauss2d_tile<cloud_c>": 3 * 8,
 }

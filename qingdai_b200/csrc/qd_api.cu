@@ -78,13 +78,14 @@ struct qd_ctx {
   std::map<const void*, int> red_cache;
   std::map<unsigned long long, cudaGraphExec_t> ocean_graphs;
   std::map<unsigned long long, std::pair<cudaGraphExec_t, long long>> step_graphs;   // variant -> (exec, launches per step)
+  bool ocean_fm_on = false;                                // set by ocean_core: closing pass fused with the next sub-step's momentum
   bool ocean_fused = false;                                // set by ocean_substep_body: the last body took the fused two-kernel path
   int ocean_fused_enable = 0;                              // qd_set_ocean_fused: opt-in (measured slower than the four-kernel form on B200)
   long long ocean_body_launches(bool do_hyper, bool do_shap, const qd_step_cfg_t* cfg) const {
     if (ocean_fused) return 6 + 1;                           // pole pass (momentum, 2 x del^4 tiles, continuity) + k_ocean_fused + k_ocean_close + advance
     const long long tiles_i = (nlon + 63) / 64;                  // launch_hyper4: large grids take the stream + pole-tile pair
     const bool stream = h4_stream && nlat >= 96 && nlon >= 64 && tiles_i * ((nlat + 31) / 32) * batch * 3 >= 2 * 148;
-    return 3 + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
+    return (ocean_fm_on ? 2 : 3) + (do_hyper ? (stream ? 2 : 1) * std::max(1, cfg->oc_k4_nsub) : 0) + (do_shap ? 2 * std::max(1, cfg->oc_shapiro_n) : 0) + 1;
   }
 #endif
   char err[512];
@@ -1752,6 +1753,29 @@ static int ocean_substep_fused(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, 
 // ------------------------------------------------------------------------------ ocean step
 // One CFL sub-step body (ocean.py:305-444).  Launched either from a host loop (stream mode) or captured
 // once as the body of a CUDA-graph WHILE node (graph mode); the sub-step index is read from device memory.
+// Closing pass of sub-step s fused with the momentum step of sub-step s+1 (qd_ocean.cuh: QdOcSstBArgs::fuse_mom): the
+// loop body is del^4 -> continuity -> closing+momentum, one momentum launch in front of the loop does sub-step 0.  Saves
+// one kernel and ~40 B per cell and sub-step (eta, uo, vo are not re-read, the home currents are only stored at the end).
+// Needs the two-cells-per-thread kernels, one del^4 pass per sub-step (its outputs must not alias the momentum outputs),
+// no latitude bands (their halo exchange sits between the closing pass and the momentum step).
+static bool ocean_fm(qd_ctx* c, const qd_step_cfg_t* cfg, bool do_hyper, bool do_shap) {
+#ifdef QD_HOST_EMU
+  (void)c; (void)cfg; (void)do_hyper; (void)do_shap;
+  return false;
+#else
+  if (c->band_on || !do_hyper || do_shap || cfg->oc_k4_nsub > 1 || (c->nlon & 1) || getenv("QD_NO_PAIRS") || getenv("QD_NO_FM")) return false;
+  return ocean_fused_rows(c, cfg, do_hyper, do_shap) == 0;
+#endif
+}
+static int ocean_momentum_launch(qd_ctx* c) {
+  QdSubCtl sc{c->d_sub_ctr};
+  QdOcMomArgs Mo; memset(&Mo, 0, sizeof(Mo));
+  Mo.eta = F(c, QD_F_ETA); Mo.uo = F(c, QD_F_UO); Mo.vo = F(c, QD_F_VO); Mo.taux = F(c, QD_F_X0); Mo.tauy = F(c, QD_F_X1);
+  Mo.ub = F(c, QD_F_X2); Mo.vb = F(c, QD_F_X3); Mo.land = M(c, QD_M_LAND);
+  BP(c, BL({Mo.eta, 1}, {Mo.uo, 0}, {Mo.vo, 0}, {Mo.taux, 0}, {Mo.tauy, 0}, {Mo.land, 0}), BL(Mo.ub, Mo.vb));
+  QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+  return QD_OK;
+}
 static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, bool do_hyper, bool do_shap, bool first_in_group = true) {
 #ifndef QD_HOST_EMU
   const int fused_rows = ocean_fused_rows(c, cfg, do_hyper, do_shap);
@@ -1771,8 +1795,11 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
     // divergence; SST: gather and diffusion).  The wind stress was exchanged once in ocean_core.
     { int rcb = band_hint(c, {QD_F_ETA, QD_F_UO, QD_F_VO, QD_F_SST}); if (rcb) return rcb; }
   }
-  BP(c, BL({Mo.eta, 1}, {Mo.uo, 0}, {Mo.vo, 0}, {Mo.taux, 0}, {Mo.tauy, 0}, {Mo.land, 0}), BL(Mo.ub, Mo.vb));
-  QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+  const bool fm = ocean_fm(c, cfg, do_hyper, do_shap);
+  if (!fm) {
+    BP(c, BL({Mo.eta, 1}, {Mo.uo, 0}, {Mo.vo, 0}, {Mo.taux, 0}, {Mo.tauy, 0}, {Mo.land, 0}), BL(Mo.ub, Mo.vb));
+    QD_K(c, k_ocean_momentum, c->geo, Mo, sc);
+  }
   double* ub = F(c, QD_F_X2); double* vb = F(c, QD_F_X3); double* eta_cur = F(c, QD_F_ETA);
   if (do_hyper) {
     const int ns = std::max(1, cfg->oc_k4_nsub);
@@ -1801,7 +1828,7 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
     int rc = op_shapiro(c, 3, fl, sx, cfg->oc_shapiro_n); if (rc) return rc;
   }
   QdOcContArgs Co; memset(&Co, 0, sizeof(Co));
-  Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
+  Co.ub = ub; Co.vb = vb; Co.eta_in = eta_cur; Co.eta = fm ? F(c, QD_F_X8) : F(c, QD_F_ETA); Co.part = c->d_part[2]; Co.land = M(c, QD_M_LAND);
   Co.sst = F(c, QD_F_SST); Co.tb = F(c, QD_F_X7);
   Co.ticket = c->d_ticket + 5 * c->batch;
   Co.band = c->band; if (!c->band_on) Co.band.world = 1;
@@ -1818,6 +1845,7 @@ static int ocean_substep_body(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, b
   Sb.sst = F(c, QD_F_SST); Sb.uo = F(c, QD_F_UO); Sb.vo = F(c, QD_F_VO); Sb.ts_atm = F(c, QD_F_TS); Sb.eta = F(c, QD_F_ETA);
   Sb.land = M(c, QD_M_LAND); Sb.ice = M(c, QD_M_ICE);
   Sb.has_q = cfg->oc_has_q; Sb.has_ice = cfg->oc_has_ice; Sb.inject = inject;
+  if (fm) { Sb.fuse_mom = 1; Sb.eta_mid = F(c, QD_F_X8); Sb.taux = F(c, QD_F_X0); Sb.tauy = F(c, QD_F_X1); Sb.ub_next = F(c, QD_F_X2); Sb.vb_next = F(c, QD_F_X3); }
   // T_s is only WRITTEN here (SST injection on a member's last sub-step, also on whatever halo rows the launch covers --
   // the neighbour computes the same values for them); nothing inside the loop reads it, and ocean_core resets its valid
   // width after the loop, so it constrains neither the compute region nor is it marked valid
@@ -1955,6 +1983,10 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
     QD_KG(c, k_ocean_k4tab, dim3((c->nlat + 127) / 128, 3, c->batch), dim3(128), c->geo, K);
   }
 #endif
+#ifndef QD_HOST_EMU
+  c->ocean_fm_on = ocean_fm(c, cfg, do_hyper, do_shap);
+#endif
+  if (ocean_fm(c, cfg, do_hyper, do_shap)) { int rcm = ocean_momentum_launch(c); if (rcm) return rcm; }   // momentum of sub-step 0; the body's closing pass does the others
 #ifndef QD_HOST_EMU
   if (c->capture_graph) {
     // whole-step capture: splice a WHILE node into the graph being captured (CUDA programming guide,

@@ -297,7 +297,39 @@ struct QdOcSstBArgs {
   double *sst, *uo, *vo, *ts_atm, *eta;
   const uint8_t *land, *ice;
   int has_q, has_ice, inject;
+  // fuse_mom: the closing pass of sub-step s also does the momentum step of sub-step s+1 (ocean.py:306-336) for every
+  // member that has one: eta comes from eta_mid (continuity's output; the finished eta goes to `eta`, a different slot,
+  // because the momentum stencil reads the neighbours' eta_mid), the post-momentum currents go to ub_next / vb_next (the
+  // del^4 input slots, dead by now); the home currents uo / vo are only written on a member's last sub-step.
+  int fuse_mom;
+  const double *eta_mid, *taux, *tauy;
+  double *ub_next, *vb_next;
 };
+// momentum step of ONE cell from its finished currents and the finished eta of its four neighbours (k_ocean_momentum,
+// operand for operand)
+QD_HD void qd_oc_momentum_cell(const QdGeo& g, const double* P, double sub_dt, double f, double iach, double rex, bool land,
+                               double e_e, double e_w, double e_n, double e_s, double taux, double tauy, double* uo_io, double* vo_io) {
+  double uo = *uo_io, vo = *vo_io;
+  const double de_dl = (e_e - e_w) * g.inv_2dlon;
+  const double de_dp = (e_n - e_s) * g.inv_2dlat;
+  const double gx = de_dl * iach;
+  const double gy = de_dp * g.inv_a;
+  const double irH = P[QD_P_OC_INV_RHO_H];
+  const double du = (f * vo - P[QD_P_OC_G] * gx + taux * irH - P[QD_P_OC_R_BOT] * uo);
+  const double dv = (-f * uo - P[QD_P_OC_G] * gy + tauy * irH - P[QD_P_OC_R_BOT] * vo);
+  uo = uo + sub_dt * du;
+  vo = vo + sub_dt * dv;
+  if (land) { uo = 0.0; vo = 0.0; }
+  uo = uo - sub_dt * rex * uo;
+  vo = vo - sub_dt * rex * vo;
+  *uo_io = uo; *vo_io = vo;
+}
+// finished eta of a cell from continuity's output (ocean.py:375,436-443): what the closing pass stores for that cell
+QD_HD double qd_oc_eta_done(double e_mid, bool any_ocean, double eta_mean, double eta_cap) {
+  double e = e_mid;
+  if (any_ocean) e = e - eta_mean;
+  return qd_clip(qd_nan_to_num(e), -eta_cap, eta_cap);
+}
 // One cell of the closing pass, general form (any row: one-sided Laplacian next to the poles, every value cleaned).
 QD_D void qd_sstf_cell_general(const QdGeo& g, const QdOcSstBArgs& A, const QdSubCtl& sc, int b, int j, int i, double eta_mean) {
   const size_t off = (size_t)b * g.ncell;
@@ -308,7 +340,7 @@ QD_D void qd_sstf_cell_general(const QdGeo& g, const QdOcSstBArgs& A, const QdSu
   const double sub_dt = S[QD_S_SUB_DT];
   const int nlon = g.nlon, nlat = g.nlat;
   {   // eta: mean removal over the ocean + hygiene (ocean.py:375,436-443); the sum comes from k_ocean_continuity
-    double e = A.eta[c];
+    double e = A.fuse_mom ? A.eta_mid[c] : A.eta[c];
     if (P[QD_P_OC_ANY_OCEAN] != 0.0) e = e - eta_mean;
     A.eta[c] = qd_clip(qd_nan_to_num(e), -P[QD_P_OC_ETA_CAP], P[QD_P_OC_ETA_CAP]);
   }
@@ -352,9 +384,20 @@ QD_D void qd_sstf_cell_general(const QdGeo& g, const QdOcSstBArgs& A, const QdSu
       vo = vo * sc1;
     }
   }
-  A.uo[c] = uo;
-  A.vo[c] = vo;
   const bool last = (*sc.ctr == (int)S[QD_S_NSUB] - 1);
+  if (!A.fuse_mom || last) { A.uo[c] = uo; A.vo[c] = vo; }
+  if (A.fuse_mom && !last) {          // momentum step of the next sub-step (np.roll: pole-to-pole wrap in latitude)
+    const bool any = P[QD_P_OC_ANY_OCEAN] != 0.0;
+    const double cap_e = P[QD_P_OC_ETA_CAP];
+    const int ip = i + 1 < nlon ? i + 1 : 0, im = i > 0 ? i - 1 : nlon - 1;
+    const int jp = j + 1 < nlat ? j + 1 : 0, jm = j > 0 ? j - 1 : nlat - 1;
+    const double* em = A.eta_mid + off;
+    qd_oc_momentum_cell(g, P, sub_dt, qd_row(g, QD_R_FCOR)[j], qd_row(g, QD_R_INV_ACOS_HALF)[j], qd_mrow(g, QD_R_OC_SPONGE, b)[j], !ocean,
+                        qd_oc_eta_done(em[(size_t)j * nlon + ip], any, eta_mean, cap_e), qd_oc_eta_done(em[(size_t)j * nlon + im], any, eta_mean, cap_e),
+                        qd_oc_eta_done(em[(size_t)jp * nlon + i], any, eta_mean, cap_e), qd_oc_eta_done(em[(size_t)jm * nlon + i], any, eta_mean, cap_e),
+                        A.taux[c], A.tauy[c], &uo, &vo);
+    A.ub_next[c] = uo; A.vb_next[c] = vo;
+  }
   if (last && j > 0 && j < nlat - 1) {
     T = qd_clip(T, P[QD_P_OC_TS_MIN], P[QD_P_OC_TS_MAX]);
     if (A.inject && ocean && !ice) A.ts_atm[c] = T;
@@ -481,7 +524,8 @@ __global__ void __launch_bounds__(QD_THREADS, 3) k_ocean_sst_finish2(QdGeo g, Qd
   const double* __restrict__ tb = A.tb + off;
   const double* cr = qd_row(g, QD_R_COS_ADV_HALF);
   const QdSstfRow R{cr[j + 1], cr[j - 1], cr[nlat + j], cr[2 * nlat + j]};
-  const double2 e2 = *reinterpret_cast<const double2*>(A.eta + off + idx);
+  const double* __restrict__ esrc = (A.fuse_mom ? A.eta_mid : A.eta) + off;
+  const double2 e2 = *reinterpret_cast<const double2*>(esrc + idx);
   const double2 t2c = *reinterpret_cast<const double2*>(tb + idx);
   double2 tn2 = t2c, ts2 = t2c;
   double tw = 0.0, te = 0.0;
@@ -510,8 +554,28 @@ __global__ void __launch_bounds__(QD_THREADS, 3) k_ocean_sst_finish2(QdGeo g, Qd
   if (ov0) qd_sstf_over(g, A, b, j, i, &uo0, &vo0);
   if (ov1) qd_sstf_over(g, A, b, j, i + 1, &uo1, &vo1);
   *reinterpret_cast<double2*>(A.eta + off + idx) = make_double2(eo0, eo1);
-  *reinterpret_cast<double2*>(A.uo + off + idx) = make_double2(uo0, uo1);
-  *reinterpret_cast<double2*>(A.vo + off + idx) = make_double2(vo0, vo1);
+  if (!A.fuse_mom || K.last) {
+    *reinterpret_cast<double2*>(A.uo + off + idx) = make_double2(uo0, uo1);
+    *reinterpret_cast<double2*>(A.vo + off + idx) = make_double2(vo0, vo1);
+  }
+  if (A.fuse_mom && !K.last) {
+    // momentum step of sub-step s+1 on the pair (rows 2 .. n_lat-3: no wrap in latitude): the finished eta of the six
+    // neighbours is formed from continuity's output exactly as their own threads form it
+    const double* P = g.prm + (size_t)b * QD_P_COUNT;
+    const double2 en2 = *reinterpret_cast<const double2*>(esrc + idx + nlon), es2 = *reinterpret_cast<const double2*>(esrc + idx - nlon);
+    const double ew = esrc[i > 0 ? idx - 1 : idx + nlon - 1], ee = esrc[i + 2 < nlon ? idx + 2 : idx + 2 - nlon];
+    const double2 tx2 = *reinterpret_cast<const double2*>(A.taux + off + idx), ty2 = *reinterpret_cast<const double2*>(A.tauy + off + idx);
+    const double f = qd_row(g, QD_R_FCOR)[j], iach = qd_row(g, QD_R_INV_ACOS_HALF)[j], rex = qd_mrow(g, QD_R_OC_SPONGE, b)[j];
+    double mu0 = uo0, mv0 = vo0, mu1 = uo1, mv1 = vo1;
+    qd_oc_momentum_cell(g, P, K.sub_dt, f, iach, rex, !oc0, eo1, qd_oc_eta_done(ew, K.any_ocean, K.eta_mean, K.eta_cap),
+                        qd_oc_eta_done(en2.x, K.any_ocean, K.eta_mean, K.eta_cap), qd_oc_eta_done(es2.x, K.any_ocean, K.eta_mean, K.eta_cap),
+                        tx2.x, ty2.x, &mu0, &mv0);
+    qd_oc_momentum_cell(g, P, K.sub_dt, f, iach, rex, !oc1, qd_oc_eta_done(ee, K.any_ocean, K.eta_mean, K.eta_cap), eo0,
+                        qd_oc_eta_done(en2.y, K.any_ocean, K.eta_mean, K.eta_cap), qd_oc_eta_done(es2.y, K.any_ocean, K.eta_mean, K.eta_cap),
+                        tx2.y, ty2.y, &mu1, &mv1);
+    *reinterpret_cast<double2*>(A.ub_next + off + idx) = make_double2(mu0, mu1);
+    *reinterpret_cast<double2*>(A.vb_next + off + idx) = make_double2(mv0, mv1);
+  }
   *reinterpret_cast<double2*>(A.sst + off + idx) = make_double2(T0, T1);
   if (K.last && K.inject) {
     if (oc0 && !ic0) A.ts_atm[off + idx] = T0;

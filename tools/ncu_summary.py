@@ -20,9 +20,17 @@ def main():
     idx = {h: i for i, h in enumerate(hdr)}
     w = csv.writer(sys.stdout)
     w.writerow(["Kernel Name"] + COLS)
-    w.writerow([""] + [units[idx[c]] if c in idx else "" for c in COLS])
+    w.writerow([""] + [("Mbyte" if units[idx[c]].endswith("byte") else units[idx[c]]) if c in idx else "" for c in COLS])
+    # ncu picks the unit of a column from its largest value (byte .. Gbyte): bytes are normalised to Mbyte here
+    scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}
     for r in rows[2:]:
-        w.writerow([r[idx["Kernel Name"]]] + [r[idx[c]] if c in idx else "" for c in COLS])
+        vals = []
+        for c in COLS:
+            v = r[idx[c]] if c in idx else ""
+            if c in idx and units[idx[c]] in scale and v:
+                v = "%.6f" % (float(v.replace(",", "")) * scale[units[idx[c]]])
+            vals.append(v)
+        w.writerow([r[idx["Kernel Name"]]] + vals)
 
 
 if __name__ == "__main__":
