@@ -70,6 +70,7 @@ struct qd_ctx {
   int last_nsub_max;
   QdGaussW w_sigma1, w_cloud; int w_set;
   int* d_sub_ctr; int use_graphs;
+  int tail_did_prep = 0;                            // set by atmos_core (loop mode): k_tail also did the ocean step's preparation
   int graph_failures = 0;                           // step / ocean graph captures that failed (the step then runs in stream mode)
 #ifndef QD_HOST_EMU
   cudaStream_t cap_stream, cap_stream2;
@@ -1627,7 +1628,12 @@ static int atmos_core(qd_ctx* c, const qd_step_cfg_t* cfg, int mode_loop) {
     T.cloud_eff = F(c, QD_F_CLOUD_EFF); T.lh = F(c, QD_F_LH); T.uo = F(c, QD_F_UO); T.vo = F(c, QD_F_VO);
     T.qnet = F(c, QD_F_QNET); T.ice = M(c, QD_M_ICE); T.land = M(c, QD_M_LAND);
     T.part_max_u = c->d_part[0]; T.part_max_va = c->d_part[1]; T.ticket = c->d_ticket + 3 * c->batch;
-    T.dt = dt; T.with_qnet = (mode_loop && cfg->with_ocean) ? 1 : 0; T.has_cloud_eff = c->has_cloud_eff; T.with_max = 0;
+    T.dt = dt; T.with_qnet = (mode_loop && cfg->with_ocean) ? 1 : 0; T.has_cloud_eff = c->has_cloud_eff;
+    // loop mode on one GPU: the ocean step's preparation rides along (ocean_core then skips k_ocean_prep); latitude bands
+    // keep the separate kernel (n_sub needs the all-reduced maxima)
+    T.with_max = (mode_loop && cfg->with_ocean && !c->band_on && !getenv("QD_NO_TAILPREP")) ? 1 : 0;
+    T.taux = F(c, QD_F_X0); T.tauy = F(c, QD_F_X1); T.sub_ctr = c->d_sub_ctr;
+    c->tail_did_prep = T.with_max;
     BP(c, BL({T.u_in, 0}, {T.v_in, 0}, {T.h_in, 0}, {T.q_in, 0}, {T.ts, 0}, {T.cloud_adv, 0}, {T.hice, 0}, {T.isr, 0}, {T.albedo, 0},
              {T.cloud_eff, 0}, {T.lh, 0}, {T.uo, 0}, {T.vo, 0}, {T.land, 0}, {T.qnet, 0}, {T.ice, 0}),
        BL(T.u, T.v, T.h, T.ts, T.q, T.cloud, T.qnet, T.ice));
@@ -1949,8 +1955,12 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
   P0.taux = F(c, QD_F_X0); P0.tauy = F(c, QD_F_X1); P0.part_u = c->d_part[0]; P0.part_va = c->d_part[1];
   P0.ticket = c->d_ticket + 4 * c->batch;
   P0.dt = dt; P0.sub_ctr = c->band_on ? nullptr : c->d_sub_ctr;      // bands: n_sub needs the all-reduced maxima first
-  BP(c, BL({P0.u, 0}, {P0.v, 0}, {P0.uo, 0}, {P0.vo, 0}), BL(P0.taux, P0.tauy));
-  QD_KR(c, k_ocean_prep, c->geo, P0);
+  const bool prep_done = c->tail_did_prep && !wind_u && !wind_v && !c->band_on;      // k_tail of this step already did it
+  c->tail_did_prep = 0;
+  if (!prep_done) {
+    BP(c, BL({P0.u, 0}, {P0.v, 0}, {P0.uo, 0}, {P0.vo, 0}), BL(P0.taux, P0.tauy));
+    QD_KR(c, k_ocean_prep, c->geo, P0);
+  }
   { int rcb = band_allreduce(c, {QD_S_MAX_UOCEAN, QD_S_MAX_VA}, true); if (rcb) return rcb; }
   if (c->band_on) QD_KG(c, k_ocean_nsub, dim3((c->batch + 63) / 64), dim3(64), c->geo, dt, c->d_sub_ctr);
   const bool do_hyper = (cfg->oc_diff_every > 0) && (c->oc_counter % cfg->oc_diff_every == 0);

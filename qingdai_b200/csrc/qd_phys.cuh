@@ -420,7 +420,12 @@ struct QdTailArgs {
   double *qnet; uint8_t* ice; const uint8_t* land;
   double *part_max_u, *part_max_va; unsigned* ticket;
   double dt; int with_qnet, has_cloud_eff, with_max;
+  // with_max (loop mode with the dynamic ocean, one GPU): this pass also does the ocean step's preparation
+  // (k_ocean_prep: wind stress ocean.py:285-290, the two maxima and n_sub ocean.py:293-303) -- it has the final winds and
+  // the currents in registers already, so the ocean step starts without re-reading four fields
+  double *taux, *tauy; int* sub_ctr;
 };
+QD_D void qd_ocean_nsub_member(const QdGeo& g, int b, double dt);      // qd_ocean.cuh
 __global__ void __launch_bounds__(QD_THREADS, 4) k_tail(QdGeo g, QdTailArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
@@ -445,10 +450,13 @@ __global__ void __launch_bounds__(QD_THREADS, 4) k_tail(QdGeo g, QdTailArgs A) {
       const double SH = qd_sensible(ts, Ta, u, v, P);
       A.qnet[c] = sw.sfc - lw.sfc - SH - A.lh[c];
     }
-    if (A.with_max) {
+    if (A.with_max) {                           // k_ocean_prep's cell code, operand for operand
       const double uo = A.uo[c], vo = A.vo[c];
       const double ur = u - uo, vr = v - vo;
       const double sp = sqrt(uo * uo + vo * vo), va = sqrt(ur * ur + vr * vr);
+      const double Ve = qd_min(va, P[QD_P_OC_VCAP]);
+      A.taux[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * ur);
+      A.tauy[c] = P[QD_P_OC_TAU_SCALE] * (P[QD_P_OC_RHO_A] * P[QD_P_OC_CD] * Ve * vr);
       if (sp > mu) mu = sp;                     // NaN-ignoring running maxima, like qd_block_max
       if (va > mva) mva = va;
     }
@@ -461,9 +469,12 @@ __global__ void __launch_bounds__(QD_THREADS, 4) k_tail(QdGeo g, QdTailArgs A) {
       double* S = g.scal + (size_t)b * QD_S_COUNT;
       double m1 = 0.0, m2 = 0.0;
       const bool o1 = qd_final_max<2>(A.part_max_u + (size_t)b * gridDim.x, gridDim.x, &m1);
-      if (o1) S[QD_S_MAX_UOCEAN] = m1;
       const bool o2 = qd_final_max<3>(A.part_max_va + (size_t)b * gridDim.x, gridDim.x, &m2);
-      if (o2) S[QD_S_MAX_VA] = m2;
+      if (o1 && o2) {                           // the owner thread of both reductions is the same thread
+        S[QD_S_MAX_UOCEAN] = m1;
+        S[QD_S_MAX_VA] = m2;
+        if (A.sub_ctr) { if (b == 0) *A.sub_ctr = 0; qd_ocean_nsub_member(g, b, A.dt); }
+      }
     }
   }
 }
