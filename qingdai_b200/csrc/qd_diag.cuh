@@ -37,7 +37,10 @@ QD_D double qd_diag_identity(int q) {
   return -DBL_MAX;
 }
 
-__global__ void __launch_bounds__(QD_THREADS) k_diag(QdGeo g, QdDiagArgs A) {
+#ifndef QD_LB_DIAG
+#define QD_LB_DIAG 1
+#endif
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_DIAG) k_diag(QdGeo g, QdDiagArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double* part = A.part + ((size_t)blockIdx.y * QD_DIAG_COUNT) * g.nvb;
   QD_VB_LOOP(g) {

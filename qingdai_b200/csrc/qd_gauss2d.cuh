@@ -158,7 +158,10 @@ __device__ __forceinline__ void qd_tma_load_2d(void* smem_dst, const CUtensorMap
 }
 
 template <int MODE, bool TMA>
-__global__ void __launch_bounds__(256) k_gauss2d_r4(QdGeo g, QdG2Args A, QdGaussW w, const __grid_constant__ CUtensorMap tm0,
+#ifndef QD_LB_G2R4
+#define QD_LB_G2R4 1
+#endif
+__global__ void __launch_bounds__(256, QD_LB_G2R4) k_gauss2d_r4(QdGeo g, QdG2Args A, QdGaussW w, const __grid_constant__ CUtensorMap tm0,
                                                    const __grid_constant__ CUtensorMap tm1) {
   constexpr int TJ = QD_G3_TJ, TI = QD_G3_TI, CW = QD_G3_CW, RH = QD_G3_RH;
   __shared__ __align__(128) double in2[2][RH * CW];          // one buffer per input field: both TMA loads are in flight from the start

@@ -14,7 +14,7 @@ struct QdPrecipAArgs {
   unsigned* ticket;
   const qd_forcing_t* forcing; const int* step_idx; double* hcos;    // first kernel of the step: also fills cos(hour angle) per column
 };
-__global__ void __launch_bounds__(QD_THREADS) k_precip_a(QdGeo g, QdPrecipAArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_PRECIPA) k_precip_a(QdGeo g, QdPrecipAArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   if (A.hcos && blockIdx.y == 0) {           // forcing.py:118-131, consumed by k_column later in the step
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nlon; i += gridDim.x * blockDim.x) qd_forcing_col(g, A.forcing, A.step_idx, A.hcos, i);
@@ -47,7 +47,10 @@ struct QdPrecipBArgs {
   double *praw, *part;
   unsigned* ticket;
 };
-__global__ void __launch_bounds__(QD_THREADS) k_precip_b(QdGeo g, QdPrecipBArgs A) {
+#ifndef QD_LB_PRECIPB
+#define QD_LB_PRECIPB 7
+#endif
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_PRECIPB) k_precip_b(QdGeo g, QdPrecipBArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   // the median scale is the same for every cell of a member (one reciprocal per thread, amortised over its cells);
   // pos is zero wherever the flow diverges
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_precip_d(QdGeo g, QdPrecipDArgs 
 // ---- cloud phase A: C_raw = C_max*tanh(precip/(P_ref+1e-12)) and the raw cloud source
 //      (physics.py:48-70, :72-108; P_ref = median(precip>0) run_simulation.py:1867-1875)
 struct QdCloudAArgs { const double *precip, *ts, *u, *v; double *craw, *sraw; };
-__global__ void __launch_bounds__(QD_THREADS) k_cloud_a(QdGeo g, QdCloudAArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_CLOUDA) k_cloud_a(QdGeo g, QdCloudAArgs A) {
   QD_CELL_PROLOGUE(g)
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity(QdGeo g, QdOcCo
 // values and of its north / south neighbours, shared row constants (the one-cell kernel spends 44 % of its issue slots on
 // index arithmetic: profiles/README.md).  Virtual block vb owns PAIRS vb*256 + t + k*nvb*256; a thread adds its cells in
 // that order, so the eta sum is still a function of the grid and the device only (not of the batch size).
-__global__ void __launch_bounds__(QD_THREADS) k_ocean_continuity2(QdGeo g, QdOcContArgs A, QdSubCtl sc) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_CONT2) k_ocean_continuity2(QdGeo g, QdOcContArgs A, QdSubCtl sc) {
   const bool done = qd_sub_done(g, blockIdx.y, sc);
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   const double sub_dt = g.scal[(size_t)blockIdx.y * QD_S_COUNT + QD_S_SUB_DT];
@@ -493,7 +493,7 @@ __device__ __forceinline__ void qd_sstf_over(const QdGeo& g, const QdOcSstBArgs&
   }
   *uo_io = uo; *vo_io = vo;
 }
-__global__ void __launch_bounds__(QD_THREADS, 3) k_ocean_sst_finish2(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_FIN2) k_ocean_sst_finish2(QdGeo g, QdOcSstBArgs A, QdSubCtl sc) {
   const int b = blockIdx.y;
   __shared__ QdSstfK sK;
   if (threadIdx.x == 0) {

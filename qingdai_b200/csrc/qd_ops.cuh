@@ -306,7 +306,10 @@ QD_HD void qd_departure(double u, double v, double dt, const QdGeo& g, double co
   *x = (double)i - dx;
 }
 
-__global__ void __launch_bounds__(QD_THREADS) k_advect(QdGeo g, QdFields f, const double* u, const double* v,
+#ifndef QD_LB_ADVECT
+#define QD_LB_ADVECT 7
+#endif
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_ADVECT) k_advect(QdGeo g, QdFields f, const double* u, const double* v,
                                                       double dt, const double* cosr, const double* iacr) {
   QD_CELL_PROLOGUE(g)
   if (!active) return;

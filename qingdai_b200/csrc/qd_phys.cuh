@@ -7,6 +7,34 @@
 #pragma once
 #include "qd_ops.cuh"
 #include "qd_select.cuh"
+// Minimum resident blocks per SM (__launch_bounds__) of the large cell kernels.  They are latency-bound (30-58 % of DRAM
+// peak AND 35-70 % issue utilisation in the r02b ncu capture), so more resident warps pay even at the price of a few
+// spilled registers: measured per kernel at 1441x2880 on one B200 (profiles/README.md), e.g. k_energy 193 -> 141 us at 7
+// blocks (36 registers instead of 54), k_column 235 -> 212 us at 5; the whole step 2.13 -> 1.99 ms.  -D overrides for A/B.
+#ifndef QD_LB_COL
+#define QD_LB_COL 5
+#endif
+#ifndef QD_LB_EN
+#define QD_LB_EN 7
+#endif
+#ifndef QD_LB_TAIL
+#define QD_LB_TAIL 5
+#endif
+#ifndef QD_LB_ADVMOM
+#define QD_LB_ADVMOM 7
+#endif
+#ifndef QD_LB_CONT2
+#define QD_LB_CONT2 6
+#endif
+#ifndef QD_LB_FIN2
+#define QD_LB_FIN2 3
+#endif
+#ifndef QD_LB_CLOUDA
+#define QD_LB_CLOUDA 7
+#endif
+#ifndef QD_LB_PRECIPA
+#define QD_LB_PRECIPA 7
+#endif
 
 // ------------------------------------------------------------------------------ humidity (humidity.py)
 QD_HD double qd_qsat(double T, double p0) {                       // humidity.py:85-101
@@ -150,7 +178,7 @@ struct QdColArgs {
   int mode_loop, has_albedo, has_cloud_eff, with_hydrology, with_eco, store_isr_ab;
 };
 
-__global__ void __launch_bounds__(QD_THREADS) k_column(QdGeo g, QdColArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_COL) k_column(QdGeo g, QdColArgs A) {
   QD_CELL_PROLOGUE(g)
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;
@@ -300,7 +328,7 @@ struct QdEnergyArgs {
   const uint8_t* land;
   double dt;
 };
-__global__ void __launch_bounds__(QD_THREADS) k_energy(QdGeo g, QdEnergyArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_EN) k_energy(QdGeo g, QdEnergyArgs A) {
   QD_CELL_PROLOGUE(g)
   const double* P = g.prm + (size_t)b * QD_P_COUNT;
   const QdRcp* D = g.udiv + (size_t)b * QD_U_COUNT;
@@ -360,7 +388,7 @@ struct QdAdvMomArgs {
   double *ts, *q, *u, *v;
   double dt;
 };
-__global__ void __launch_bounds__(QD_THREADS) k_advect_momentum(QdGeo g, QdAdvMomArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_ADVMOM) k_advect_momentum(QdGeo g, QdAdvMomArgs A) {
   QD_CELL_PROLOGUE(g)
   if (!active) return;
   const size_t c = off + idx;
@@ -426,7 +454,7 @@ struct QdTailArgs {
   double *taux, *tauy; int* sub_ctr;
 };
 QD_D void qd_ocean_nsub_member(const QdGeo& g, int b, double dt);      // qd_ocean.cuh
-__global__ void __launch_bounds__(QD_THREADS, 4) k_tail(QdGeo g, QdTailArgs A) {
+__global__ void __launch_bounds__(QD_THREADS, QD_LB_TAIL) k_tail(QdGeo g, QdTailArgs A) {
   const double* P = g.prm + (size_t)blockIdx.y * QD_P_COUNT;
   double mu = 0.0, mva = 0.0;
   const QdRcp* D = g.udiv + (size_t)blockIdx.y * QD_U_COUNT;
