@@ -2057,7 +2057,7 @@ static int ocean_core(qd_ctx* c, const qd_step_cfg_t* cfg, int inject, const dou
   Po.sst = F(c, QD_F_SST); Po.uo = F(c, QD_F_UO); Po.vo = F(c, QD_F_VO); Po.ts_atm = F(c, QD_F_TS);
   Po.land = M(c, QD_M_LAND); Po.ice = M(c, QD_M_ICE); Po.has_ice = cfg->oc_has_ice; Po.inject = inject;
   Po.step_idx = c->polar_advances_step ? c->d_step_idx : nullptr;
-  QD_KG(c, k_ocean_polar, dim3(2, c->batch), dim3(QD_THREADS), c->geo, Po);
+  QD_KG(c, k_ocean_polar, dim3(2, c->batch), dim3(QD_POLAR_THREADS), c->geo, Po);
   if (c->band_on) for (int id : {(int)QD_F_SST, (int)QD_F_UO, (int)QD_F_VO, (int)QD_F_TS}) c->band_valid[id] = 0;   // pole rows changed on their owners only
   QD_CHECK_LAUNCH(c);
   return QD_OK;

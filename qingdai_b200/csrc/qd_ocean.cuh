@@ -606,7 +606,10 @@ struct QdOcPolarArgs {
   int has_ice, inject;
   int* step_idx;           // loop mode: the step counter of the forcing table advances here (last kernel of the step)
 };
-__global__ void __launch_bounds__(QD_THREADS) k_ocean_polar(QdGeo g, QdOcPolarArgs A) {
+// Two blocks only (one per pole): 1024 threads each, so a ring of 2880 cells takes 3 trips per sweep instead of 12
+// (25 -> ~12 us at 1441x2880; the kernel is a chain of three dependent sweeps).
+#define QD_POLAR_THREADS 1024
+__global__ void __launch_bounds__(QD_POLAR_THREADS) k_ocean_polar(QdGeo g, QdOcPolarArgs A) {
   const int b = blockIdx.y, north = blockIdx.x;
   if (A.step_idx && b == 0 && north == 0 && threadIdx.x == 0) *A.step_idx = *A.step_idx + 1;
   const int j = north ? g.nlat - 1 : 0, n = g.nlon;
