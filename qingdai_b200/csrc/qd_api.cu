@@ -872,6 +872,18 @@ static int op_laplacian(qd_ctx* c, int n, const double* const* src, double* cons
 }
 // Fused del^4 (csrc/qd_hyper4.cuh): n fields, src[k] -> dst[k] (out of place), nsub sub-divisions
 // ping-ponging between the two buffer sets; returns in *final_in_dst whether the result ended in dst.
+#ifndef QD_HOST_EMU
+// Rows per warp of the streaming del^4 kernel.  A warp marches down its chunk row by row (~0.3 us per row of dependent
+// work): 64-row chunks keep the 8-row warm-up at 12 % but need enough strips x chunks to fill the machine (148 SMs x 24
+// resident warps); smaller problems (latitude bands on 4+ GPUs, batches of 181x360 members) take 32- or 16-row chunks --
+// more warps, shorter chains: the largest chunk that still fills the machine.  Identical bits (the chunk length only decides who computes a row).
+static int h4s_rows(qd_ctx* c, int nstrips, int rows, int nfields) {
+  if (const char* ov = getenv("QD_H4S_ROWS")) { const int r = atoi(ov); return r == 16 ? 16 : (r == 32 ? 32 : 64); }      // A/B override
+  for (int R = 64; R > 16; R >>= 1)
+    if ((long long)nstrips * ((rows + R - 1) / R) * nfields * c->batch >= 148LL * 24) return R;
+  return 16;
+}
+#endif
 static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   const int tiles_i = (c->nlon + QD_H4_TI - 1) / QD_H4_TI;
   const long long blocks32 = (long long)tiles_i * ((c->nlat + 31) / 32) * c->batch * H.n;
@@ -896,13 +908,15 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
 #ifndef QD_HOST_EMU
       const int ja = std::max(s0, 8), jb = std::min(s1, ((c->nlat + 7) / 8 - 2) * 8);
       if (c->h4_stream && c->nlon >= 64 && jb - ja >= 32 && (long long)(jb - ja) * c->nlon * H.n >= (1 << 20)) {
-        constexpr int R = 64;
         H.ja = ja; H.jb = jb;
         const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+        const int R = h4s_rows(c, nstrips, jb - ja, H.n);
         const int nwarps = nstrips * ((jb - ja + R - 1) / R);
         if (s0 < ja) { H.row0 = s0; H.row1 = ja; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((ja - s0 + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
         if (jb < s1) { H.row0 = jb; H.row1 = s1; QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * ((s1 - jb + 7) / 8), c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H); }
-        QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        if (R == 16) QD_KGN(c, nms[nn], k_hyper4_stream<16>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        else if (R == 32) QD_KGN(c, nms[nn], k_hyper4_stream<32>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+        else QD_KGN(c, nms[nn], k_hyper4_stream<64>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
         continue;
       }
 #endif
@@ -916,13 +930,15 @@ static int launch_hyper4(qd_ctx* c, QdHyper4Args& H) {
   if (blocks32 >= 2 * 148 && c->nlat >= 96 && c->nlon >= 64 && c->h4_stream) {
     // large grid: warp-streaming kernel on the rows with a centred dependency cone, tile kernel on the
     // tile rows that touch a pole (tile row 0 and the last two)
-    constexpr int R = 64;
     H.ja = 8; H.jb = (ntj8 - 2) * 8;
     const int nstrips = (c->nlon + QD_H4S_COLS - 1) / QD_H4S_COLS;
+    const int R = h4s_rows(c, nstrips, H.jb - H.ja, H.n);
     const int nwarps = nstrips * ((H.jb - H.ja + R - 1) / R);
     H.tj_lo = 1; H.tj_skip = ntj8 - 3;
     QD_KGN(c, nm8[nn], k_hyper4_tile<8>, dim3(tiles_i * 3, c->batch, H.n), dim3(QD_H4_NX, QD_H4_NY), c->geo, H);
-    QD_KGN(c, nms[nn], k_hyper4_stream<R>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+    if (R == 16) QD_KGN(c, nms[nn], k_hyper4_stream<16>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+    else if (R == 32) QD_KGN(c, nms[nn], k_hyper4_stream<32>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
+    else QD_KGN(c, nms[nn], k_hyper4_stream<64>, dim3((nwarps + QD_H4S_WARPS - 1) / QD_H4S_WARPS, c->batch, H.n), dim3(32 * QD_H4S_WARPS), c->geo, H);
     return QD_OK;
   }
 #endif

@@ -345,7 +345,7 @@ __device__ __forceinline__ bool qd_h4s_chunk(const QdGeo& g, const QdHyper4Args&
 #endif
 template <int R>
 __global__ void __launch_bounds__(32 * QD_H4S_WARPS, QD_H4S_MINB) k_hyper4_stream(QdGeo g, QdHyper4Args A) {
-  static_assert(R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
+  static_assert(R == 16 || R == 32 || R == 64, "k4 rows are staged in one or two registers per lane");
   const int b = blockIdx.y;
   if (A.ocean && qd_sub_done(g, b, A.sc)) return;
   const int lane = threadIdx.x & 31;
