@@ -91,3 +91,22 @@ def test_latitude_bands_two_substeps_per_exchange(tmp_path):
         scale = max(float(np.max(np.abs(a[k]))), 1e-300)
         err = float(np.max(np.abs(a[k] - b[k]))) / scale
         assert err < 1e-10, (k, err)
+
+
+def test_latitude_bands_with_trimmed_pole_ranks(tmp_path):
+    """Unequal shares: the two pole ranks hand rows to the rank in between (qd_api.cu: band_rows_of; the default of 32
+    rows only applies to shares of >= 128 rows, so the override is used here)."""
+    one, many = str(tmp_path / "one.npz"), str(tmp_path / "w3.npz")
+    os.environ["QD_BAND_POLE_TRIM"] = "5"                # inherited by the spawned ranks
+    try:
+        _run(0, 1, 0, one)
+        port = 29700 + (os.getpid() % 1500) + 11
+        mp.spawn(_run, args=(3, port, many), nprocs=3, join=True)
+    finally:
+        os.environ.pop("QD_BAND_POLE_TRIM", None)
+    a, b = np.load(one), np.load(many)
+    assert int(b["err"]) == 0
+    for k in FIELDS:
+        scale = max(float(np.max(np.abs(a[k]))), 1e-300)
+        err = float(np.max(np.abs(a[k] - b[k]))) / scale
+        assert err < 1e-10, (k, err)
