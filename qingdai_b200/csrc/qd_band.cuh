@@ -11,11 +11,11 @@
 //
 // Transport: each rank owns one exchange buffer (cudaMalloc + cudaIpc handle; POSIX shared memory in the
 // host check build) that its peers map.  A sender WRITES its boundary rows / partial sums / histograms
-// straight into the receiver's inbox over NVLink and then raises an epoch flag there; the receiver spins
-// on its own flag and unpacks.  Everything is ordinary kernels on the step's stream (graph-capturable, no
-// host round trip, no NCCL on the data path).  Inboxes are double-buffered by epoch parity: a sender can
-// be at most one collective ahead of a receiver.  Spins are bounded and raise an error word instead of
-// hanging the GPU.
+// straight into the receiver's inbox over NVLink as flagged 16-byte lines (value + arrival flag in one posted
+// store, see qd_ll_store below); the receiver polls its own inbox and takes each value as it lands.
+// Everything is ordinary kernels on the step's stream (graph-capturable, no host round trip, no NCCL on the
+// data path).  Inboxes are double-buffered by epoch parity: a sender can be at most one collective ahead of
+// a receiver.  Spins are bounded and raise an error word instead of hanging the GPU.
 #pragma once
 #include "qd_ops.cuh"
 #if QD_EMU
