@@ -507,7 +507,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short sub-records of the other workloads")
     ap.add_argument("--all-kernels", action="store_true", help="list every kernel in roofline.top_kernels")
-    ap.add_argument("--halo", type=int, default=16, help="latitude bands: halo rows per exchange")
+    ap.add_argument("--halo", type=int, default=0, help="latitude bands: halo rows per exchange (0 = 8 rows on 2 GPUs, 16 on more: measured, profiles/README.md)")
     ap.add_argument("--streams", type=int, default=0, help="ensemble workloads: member groups (CUDA streams) per GPU, 0 = automatic")
     ap.add_argument("--members", type=int, default=0, help="ensemble workloads: total members instead of 64 (tuning runs)")
     ap.add_argument("--replicas", action="store_true", help="hires at N>1: independent replicas instead of latitude bands")
@@ -516,6 +516,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.halo <= 0:
+        # fewer halo rows = less redundant compute next to a cut but more exchanges: with two ranks (720 own rows each at
+        # 1441x2880) 8 rows win (1.358 vs 1.384 ms/step); with 4 / 8 ranks the per-rank compute is too small to pay for
+        # the extra exchanges
+        args.halo = 8 if max(world, args.gpus) == 2 else 16
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
